@@ -1,0 +1,169 @@
+/* b200sd -- C-ABI of the Blackwell-native Stable Diffusion hot path.
+ *
+ * Drop-in boundary.  The reference (apple/ml-stable-diffusion) is pure Python; its device
+ * boundary is `CoreMLModel.__call__(**np.ndarray) -> dict` (python_coreml_stable_diffusion/
+ * coreml_model.py:118-120) which hands the whole UNet / VAE graph to Core ML.  The
+ * replacement for that opaque runtime is this library: the graph of the reference network
+ * definitions (unet.py:975-1048 etc.) is issued op-by-op through the entry points below by
+ * the Python host mirror (`b200sd.model.B200Model`, same `expected_inputs` / `__call__`
+ * contract), captured once into a CUDA graph and replayed per denoising step.
+ *
+ * Conventions
+ *   - plain pointers + sizes, no torch types; all pointers are DEVICE pointers unless noted;
+ *   - activations are fp16, channels-last: images NHWC, token matrices [rows, channels];
+ *   - weights fp16, bias / statistics / scheduler scalars fp32;
+ *   - every function returns 0 on success, non-zero on failure with the message available
+ *     from b200sd_last_error(); nothing falls back to a CPU path;
+ *   - `stream` is a cudaStream_t passed as void*.
+ *
+ * Each entry point cites the reference code it replaces.
+ */
+#ifndef B200SD_H
+#define B200SD_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* b200sd_last_error(void);
+int b200sd_version(void);
+/* number of kernels launched by this library since load (bench.py's gpu_launches) */
+uint64_t b200sd_launch_count(void);
+
+/* ---- tensor-core GEMM / implicit-GEMM convolution --------------------------------------
+ * out[M, N] = epilogue( A[M, K] * W[N, K]^T ),  fp16 operands, fp32 accumulate (tcgen05.mma
+ * kind::f16, accumulators in TMEM, operands TMA-staged with 128B swizzle).
+ *
+ *   mode 0  "linear"  : every nn.Conv2d(k=1) of the reference (unet.py:74-84 q/k/v/out,
+ *                       :533-551 proj_in/out, :613 GEGLU proj, :601 FF out, :464 conv_shortcut,
+ *                       :642-658 TimestepEmbedding).  A = a0 [M, c0] (optionally ++ a1 [M, c1]
+ *                       along K: the concat-free form of torch.cat, unet.py:215,270).
+ *   mode 1  "conv3x3" : 3x3 pad-1 convolution as an im2col-free implicit GEMM
+ *                       (ResnetBlock2D.conv1/conv2 unet.py:435-456, conv_in/out :853,970,
+ *                       Downsample2D :507 with stride 2, Upsample2D conv :499).  A = NHWC image
+ *                       a0 [n_img, h, w, c0] (optionally ++ a1 with c1 channels); the 9 taps are
+ *                       9 shifted TMA boxes with hardware zero fill at the borders.
+ *                       W is [N, 9 * (c0 + c1)] with k = (ky*3 + kx) * C + c  (OHWI).
+ *   epilogue: + bias[(row / bias_rows) * N + col] (bias_rows = rows sharing one bias vector;
+ *             0 = one vector for all rows; h*w adds the per-image time embedding, unet.py:476-478)
+ *             ; GEGLU a*gelu_erf(g) on interleaved column pairs (unet.py:616-617), output N/2 cols
+ *             ; + residual[row, col] (unet.py:484-487, :563, :587-589)
+ *             ; store fp16 or fp32.
+ *   split_k > 1 accumulates fp32 partials in `workspace` and finishes with a reduce kernel.
+ */
+typedef struct {
+    int32_t mode;          /* 0 linear, 1 conv3x3 */
+    int32_t m;             /* rows (linear); ignored for conv (= n_img*h_out*w_out) */
+    int32_t n;             /* output channels (before GEGLU halving) */
+    int32_t c0, c1;        /* input channels from a0 / a1 (c1 = 0: single source) */
+    int32_t n_img, h, w;   /* conv: INPUT image geometry */
+    int32_t stride;        /* conv: 1 or 2 */
+    int32_t geglu;         /* 1: GEGLU epilogue */
+    int32_t out_f32;       /* 1: store fp32 */
+    int32_t bias_rows;     /* see above */
+    int32_t split_k;       /* 0 = auto */
+    int32_t block_n;       /* 0 = auto; else multiple of 16 in [16, 256] */
+    const void* a0;
+    const void* a1;
+    const void* wgt;
+    const float* bias;     /* or NULL */
+    const void* residual;  /* fp16 [M, N_out] or NULL */
+    void* out;             /* [M, N_out] fp16 / fp32 */
+    float* workspace;      /* split-K scratch (may be NULL when split_k == 1) */
+    size_t workspace_bytes;
+} b200sd_gemm_args;
+
+int b200sd_gemm(const b200sd_gemm_args* args, void* stream);
+/* bytes of fp32 scratch b200sd_gemm would need for these args (0 if no split-K) */
+size_t b200sd_gemm_workspace_bytes(const b200sd_gemm_args* args);
+
+/* small-M linear on CUDA cores (weight-bandwidth bound): out[m, n] = act_in(x[m, :]) . W[n, :] + b[n]
+ * for the time-embedding MLPs (unet.py:665-682) and the per-ResNet time_emb_proj(silu(emb))
+ * (unet.py:442, 476-478).  x, out fp32; W fp16 [n, k]; act_in: 0 none, 1 SiLU on the input;
+ * act_out: 0 none, 1 SiLU on the output; add: fp32 [n] added to every row (conv bias fold) or NULL. */
+int b200sd_linear_small(const float* x, const void* wgt, const float* bias, const float* add, float* out,
+                        int32_t m, int32_t n, int32_t k, int32_t act_in, int32_t act_out, void* stream);
+
+/* sinusoidal timestep embedding (unet.py:703-728; flip_sin_to_cos: cos first): out fp32 [m, dim] */
+int b200sd_timestep_embedding(const float* timesteps, float* out, int32_t m, int32_t dim,
+                              int32_t flip_sin_to_cos, float freq_shift, void* stream);
+
+/* ---- normalisation ------------------------------------------------------------------------
+ * GroupNorm (torch.nn.GroupNorm, unet.py:430,448,528,966) on NHWC fp16, fp32 statistics, optional
+ * fused SiLU (unet.py:472-473,480-481), reading one or two channel-concatenated sources and writing
+ * the concatenated normalised tensor (the torch.cat of unet.py:215,270 never materialises raw).
+ * Two launches: partial (mean, M2) per (image, group, chunk), then apply (Chan merge in prologue). */
+int b200sd_group_norm(const void* x0, const void* x1, int32_t c0, int32_t c1, int32_t n_img, int32_t hw,
+                      int32_t groups, float eps, const float* gamma, const float* beta, int32_t silu,
+                      void* out, float* stats_ws, size_t stats_ws_bytes, void* stream);
+size_t b200sd_group_norm_workspace_bytes(int32_t n_img, int32_t hw, int32_t c, int32_t groups);
+
+/* LayerNorm over channels of a token matrix [rows, c] (LayerNormANE, layer_norm.py:51-80, in the
+ * x_hat*w+b convention of the checkpoint, cf. unet.py:132-138). */
+int b200sd_layer_norm(const void* x, const float* gamma, const float* beta, void* out, int32_t rows,
+                      int32_t c, float eps, void* stream);
+
+/* ---- attention ------------------------------------------------------------------------------
+ * softmax(q k^T / sqrt(d) [+ mask]) v per (batch, head): attention.py:24-168 (all three
+ * AttentionImplementations compute this function) via Einsum (unet.py:45-59).
+ * q [batch, sq, ldq] / k,v [batch, sk, ldk] fp16 token-major with head h in columns
+ * [h*d, (h+1)*d) of the given base pointers; out [batch, sq, ldo].  d must be 64.
+ * mask: optional fp32 additive [batch, sk] (unet.py:99-114) or NULL.
+ * impl: 0 ORIGINAL, 1 SPLIT_EINSUM, 2 SPLIT_EINSUM_V2 (tile policy only; same result). */
+int b200sd_attention(const void* q, const void* k, const void* v, void* out, const float* mask,
+                     int32_t batch, int32_t heads, int32_t sq, int32_t sk, int32_t d,
+                     int32_t ldq, int32_t ldk, int32_t ldv, int32_t ldo, float scale, int32_t impl,
+                     void* stream);
+
+/* ---- layout / elementwise ----------------------------------------------------------------- */
+/* NCHW (fp16 or fp32) -> NHWC fp16 with channel padding to c_pad (zeros) */
+int b200sd_nchw_to_nhwc(const void* in, int32_t in_f32, void* out, int32_t n, int32_t c, int32_t h,
+                        int32_t w, int32_t c_pad, void* stream);
+/* NHWC fp32/fp16 [n,h,w,c_pad] -> NCHW fp32 [n,c,h,w] (first c channels) */
+int b200sd_nhwc_to_nchw_f32(const void* in, int32_t in_f32, float* out, int32_t n, int32_t c, int32_t h,
+                            int32_t w, int32_t c_pad, void* stream);
+/* nearest x2 upsample NHWC fp16 (F.interpolate, unet.py:499) */
+int b200sd_upsample2x(const void* in, void* out, int32_t n, int32_t h, int32_t w, int32_t c, void* stream);
+/* out = a + b (fp16; ControlNet residual injection unet.py:1009-1022) */
+int b200sd_add(const void* a, const void* b, void* out, size_t numel, void* stream);
+/* BC1S fp16/fp32 context (B, D, 1, S) -> token-major fp16 [B*S, D] */
+int b200sd_ctx_to_tokens(const void* in, int32_t in_f32, void* out, int32_t b, int32_t d, int32_t s,
+                         void* stream);
+
+/* ---- CFG + scheduler step (single fused elementwise kernel) -------------------------------
+ * eps = eps_u + g (eps_c - eps_u)           (pipeline.py:559-562; performGuidance
+ *                                            StableDiffusionPipeline.swift:469-483)
+ * then one scheduler update written as a linear combination
+ *     x_prev = cx * x + ce * eps' + sum_i ch[i] * hist[i]
+ * whose fp32 coefficients the host derives per step for DDIM (eta=0), DPM-Solver++(2M) and
+ * PNDM/PLMS (Scheduler.swift:218-343, DPMSolverMultistepScheduler.swift:135-244); `hist` holds
+ * past eps (PNDM) or past x0 (DPM).  kind selects what is pushed into the history ring:
+ * 0 nothing (DDIM), 1 eps (PNDM), 2 x0 = (x - sigma_t eps)/alpha_t (DPM).
+ * noise_pred: fp32 NCHW [2*n, c, h, w] (uncond batch first); latents fp32 [n, c, h, w] updated in
+ * place; `unet_in` (fp16 NHWC [2n, h, w, c_pad], may be NULL) receives the duplicated next input. */
+typedef struct {
+    float guidance;
+    float cx, ce;
+    float ch[4];
+    float x0_cx, x0_ce;      /* x0 = x0_cx * x + x0_ce * eps  (kind 2 history / denoised output) */
+    int32_t n_hist;          /* history entries used this step */
+    int32_t push_kind;       /* 0 none, 1 eps, 2 x0 */
+    int32_t hist_head;       /* ring slot to overwrite when pushing */
+} b200sd_step_coeffs;
+
+int b200sd_cfg_scheduler_step(const float* noise_pred, float* latents, float* hist /* [4][numel] */,
+                              float* denoised /* x0 out or NULL */, void* unet_in, int32_t c_pad,
+                              int32_t n, int32_t c, int32_t h, int32_t w,
+                              const b200sd_step_coeffs* coeffs /* host */, void* stream);
+
+/* VAE post-process: clip(x/2+0.5,0,1) (pipeline.py:317) NHWC fp16/32 -> NHWC fp32 [n,h,w,3] and/or u8 */
+int b200sd_image_postprocess(const void* in, int32_t in_f32, int32_t c_pad, float* out_f32, uint8_t* out_u8,
+                             int32_t n, int32_t h, int32_t w, int32_t c, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SD_H */

@@ -1,0 +1,192 @@
+"""Model configurations and parameter schemas for the b200sd hot path.
+
+The configs mirror the keyword arguments of the reference constructors
+(``python_coreml_stable_diffusion/unet.py:800-832`` ``UNet2DConditionModel.__init__``;
+``controlnet.py:52-70``) and the diffusers ``AutoencoderKL`` config read by
+``torch2coreml.py:548-642``.  Parameter names are the diffusers state-dict keys the reference
+loads (``unet.py:121-146`` hooks).
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+
+import torch
+
+SD21_BASE_UNET = dict(
+    sample_size=64, in_channels=4, out_channels=4,
+    down_block_types=("CrossAttnDownBlock2D", "CrossAttnDownBlock2D", "CrossAttnDownBlock2D", "DownBlock2D"),
+    up_block_types=("UpBlock2D", "CrossAttnUpBlock2D", "CrossAttnUpBlock2D", "CrossAttnUpBlock2D"),
+    block_out_channels=(320, 640, 1280, 1280), layers_per_block=2,
+    attention_head_dim=(5, 10, 20, 20),  # == number of heads (unet.py:194-197)
+    cross_attention_dim=1024, norm_num_groups=32, norm_eps=1e-5,
+    flip_sin_to_cos=True, freq_shift=0, transformer_layers_per_block=1,
+)
+
+SDXL_BASE_UNET = dict(
+    sample_size=128, in_channels=4, out_channels=4,
+    down_block_types=("DownBlock2D", "CrossAttnDownBlock2D", "CrossAttnDownBlock2D"),
+    up_block_types=("CrossAttnUpBlock2D", "CrossAttnUpBlock2D", "UpBlock2D"),
+    block_out_channels=(320, 640, 1280), layers_per_block=2,
+    attention_head_dim=(5, 10, 20), cross_attention_dim=2048,
+    norm_num_groups=32, norm_eps=1e-5, flip_sin_to_cos=True, freq_shift=0,
+    transformer_layers_per_block=(1, 2, 10),
+    addition_embed_type="text_time", addition_time_embed_dim=256,
+    projection_class_embeddings_input_dim=2816,
+)
+
+# small config for fast CPU/GPU parity tests (same topology, d_head = 64)
+TINY_UNET = dict(
+    sample_size=16, in_channels=4, out_channels=4,
+    down_block_types=("CrossAttnDownBlock2D", "CrossAttnDownBlock2D", "DownBlock2D"),
+    up_block_types=("UpBlock2D", "CrossAttnUpBlock2D", "CrossAttnUpBlock2D"),
+    block_out_channels=(64, 128, 128), layers_per_block=1,
+    attention_head_dim=(1, 2, 2), cross_attention_dim=96, norm_num_groups=32, norm_eps=1e-5,
+    flip_sin_to_cos=True, freq_shift=0, transformer_layers_per_block=1,
+)
+
+SD_VAE = dict(latent_channels=4, out_channels=3, block_out_channels=(128, 256, 512, 512),
+              layers_per_block=2, norm_num_groups=32, scaling_factor=0.18215)
+
+TINY_VAE = dict(latent_channels=4, out_channels=3, block_out_channels=(64, 64, 128),
+                layers_per_block=1, norm_num_groups=32, scaling_factor=0.18215)
+
+
+def _as_list(v, n):
+    return list(v) if isinstance(v, (list, tuple)) else [v] * n
+
+
+def _conv(sh, name, co, ci, k, bias=True):
+    sh[name + ".weight"] = (co, ci, k, k)
+    if bias:
+        sh[name + ".bias"] = (co,)
+
+
+def _norm(sh, name, c):
+    sh[name + ".weight"] = (c,)
+    sh[name + ".bias"] = (c,)
+
+
+def _resnet(sh, p, ci, co, temb):
+    _norm(sh, p + ".norm1", ci)
+    _conv(sh, p + ".conv1", co, ci, 3)
+    if temb:
+        _conv(sh, p + ".time_emb_proj", co, temb, 1)
+    _norm(sh, p + ".norm2", co)
+    _conv(sh, p + ".conv2", co, co, 3)
+    if ci != co:
+        _conv(sh, p + ".conv_shortcut", co, ci, 1)
+
+
+def _transformer(sh, p, c, ctx_dim, depth):
+    _norm(sh, p + ".norm", c)
+    _conv(sh, p + ".proj_in", c, c, 1)
+    for d in range(depth):
+        b = f"{p}.transformer_blocks.{d}"
+        for a, kd in (("attn1", c), ("attn2", ctx_dim)):
+            _conv(sh, f"{b}.{a}.to_q", c, c, 1, bias=False)
+            _conv(sh, f"{b}.{a}.to_k", c, kd, 1, bias=False)
+            _conv(sh, f"{b}.{a}.to_v", c, kd, 1, bias=False)
+            _conv(sh, f"{b}.{a}.to_out.0", c, c, 1)
+        _conv(sh, f"{b}.ff.net.0.proj", 8 * c, c, 1)
+        _conv(sh, f"{b}.ff.net.2", c, 4 * c, 1)
+        for n in ("norm1", "norm2", "norm3"):
+            _norm(sh, f"{b}.{n}", c)
+    _conv(sh, p + ".proj_out", c, c, 1)
+
+
+def unet_param_shapes(cfg) -> "OrderedDict[str, tuple]":
+    """name -> shape for every parameter of the reference UNet built from ``cfg``."""
+    sh = OrderedDict()
+    boc = list(cfg["block_out_channels"])
+    nb = len(boc)
+    lpb = cfg.get("layers_per_block", 2)
+    depth = _as_list(cfg.get("transformer_layers_per_block", 1), nb)
+    ctx = cfg["cross_attention_dim"]
+    temb = boc[0] * 4
+    _conv(sh, "conv_in", boc[0], cfg["in_channels"], 3)
+    _conv(sh, "time_embedding.linear_1", temb, boc[0], 1)
+    _conv(sh, "time_embedding.linear_2", temb, temb, 1)
+    if cfg.get("addition_embed_type") == "text_time":
+        _conv(sh, "add_embedding.linear_1", temb, cfg["projection_class_embeddings_input_dim"], 1)
+        _conv(sh, "add_embedding.linear_2", temb, temb, 1)
+    out = boc[0]
+    for i, typ in enumerate(cfg["down_block_types"]):
+        inp, out = out, boc[i]
+        for j in range(lpb):
+            _resnet(sh, f"down_blocks.{i}.resnets.{j}", inp if j == 0 else out, out, temb)
+            if typ == "CrossAttnDownBlock2D":
+                _transformer(sh, f"down_blocks.{i}.attentions.{j}", out, ctx, depth[i])
+        if i != nb - 1:
+            _conv(sh, f"down_blocks.{i}.downsamplers.0.conv", out, out, 3)
+    _resnet(sh, "mid_block.resnets.0", boc[-1], boc[-1], temb)
+    _transformer(sh, "mid_block.attentions.0", boc[-1], ctx, depth[-1])
+    _resnet(sh, "mid_block.resnets.1", boc[-1], boc[-1], temb)
+    rboc = boc[::-1]
+    rdepth = depth[::-1]
+    out = rboc[0]
+    for i, typ in enumerate(cfg["up_block_types"]):
+        prev, out = out, rboc[i]
+        inp = rboc[min(i + 1, nb - 1)]
+        for j in range(lpb + 1):
+            skip = inp if j == lpb else out
+            rin = prev if j == 0 else out
+            _resnet(sh, f"up_blocks.{i}.resnets.{j}", rin + skip, out, temb)
+            if typ == "CrossAttnUpBlock2D":
+                _transformer(sh, f"up_blocks.{i}.attentions.{j}", out, ctx, rdepth[i])
+        if i != nb - 1:
+            _conv(sh, f"up_blocks.{i}.upsamplers.0.conv", out, out, 3)
+    _norm(sh, "conv_norm_out", boc[0])
+    _conv(sh, "conv_out", cfg["out_channels"], boc[0], 3)
+    return sh
+
+
+def vae_decoder_param_shapes(cfg) -> "OrderedDict[str, tuple]":
+    """diffusers ``AutoencoderKL`` decoder + post_quant_conv keys."""
+    sh = OrderedDict()
+    boc = list(cfg["block_out_channels"])
+    lpb = cfg.get("layers_per_block", 2)
+    lc = cfg.get("latent_channels", 4)
+    top = boc[-1]
+    _conv(sh, "post_quant_conv", lc, lc, 1)
+    _conv(sh, "decoder.conv_in", top, lc, 3)
+    _resnet(sh, "decoder.mid_block.resnets.0", top, top, 0)
+    a = "decoder.mid_block.attentions.0"
+    _norm(sh, a + ".group_norm", top)
+    for n in ("to_q", "to_k", "to_v", "to_out.0"):
+        _conv(sh, f"{a}.{n}", top, top, 1)
+    _resnet(sh, "decoder.mid_block.resnets.1", top, top, 0)
+    rboc = boc[::-1]
+    out = rboc[0]
+    for i in range(len(boc)):
+        prev, out = out, rboc[i]
+        for j in range(lpb + 1):
+            _resnet(sh, f"decoder.up_blocks.{i}.resnets.{j}", prev if j == 0 else out, out, 0)
+        if i != len(boc) - 1:
+            _conv(sh, f"decoder.up_blocks.{i}.upsamplers.0.conv", out, out, 3)
+    _norm(sh, "decoder.conv_norm_out", boc[0])
+    _conv(sh, "decoder.conv_out", cfg.get("out_channels", 3), boc[0], 3)
+    return sh
+
+
+def random_state_dict(shapes, seed=0, dtype=torch.float32):
+    """Deterministic random-init weights with torch's default conv statistics
+    (U(-1/sqrt(fan_in), 1/sqrt(fan_in)) for weights and biases) and *non-trivial* norm affines
+    (w = 1 + 0.1 n, b = 0.1 n) so that parity tests exercise every term.  There is no network
+    for real checkpoints; BASELINE.json asks for random-init weights of the named architecture."""
+    g = torch.Generator().manual_seed(seed)
+    sd = OrderedDict()
+    fan = {}
+    for name, shp in shapes.items():
+        if len(shp) == 4:
+            fan[name.rsplit(".", 1)[0]] = shp[1] * shp[2] * shp[3]
+    for name, shp in shapes.items():
+        mod = name.rsplit(".", 1)[0]
+        if mod in fan:
+            b = fan[mod] ** -0.5
+            t = (torch.rand(shp, generator=g) * 2 - 1) * b
+        elif name.endswith(".weight"):
+            t = 1.0 + 0.1 * torch.randn(shp, generator=g)
+        else:
+            t = 0.1 * torch.randn(shp, generator=g)
+        sd[name] = t.to(dtype)
+    return sd

@@ -1,0 +1,322 @@
+// b200sd -- flash-style attention for sm_100a: S = Q K^T and O += P V on tcgen05 tensor cores
+// (accumulators in TMEM), Q/K/V tiles staged by TMA (SWIZZLE_128B), online softmax (exp2 domain)
+// in registers, P handed back to the tensor core through shared memory.
+//
+// Replaces attention.original / split_einsum / split_einsum_v2 of the reference
+// (python_coreml_stable_diffusion/attention.py:24-168, dispatched by Einsum unet.py:45-59): the
+// three variants are one function, softmax(q^T k / sqrt(d) + mask) v per (batch, head); the
+// (B, heads, Sq, Sk) score tensor the reference materialises (671 MB at S=4096) never leaves the SM.
+//
+// CTA = 128 queries x 1 head; warp 0 TMA producer, warp 1 MMA issuer, warps 2..5 softmax (one query
+// row per thread).  256 TMEM columns (S 128 + O_step 64) so two CTAs share an SM and overlap one
+// CTA's softmax with the other's MMAs.
+#include "common.cuh"
+#include "../../include/b200sd.h"
+
+namespace b200sd {
+
+extern void count_launch(int n);
+
+static constexpr int kQ = 128;   // queries per CTA
+static constexpr int kKV = 128;  // keys per step
+static constexpr int kD = 64;    // head dim
+static constexpr int kAttnThreads = 192;
+static constexpr int kTileBytes = 128 * 64 * 2;  // 16 KiB: one [128 x 64] fp16 tile
+static constexpr int kKvStages = 2;
+
+struct __align__(64) AttnParams {
+    CUtensorMap tmQ, tmK, tmV;
+    __half* out;
+    const float* mask;  // [batch, sk] additive or null
+    int sq, sk, ldo;
+    float scale_log2;  // scale * log2(e)
+    int* error_flag;
+};
+
+// smem layout (1024-aligned): Q | P (2 x 16K, K-chunks of 64 keys) | K[2] | V[2] | barriers
+static constexpr int kSmemQ = 0;
+static constexpr int kSmemP = kTileBytes;
+static constexpr int kSmemK = kSmemP + 2 * kTileBytes;
+static constexpr int kSmemV = kSmemK + kKvStages * kTileBytes;
+static constexpr int kSmemBar = kSmemV + kKvStages * kTileBytes;
+static constexpr int kAttnSmemBytes = kSmemBar + 128;
+
+__global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid_constant__ AttnParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSmemBar);
+    uint64_t* q_full = bars + 0;
+    uint64_t* kv_full = bars + 1;   // [2]
+    uint64_t* kv_empty = bars + 3;  // [2]
+    uint64_t* s_full = bars + 5;
+    uint64_t* s_empty = bars + 6;
+    uint64_t* p_full = bars + 7;
+    uint64_t* o_full = bars + 8;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 9);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * kQ;
+    const int head = blockIdx.y;
+    const int batch = blockIdx.z;
+    const int n_kv = (p.sk + kKV - 1) / kKV;
+
+    if (threadIdx.x == 0) {
+        if ((smem_u32(smem) & 1023u) != 0) atomicExch(p.error_flag, 1);  // swizzle needs 1024 B alignment
+        prefetch_tmap(&p.tmQ);
+        prefetch_tmap(&p.tmK);
+        prefetch_tmap(&p.tmV);
+        mbar_init(q_full, 1);
+        for (int s = 0; s < kKvStages; ++s) {
+            mbar_init(&kv_full[s], 1);
+            mbar_init(&kv_empty[s], 1);
+        }
+        mbar_init(s_full, 1);
+        mbar_init(s_empty, 128);
+        mbar_init(p_full, 128);
+        mbar_init(o_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_ptr, 256);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+    const uint32_t tmem_s = tmem_base;        // 128 columns
+    const uint32_t tmem_o = tmem_base + 128;  // 64 columns
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(q_full, kTileBytes);
+            tma_load_3d(smem + kSmemQ, &p.tmQ, q_full, head * kD, q0, batch, kEvictFirst);
+            for (int j = 0; j < n_kv; ++j) {
+                const int st = j % kKvStages;
+                const uint32_t ph = (j / kKvStages) & 1;
+                mbar_wait(&kv_empty[st], ph ^ 1);
+                mbar_expect_tx(&kv_full[st], 2 * kTileBytes);
+                tma_load_3d(smem + kSmemK + st * kTileBytes, &p.tmK, &kv_full[st], head * kD, j * kKV, batch,
+                            kEvictLast);
+                tma_load_3d(smem + kSmemV + st * kTileBytes, &p.tmV, &kv_full[st], head * kD, j * kKV, batch,
+                            kEvictLast);
+            }
+        }
+    } else if (warp == 1) {
+        // S = Q K^T : A = Q (K-major), B = K tile (K-major), M=128 N=128 K=64
+        const uint32_t idesc_s = make_idesc_f16(128, kKV, 0, 0);
+        // O_step = P V : A = P (K-major, two 64-key chunks), B = V tile [keys][d] = MN-major, N=64 K=128
+        const uint32_t idesc_o = make_idesc_f16(128, kD, 0, 1);
+        const uint32_t q_addr = smem_u32(smem + kSmemQ);
+        const uint32_t p_addr = smem_u32(smem + kSmemP);
+        auto issue_s = [&](int j) {
+            const int st = j % kKvStages;
+            mbar_wait(&kv_full[st], (j / kKvStages) & 1);
+            if (j > 0) mbar_wait(s_empty, (j - 1) & 1);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint64_t adesc = make_smem_desc_sw128(q_addr, 1024, 0);
+                const uint64_t bdesc = make_smem_desc_sw128(smem_u32(smem + kSmemK + st * kTileBytes), 1024, 0);
+#pragma unroll
+                for (int k = 0; k < kD / 16; ++k)
+                    umma_f16_ss(tmem_s, adesc + 2 * k, bdesc + 2 * k, idesc_s, k > 0 ? 1u : 0u);
+                umma_commit(s_full);
+            }
+            __syncwarp();
+        };
+        mbar_wait(q_full, 0);
+        issue_s(0);
+        for (int j = 0; j < n_kv; ++j) {
+            if (j + 1 < n_kv) issue_s(j + 1);
+            const int st = j % kKvStages;
+            mbar_wait(p_full, j & 1);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t v_addr = smem_u32(smem + kSmemV + st * kTileBytes);
+#pragma unroll
+                for (int k = 0; k < kKV / 16; ++k) {
+                    // A: chunk (k / 4) of P, +32 B per 16 keys inside the chunk's 128 B rows
+                    const uint64_t adesc =
+                        make_smem_desc_sw128(p_addr + (k >> 2) * kTileBytes, 1024, 0) + 2 * (k & 3);
+                    // B: 16 keys = 16 rows of 128 B = 2048 B further down the MN-major tile
+                    const uint64_t bdesc = make_smem_desc_sw128(v_addr + k * 2048, 1024, kKV * 128);
+                    umma_f16_ss(tmem_o, adesc, bdesc, idesc_o, k > 0 ? 1u : 0u);
+                }
+                umma_commit(o_full);
+                umma_commit(&kv_empty[st]);
+            }
+            __syncwarp();
+        }
+    } else {
+        const int lane_group = warp & 3;
+        const int row = lane_group * 32 + lane;
+        const uint32_t lane_addr = static_cast<uint32_t>(lane_group * 32) << 16;
+        float o_acc[kD];
+#pragma unroll
+        for (int i = 0; i < kD; ++i) o_acc[i] = 0.f;
+        float m_run = -INFINITY, l_run = 0.f;
+        const float* mask_row = p.mask ? p.mask + static_cast<size_t>(batch) * p.sk : nullptr;
+        uint8_t* p_row = smem + kSmemP + row * 128;
+        const int sw = row & 7;
+
+        for (int j = 0; j < n_kv; ++j) {
+            const int kvalid = min(kKV, p.sk - j * kKV);  // >= 1
+            mbar_wait(s_full, j & 1);
+            tc_fence_after();
+            // ---- pass 1: row maximum (log2 domain) ----
+            float m_tile = -INFINITY;
+#pragma unroll 1
+            for (int c = 0; c < kKV; c += 32) {
+                uint32_t v[32];
+                tmem_ld32(tmem_s + lane_addr + c, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    float s = __uint_as_float(v[i]) * p.scale_log2;
+                    if (mask_row && c + i < kvalid) s += mask_row[j * kKV + c + i] * 1.4426950408889634f;
+                    if (c + i < kvalid) m_tile = fmaxf(m_tile, s);
+                }
+            }
+            const float m_new = fmaxf(m_run, m_tile);
+            const float alpha = exp2f(m_run - m_new);  // 0 on the first tile
+            // ---- fold in the previous step's P V, then rescale to the new maximum ----
+            if (j > 0) {
+                mbar_wait(o_full, (j - 1) & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int c = 0; c < kD; c += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem_o + lane_addr + c, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) o_acc[c + i] = (o_acc[c + i] + __uint_as_float(v[i])) * alpha;
+                }
+            }
+            // ---- pass 2: P = exp2(s - m), row sum, fp16 P tile into swizzled smem ----
+            float l_tile = 0.f;
+#pragma unroll 1
+            for (int c = 0; c < kKV; c += 32) {
+                uint32_t v[32];
+                tmem_ld32(tmem_s + lane_addr + c, v);
+                tmem_ld_wait();
+                uint32_t pk[16];
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    float s0 = __uint_as_float(v[i]) * p.scale_log2;
+                    float s1 = __uint_as_float(v[i + 1]) * p.scale_log2;
+                    if (mask_row) {
+                        if (c + i < kvalid) s0 += mask_row[j * kKV + c + i] * 1.4426950408889634f;
+                        if (c + i + 1 < kvalid) s1 += mask_row[j * kKV + c + i + 1] * 1.4426950408889634f;
+                    }
+                    const float p0 = (c + i < kvalid) ? exp2f(s0 - m_new) : 0.f;
+                    const float p1 = (c + i + 1 < kvalid) ? exp2f(s1 - m_new) : 0.f;
+                    l_tile += p0 + p1;
+                    pk[i >> 1] = pack_half2(p0, p1);
+                }
+                // 32 keys = 64 B = four 16 B pieces; key c lives in chunk c/64, byte (c%64)*2
+                uint8_t* dst = p_row + (c >> 6) * kTileBytes;
+                const int piece0 = (c & 63) >> 3;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    uint4 val = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                    *reinterpret_cast<uint4*>(dst + (((piece0 + q) ^ sw) << 4)) = val;
+                }
+            }
+            l_run = l_run * alpha + l_tile;
+            m_run = m_new;
+            tc_fence_before();
+            mbar_arrive(s_empty);
+            fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+            mbar_arrive(p_full);
+        }
+        // ---- last P V and normalisation ----
+        mbar_wait(o_full, (n_kv - 1) & 1);
+        tc_fence_after();
+        const float inv_l = 1.0f / l_run;
+#pragma unroll
+        for (int c = 0; c < kD; c += 32) {
+            uint32_t v[32];
+            tmem_ld32(tmem_o + lane_addr + c, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o_acc[c + i] = (o_acc[c + i] + __uint_as_float(v[i])) * inv_l;
+        }
+        if (q0 + row < p.sq) {
+            __half* dst = p.out + (static_cast<size_t>(batch) * p.sq + q0 + row) * p.ldo + head * kD;
+#pragma unroll
+            for (int c = 0; c < kD; c += 8) {
+                uint4 val;
+                val.x = pack_half2(o_acc[c], o_acc[c + 1]);
+                val.y = pack_half2(o_acc[c + 2], o_acc[c + 3]);
+                val.z = pack_half2(o_acc[c + 4], o_acc[c + 5]);
+                val.w = pack_half2(o_acc[c + 6], o_acc[c + 7]);
+                *reinterpret_cast<uint4*>(dst + c) = val;
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 256);
+    }
+}
+
+static int* attn_error_flag() {
+    static int* flag = nullptr;
+    if (!flag) {
+        if (cudaMalloc(&flag, sizeof(int)) != cudaSuccess) return nullptr;
+        cudaMemset(flag, 0, sizeof(int));
+    }
+    return flag;
+}
+
+}  // namespace b200sd
+
+using namespace b200sd;
+
+extern "C" int b200sd_attention(const void* q, const void* k, const void* v, void* out, const float* mask,
+                                int32_t batch, int32_t heads, int32_t sq, int32_t sk, int32_t d, int32_t ldq,
+                                int32_t ldk, int32_t ldv, int32_t ldo, float scale, int32_t impl, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    B200SD_REQUIRE(q && k && v && out, "b200sd_attention: null pointer");
+    B200SD_REQUIRE(d == kD, "b200sd_attention: head dim %d not supported by this kernel (needs 64)", d);
+    B200SD_REQUIRE(impl >= 0 && impl <= 2, "b200sd_attention: unknown attention implementation %d", impl);
+    B200SD_REQUIRE(batch > 0 && heads > 0 && sq > 0 && sk > 0, "b200sd_attention: bad sizes");
+    B200SD_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0,
+                   "b200sd_attention: leading dimensions must be multiples of 8");
+    AttnParams p;
+    memset(&p, 0, sizeof(p));
+    const uint32_t es[3] = {1, 1, 1};
+    const uint32_t box[3] = {kD, 128, 1};
+    const void* ptrs[3] = {q, k, v};
+    const int lds[3] = {ldq, ldk, ldv};
+    const int seqs[3] = {sq, sk, sk};
+    CUtensorMap* maps[3] = {&p.tmQ, &p.tmK, &p.tmV};
+    for (int i = 0; i < 3; ++i) {
+        const uint64_t dims[3] = {static_cast<uint64_t>(heads) * kD, static_cast<uint64_t>(seqs[i]),
+                                  static_cast<uint64_t>(batch)};
+        const uint64_t str[2] = {static_cast<uint64_t>(lds[i]) * 2, static_cast<uint64_t>(lds[i]) * 2 * seqs[i]};
+        if (int rc = encode_tmap_f16(maps[i], ptrs[i], 3, dims, str, box, es)) return rc;
+    }
+    p.out = reinterpret_cast<__half*>(out);
+    p.mask = mask;
+    p.sq = sq;
+    p.sk = sk;
+    p.ldo = ldo;
+    p.scale_log2 = scale * 1.4426950408889634f;
+    p.error_flag = attn_error_flag();
+    B200SD_REQUIRE(p.error_flag != nullptr, "b200sd_attention: could not allocate the error flag");
+    static bool attr_set = false;
+    if (!attr_set) {
+        B200SD_CHECK_CUDA(
+            cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes));
+        attr_set = true;
+    }
+    dim3 grid((sq + kQ - 1) / kQ, heads, batch);
+    attention_kernel<<<grid, kAttnThreads, kAttnSmemBytes, stream>>>(p);
+    B200SD_CHECK_CUDA(cudaGetLastError());
+    count_launch(1);
+    return 0;
+}

@@ -1,0 +1,351 @@
+// b200sd -- layout conversion, small-M linear, timestep embedding, fused CFG + scheduler step and
+// image post-processing kernels (HBM / latency bound; vectorised, coalesced, one launch each).
+#include "common.cuh"
+#include "../../include/b200sd.h"
+
+#include <algorithm>
+
+namespace b200sd {
+
+extern void count_launch(int n);
+
+static inline int grid_for(size_t n, int threads) {
+    return static_cast<int>(std::min<size_t>((n + threads - 1) / threads, static_cast<size_t>(num_sms()) * 16));
+}
+
+// ---- NCHW -> NHWC fp16 (pad channels) -------------------------------------------------------
+template <typename T>
+__global__ void nchw_to_nhwc_kernel(const T* __restrict__ in, __half* __restrict__ out, int n, int c, int hw,
+                                    int c_pad) {
+    const size_t total = static_cast<size_t>(n) * hw * c_pad;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int ch = static_cast<int>(i % c_pad);
+        const size_t px = i / c_pad;
+        const int p = static_cast<int>(px % hw);
+        const int b = static_cast<int>(px / hw);
+        float v = 0.f;
+        if (ch < c) v = static_cast<float>(in[(static_cast<size_t>(b) * c + ch) * hw + p]);
+        out[i] = __float2half_rn(v);
+    }
+}
+
+template <typename T>
+__global__ void nhwc_to_nchw_f32_kernel(const T* __restrict__ in, float* __restrict__ out, int n, int c, int hw,
+                                        int c_pad) {
+    const size_t total = static_cast<size_t>(n) * c * hw;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int p = static_cast<int>(i % hw);
+        const size_t r = i / hw;
+        const int ch = static_cast<int>(r % c);
+        const int b = static_cast<int>(r / c);
+        out[i] = static_cast<float>(in[(static_cast<size_t>(b) * hw + p) * c_pad + ch]);
+    }
+}
+
+// ---- (B, D, 1, S) -> [B*S, D] fp16 (tiled transpose through shared memory) -------------------
+template <typename T>
+__global__ void ctx_to_tokens_kernel(const T* __restrict__ in, __half* __restrict__ out, int d, int s) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z;
+    const int d0 = blockIdx.y * 32, s0 = blockIdx.x * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int dd = d0 + r, ss = s0 + threadIdx.x;
+        if (dd < d && ss < s) tile[r][threadIdx.x] = static_cast<float>(in[(static_cast<size_t>(b) * d + dd) * s + ss]);
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int ss = s0 + r, dd = d0 + threadIdx.x;
+        if (dd < d && ss < s) out[(static_cast<size_t>(b) * s + ss) * d + dd] = __float2half_rn(tile[threadIdx.x][r]);
+    }
+}
+
+// ---- nearest x2 upsample, NHWC fp16, 16-byte vectors ------------------------------------------
+__global__ void upsample2x_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int n, int h, int w,
+                                  int vecs) {
+    const size_t total = static_cast<size_t>(n) * (2 * h) * (2 * w) * vecs;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int v = static_cast<int>(i % vecs);
+        size_t r = i / vecs;
+        const int ox = static_cast<int>(r % (2 * w));
+        r /= (2 * w);
+        const int oy = static_cast<int>(r % (2 * h));
+        const int b = static_cast<int>(r / (2 * h));
+        out[i] = in[((static_cast<size_t>(b) * h + (oy >> 1)) * w + (ox >> 1)) * vecs + v];
+    }
+}
+
+__global__ void add_kernel(const __half2* __restrict__ a, const __half2* __restrict__ b, __half2* __restrict__ out,
+                           size_t n2) {
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n2;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const float2 x = __half22float2(a[i]), y = __half22float2(b[i]);
+        out[i] = __floats2half2_rn(x.x + y.x, x.y + y.y);
+    }
+}
+
+// ---- small-M linear: one warp per output column, all M rows at once (M <= 8) -------------------
+template <int kM>
+__global__ void __launch_bounds__(256) linear_small_kernel(const float* __restrict__ x, const __half* __restrict__ w,
+                                                           const float* __restrict__ bias,
+                                                           const float* __restrict__ add, float* __restrict__ out,
+                                                           int m, int n, int k, int act_in, int act_out) {
+    const int col = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (col >= n) return;
+    const __half* wr = w + static_cast<size_t>(col) * k;
+    float acc[kM];
+#pragma unroll
+    for (int r = 0; r < kM; ++r) acc[r] = 0.f;
+    for (int kk = lane * 8; kk < k; kk += 32 * 8) {
+        const uint4 raw = *reinterpret_cast<const uint4*>(wr + kk);
+        const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+        float wf[8];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float2 t = __half22float2(h2[q]);
+            wf[2 * q] = t.x;
+            wf[2 * q + 1] = t.y;
+        }
+#pragma unroll
+        for (int r = 0; r < kM; ++r) {
+            if (r < m) {
+                const float* xr = x + static_cast<size_t>(r) * k + kk;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    float xv = xr[e];
+                    if (act_in) xv = silu_f(xv);
+                    acc[r] += xv * wf[e];
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < kM; ++r) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], o);
+    }
+    if (lane == 0) {
+        const float b = (bias ? bias[col] : 0.f) + (add ? add[col] : 0.f);
+        for (int r = 0; r < m && r < kM; ++r) {
+            float v = acc[r] + b;
+            if (act_out) v = silu_f(v);
+            out[static_cast<size_t>(r) * n + col] = v;
+        }
+    }
+}
+
+// ---- sinusoidal timestep embedding (unet.py:703-728) -------------------------------------------
+__global__ void timestep_embedding_kernel(const float* __restrict__ t, float* __restrict__ out, int m, int dim,
+                                          int flip, float freq_shift) {
+    const int half = dim / 2;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m * half) return;
+    const int r = i / half, j = i % half;
+    const float freq = expf(-logf(10000.0f) * static_cast<float>(j) / (static_cast<float>(half) - freq_shift));
+    const float ang = t[r] * freq;
+    const float s = sinf(ang), c = cosf(ang);
+    float* o = out + static_cast<size_t>(r) * dim;
+    if (flip) {
+        o[j] = c;
+        o[half + j] = s;
+    } else {
+        o[j] = s;
+        o[half + j] = c;
+    }
+}
+
+// ---- fused CFG + scheduler step ------------------------------------------------------------------
+// One thread per latent element (n*c*h*w, NCHW fp32).  See include/b200sd.h for the algebra.
+__global__ void cfg_step_kernel(const float* __restrict__ noise_pred, float* __restrict__ latents,
+                                float* __restrict__ hist, float* __restrict__ denoised, __half* __restrict__ unet_in,
+                                int c_pad, int n, int c, int hw, b200sd_step_coeffs k) {
+    const int numel = n * c * hw;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= numel) return;
+    const float eu = noise_pred[i];
+    const float ec = noise_pred[numel + i];
+    const float eps = eu + k.guidance * (ec - eu);
+    const float x = latents[i];
+    float xp = k.cx * x + k.ce * eps;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        if (j < k.n_hist) xp += k.ch[j] * hist[static_cast<size_t>(j) * numel + i];
+    const float x0 = k.x0_cx * x + k.x0_ce * eps;
+    if (k.push_kind == 1) hist[static_cast<size_t>(k.hist_head) * numel + i] = eps;
+    if (k.push_kind == 2) hist[static_cast<size_t>(k.hist_head) * numel + i] = x0;
+    if (denoised) denoised[i] = x0;
+    latents[i] = xp;
+    if (unet_in) {
+        // NCHW index -> NHWC, duplicated for the (uncond, cond) batch halves
+        const int p = i % hw;
+        const int ch = (i / hw) % c;
+        const int b = i / (hw * c);
+        const __half hv = __float2half_rn(xp);
+        unet_in[(static_cast<size_t>(b) * hw + p) * c_pad + ch] = hv;
+        unet_in[(static_cast<size_t>(n + b) * hw + p) * c_pad + ch] = hv;
+    }
+}
+
+// ---- image post-process: clip(x/2+0.5, 0, 1), NHWC(c_pad) -> NHWC(c) fp32 and/or u8 -------------
+template <typename T>
+__global__ void image_post_kernel(const T* __restrict__ in, int c_pad, float* __restrict__ of, uint8_t* __restrict__ ou,
+                                  size_t pixels, int c) {
+    const size_t total = pixels * c;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const size_t px = i / c;
+        const int ch = static_cast<int>(i % c);
+        float v = static_cast<float>(in[px * c_pad + ch]) * 0.5f + 0.5f;
+        v = fminf(fmaxf(v, 0.f), 1.f);
+        if (of) of[i] = v;
+        if (ou) ou[i] = static_cast<uint8_t>(__float2int_rn(v * 255.f));
+    }
+}
+
+}  // namespace b200sd
+
+using namespace b200sd;
+
+extern "C" int b200sd_nchw_to_nhwc(const void* in, int32_t in_f32, void* out, int32_t n, int32_t c, int32_t h,
+                                   int32_t w, int32_t c_pad, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    B200SD_REQUIRE(in && out && c_pad >= c, "b200sd_nchw_to_nhwc: bad arguments");
+    const size_t total = static_cast<size_t>(n) * h * w * c_pad;
+    if (in_f32)
+        nchw_to_nhwc_kernel<float><<<grid_for(total, 256), 256, 0, stream>>>(reinterpret_cast<const float*>(in),
+                                                                             reinterpret_cast<__half*>(out), n, c,
+                                                                             h * w, c_pad);
+    else
+        nchw_to_nhwc_kernel<__half><<<grid_for(total, 256), 256, 0, stream>>>(reinterpret_cast<const __half*>(in),
+                                                                              reinterpret_cast<__half*>(out), n, c,
+                                                                              h * w, c_pad);
+    B200SD_CHECK_CUDA(cudaGetLastError());
+    count_launch(1);
+    return 0;
+}
+
+extern "C" int b200sd_nhwc_to_nchw_f32(const void* in, int32_t in_f32, float* out, int32_t n, int32_t c, int32_t h,
+                                       int32_t w, int32_t c_pad, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    B200SD_REQUIRE(in && out && c_pad >= c, "b200sd_nhwc_to_nchw_f32: bad arguments");
+    const size_t total = static_cast<size_t>(n) * c * h * w;
+    if (in_f32)
+        nhwc_to_nchw_f32_kernel<float><<<grid_for(total, 256), 256, 0, stream>>>(reinterpret_cast<const float*>(in),
+                                                                                 out, n, c, h * w, c_pad);
+    else
+        nhwc_to_nchw_f32_kernel<__half><<<grid_for(total, 256), 256, 0, stream>>>(reinterpret_cast<const __half*>(in),
+                                                                                  out, n, c, h * w, c_pad);
+    B200SD_CHECK_CUDA(cudaGetLastError());
+    count_launch(1);
+    return 0;
+}
+
+extern "C" int b200sd_ctx_to_tokens(const void* in, int32_t in_f32, void* out, int32_t b, int32_t d, int32_t s,
+                                    void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    B200SD_REQUIRE(in && out, "b200sd_ctx_to_tokens: null pointer");
+    dim3 grid((s + 31) / 32, (d + 31) / 32, b), block(32, 8);
+    if (in_f32)
+        ctx_to_tokens_kernel<float><<<grid, block, 0, stream>>>(reinterpret_cast<const float*>(in),
+                                                                reinterpret_cast<__half*>(out), d, s);
+    else
+        ctx_to_tokens_kernel<__half><<<grid, block, 0, stream>>>(reinterpret_cast<const __half*>(in),
+                                                                 reinterpret_cast<__half*>(out), d, s);
+    B200SD_CHECK_CUDA(cudaGetLastError());
+    count_launch(1);
+    return 0;
+}
+
+extern "C" int b200sd_upsample2x(const void* in, void* out, int32_t n, int32_t h, int32_t w, int32_t c,
+                                 void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    B200SD_REQUIRE(in && out && c % 8 == 0, "b200sd_upsample2x: c=%d must be a multiple of 8", c);
+    const size_t total = static_cast<size_t>(n) * 4 * h * w * (c / 8);
+    upsample2x_kernel<<<grid_for(total, 256), 256, 0, stream>>>(reinterpret_cast<const uint4*>(in),
+                                                                reinterpret_cast<uint4*>(out), n, h, w, c / 8);
+    B200SD_CHECK_CUDA(cudaGetLastError());
+    count_launch(1);
+    return 0;
+}
+
+extern "C" int b200sd_add(const void* a, const void* b, void* out, size_t numel, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    B200SD_REQUIRE(a && b && out && numel % 2 == 0, "b200sd_add: bad arguments");
+    add_kernel<<<grid_for(numel / 2, 256), 256, 0, stream>>>(reinterpret_cast<const __half2*>(a),
+                                                             reinterpret_cast<const __half2*>(b),
+                                                             reinterpret_cast<__half2*>(out), numel / 2);
+    B200SD_CHECK_CUDA(cudaGetLastError());
+    count_launch(1);
+    return 0;
+}
+
+extern "C" int b200sd_linear_small(const float* x, const void* wgt, const float* bias, const float* add, float* out,
+                                   int32_t m, int32_t n, int32_t k, int32_t act_in, int32_t act_out, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    B200SD_REQUIRE(x && wgt && out, "b200sd_linear_small: null pointer");
+    B200SD_REQUIRE(m >= 1 && m <= 32 && k % 8 == 0, "b200sd_linear_small: need 1 <= m <= 32 and k %% 8 == 0 (m=%d k=%d)",
+                   m, k);
+    const int blocks = (n + 7) / 8;
+    const __half* w = reinterpret_cast<const __half*>(wgt);
+    for (int r0 = 0; r0 < m; r0 += 8) {
+        const int mm = std::min(8, m - r0);
+        const float* xr = x + static_cast<size_t>(r0) * k;
+        float* orow = out + static_cast<size_t>(r0) * n;
+        if (mm <= 2)
+            linear_small_kernel<2><<<blocks, 256, 0, stream>>>(xr, w, bias, add, orow, mm, n, k, act_in, act_out);
+        else
+            linear_small_kernel<8><<<blocks, 256, 0, stream>>>(xr, w, bias, add, orow, mm, n, k, act_in, act_out);
+        B200SD_CHECK_CUDA(cudaGetLastError());
+        count_launch(1);
+    }
+    return 0;
+}
+
+extern "C" int b200sd_timestep_embedding(const float* timesteps, float* out, int32_t m, int32_t dim,
+                                         int32_t flip_sin_to_cos, float freq_shift, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    B200SD_REQUIRE(timesteps && out && dim % 2 == 0, "b200sd_timestep_embedding: bad arguments");
+    const int total = m * (dim / 2);
+    timestep_embedding_kernel<<<(total + 127) / 128, 128, 0, stream>>>(timesteps, out, m, dim, flip_sin_to_cos,
+                                                                      freq_shift);
+    B200SD_CHECK_CUDA(cudaGetLastError());
+    count_launch(1);
+    return 0;
+}
+
+extern "C" int b200sd_cfg_scheduler_step(const float* noise_pred, float* latents, float* hist, float* denoised,
+                                         void* unet_in, int32_t c_pad, int32_t n, int32_t c, int32_t h, int32_t w,
+                                         const b200sd_step_coeffs* coeffs, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    B200SD_REQUIRE(noise_pred && latents && coeffs, "b200sd_cfg_scheduler_step: null pointer");
+    B200SD_REQUIRE(coeffs->n_hist >= 0 && coeffs->n_hist <= 4 && (coeffs->n_hist == 0 || hist),
+                   "b200sd_cfg_scheduler_step: bad history arguments");
+    B200SD_REQUIRE(coeffs->push_kind == 0 || (hist && coeffs->hist_head >= 0 && coeffs->hist_head < 4),
+                   "b200sd_cfg_scheduler_step: bad history ring slot");
+    const int numel = n * c * h * w;
+    cfg_step_kernel<<<(numel + 255) / 256, 256, 0, stream>>>(noise_pred, latents, hist, denoised,
+                                                             reinterpret_cast<__half*>(unet_in), c_pad, n, c, h * w,
+                                                             *coeffs);
+    B200SD_CHECK_CUDA(cudaGetLastError());
+    count_launch(1);
+    return 0;
+}
+
+extern "C" int b200sd_image_postprocess(const void* in, int32_t in_f32, int32_t c_pad, float* out_f32,
+                                        uint8_t* out_u8, int32_t n, int32_t h, int32_t w, int32_t c, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    B200SD_REQUIRE(in && (out_f32 || out_u8), "b200sd_image_postprocess: null pointer");
+    const size_t pixels = static_cast<size_t>(n) * h * w;
+    if (in_f32)
+        image_post_kernel<float><<<grid_for(pixels * c, 256), 256, 0, stream>>>(reinterpret_cast<const float*>(in),
+                                                                                c_pad, out_f32, out_u8, pixels, c);
+    else
+        image_post_kernel<__half><<<grid_for(pixels * c, 256), 256, 0, stream>>>(reinterpret_cast<const __half*>(in),
+                                                                                 c_pad, out_f32, out_u8, pixels, c);
+    B200SD_CHECK_CUDA(cudaGetLastError());
+    count_launch(1);
+    return 0;
+}

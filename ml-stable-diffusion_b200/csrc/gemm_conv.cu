@@ -1,0 +1,580 @@
+// b200sd -- tcgen05 GEMM / im2col-free implicit-GEMM 3x3 convolution for sm_100a.
+//
+// One persistent, warp-specialised kernel:
+//   warp 0      TMA producer  (cp.async.bulk.tensor 2D/4D boxes, SWIZZLE_128B, mbarrier tx)
+//   warp 1      MMA issuer    (one elected lane; tcgen05.mma kind::f16 M=128, N=block_n, K=16;
+//                              accumulators double-buffered in TMEM; tcgen05.commit -> mbarriers)
+//   warps 2..5  epilogue      (tcgen05.ld 32x32b; bias / time-embedding / GEGLU / residual; fp16|fp32
+//                              stores or fp32 split-K partials)
+//
+// Replaces every nn.Conv2d of the reference UNet / VAE decoder (reference
+// python_coreml_stable_diffusion/unet.py:74-84, 435-464, 499-507, 533-551, 601-617, 853, 970).
+// The 3x3 convolution never materialises im2col: k-block (tap, 64-channel chunk) is one TMA box
+// of the NHWC activation shifted by the tap offset; TMA's out-of-bounds zero fill is the padding.
+#include "common.cuh"
+#include "../../include/b200sd.h"
+
+#include <algorithm>
+
+namespace b200sd {
+
+static constexpr int kBM = 128;
+static constexpr int kBK = 64;
+static constexpr int kAStage = kBM * kBK * 2;  // 16 KiB
+static constexpr int kGemmThreads = 192;
+static constexpr int kMaxStages = 8;
+static constexpr int kSmemBudget = 200 * 1024;
+
+struct __align__(64) GemmParams {
+    CUtensorMap tmA0, tmA1, tmB;
+    int mode, M, N, n_store;  // n_store: columns written per row (N or N/2 for GEGLU)
+    int C0, Kpt, kc0, kc, taps;
+    int kb_total, kb_per_split, splits;
+    int m_tiles, n_tiles, block_n, stages;
+    int n_img, Hout, Wout, stride, bw_log2, bh_log2, tiles_w, tiles_h;
+    int bias_rows, geglu, out_f32;
+    void* out;
+    const float* bias;
+    const __half* residual;
+    float* partial;
+};
+
+struct TileCoord {
+    int m_tile, n_tile, split;
+    int n0, h0, w0;  // conv: output-space origin of the 128-pixel box
+};
+
+__device__ __forceinline__ TileCoord decode_work(const GemmParams& p, int work) {
+    TileCoord t;
+    t.m_tile = work % p.m_tiles;
+    int r = work / p.m_tiles;
+    t.n_tile = r % p.n_tiles;
+    t.split = r / p.n_tiles;
+    t.n0 = t.h0 = t.w0 = 0;
+    if (p.mode == 1) {
+        int tw = t.m_tile % p.tiles_w;
+        int r2 = t.m_tile / p.tiles_w;
+        int th = r2 % p.tiles_h;
+        int tn = r2 / p.tiles_h;
+        t.w0 = tw << p.bw_log2;
+        t.h0 = th << p.bh_log2;
+        t.n0 = tn << (7 - p.bw_log2 - p.bh_log2);
+    }
+    return t;
+}
+
+// Applies the epilogue to 16 consecutive accumulator columns of one output row and stores them.
+__device__ __forceinline__ void epilogue_store16(const GemmParams& p, float (&acc)[16], int out_row, int col0,
+                                                 int split, int bias_base) {
+    if (p.partial != nullptr) {
+        float* dst = p.partial + (static_cast<size_t>(split) * p.M + out_row) * p.N + col0;
+        if (col0 + 16 <= p.N && (p.N & 3) == 0) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4)
+                *reinterpret_cast<float4*>(dst + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                if (col0 + j < p.N) dst[j] = acc[j];
+        }
+        return;
+    }
+    const bool full = (col0 + 16 <= p.N);
+    if (p.bias != nullptr) {
+        const float* b = p.bias + bias_base + col0;
+        if (full && (p.N & 3) == 0) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+                float4 bv = *reinterpret_cast<const float4*>(b + j);
+                acc[j] += bv.x, acc[j + 1] += bv.y, acc[j + 2] += bv.z, acc[j + 3] += bv.w;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                if (col0 + j < p.N) acc[j] += b[j];
+        }
+    }
+    int ocol0 = col0, nvals = 16;
+    if (p.geglu) {
+        // interleaved columns: even = value, odd = gate  (unet.py:616-617: a * gelu(g))
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = acc[2 * j] * gelu_erf_f(acc[2 * j + 1]);
+        ocol0 = col0 >> 1;
+        nvals = 8;
+    }
+    const int ld = p.n_store;
+    const size_t off = static_cast<size_t>(out_row) * ld + ocol0;
+    const bool vec_ok = (ocol0 + nvals <= ld) && ((ld & 7) == 0);
+    if (p.residual != nullptr) {
+        const __half* r = p.residual + off;
+        if (vec_ok) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 8) {
+                if (j < nvals) {
+                    uint4 rv = *reinterpret_cast<const uint4*>(r + j);
+                    const __half2* h2 = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        float2 f = __half22float2(h2[q]);
+                        acc[j + 2 * q] += f.x;
+                        acc[j + 2 * q + 1] += f.y;
+                    }
+                }
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                if (j < nvals && ocol0 + j < ld) acc[j] += __half2float(r[j]);
+        }
+    }
+    if (p.out_f32) {
+        float* o = reinterpret_cast<float*>(p.out) + off;
+        if (vec_ok) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4)
+                if (j < nvals)
+                    *reinterpret_cast<float4*>(o + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                if (j < nvals && ocol0 + j < ld) o[j] = acc[j];
+        }
+    } else {
+        __half* o = reinterpret_cast<__half*>(p.out) + off;
+        if (vec_ok) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 8) {
+                if (j < nvals) {
+                    uint4 pk;
+                    pk.x = pack_half2(acc[j], acc[j + 1]);
+                    pk.y = pack_half2(acc[j + 2], acc[j + 3]);
+                    pk.z = pack_half2(acc[j + 4], acc[j + 5]);
+                    pk.w = pack_half2(acc[j + 6], acc[j + 7]);
+                    *reinterpret_cast<uint4*>(o + j) = pk;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                if (j < nvals && ocol0 + j < ld) o[j] = __float2half_rn(acc[j]);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kGemmThreads, 1) umma_gemm_kernel(const __grid_constant__ GemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int b_stage = p.block_n * (kBK * 2);
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + p.stages * kAStage;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b + p.stages * b_stage);
+    uint64_t* empty_bar = full_bar + kMaxStages;
+    uint64_t* tmem_full = empty_bar + kMaxStages;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&p.tmA0);
+        prefetch_tmap(&p.tmA1);
+        prefetch_tmap(&p.tmB);
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&tmem_full[s], 1);
+            mbar_init(&tmem_empty[s], 128);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_ptr, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    const int total_work = p.m_tiles * p.n_tiles * p.splits;
+
+    if (warp == 0) {
+        // ------------------------------- TMA producer -------------------------------
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            const uint32_t tx_bytes = kAStage + b_stage;
+            for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
+                const TileCoord t = decode_work(p, work);
+                const int kb0 = t.split * p.kb_per_split;
+                const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_expect_tx(&full_bar[stage], tx_bytes);
+                    const int tap = kb / p.kc;
+                    const int j = kb - tap * p.kc;
+                    const bool src1 = j >= p.kc0;
+                    const int c = (src1 ? (j - p.kc0) : j) * kBK;
+                    const int wk = tap * p.Kpt + (src1 ? p.C0 : 0) + c;
+                    const CUtensorMap* tmA = src1 ? &p.tmA1 : &p.tmA0;
+                    void* dst_a = smem_a + stage * kAStage;
+                    if (p.mode == 0) {
+                        tma_load_2d(dst_a, tmA, &full_bar[stage], c, t.m_tile * kBM, kEvictNormal);
+                    } else {
+                        const int r = tap / 3, s = tap - 3 * r;
+                        tma_load_4d(dst_a, tmA, &full_bar[stage], c, t.w0 * p.stride + s - 1,
+                                    t.h0 * p.stride + r - 1, t.n0, kEvictNormal);
+                    }
+                    tma_load_2d(smem_b + stage * b_stage, &p.tmB, &full_bar[stage], wk, t.n_tile * p.block_n,
+                                kEvictLast);
+                    if (++stage == p.stages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------- MMA issuer ---------------------------------
+        const uint32_t idesc = make_idesc_f16(kBM, p.block_n, 0, 0);
+        int stage = 0;
+        uint32_t phase = 0;
+        int iter = 0;
+        for (int work = blockIdx.x; work < total_work; work += gridDim.x, ++iter) {
+            const TileCoord t = decode_work(p, work);
+            const int kb0 = t.split * p.kb_per_split;
+            const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+            const int as = iter & 1;
+            const uint32_t aphase = (iter >> 1) & 1;
+            mbar_wait(&tmem_empty[as], aphase ^ 1);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + as * 256;
+            for (int kb = kb0; kb < kb1; ++kb) {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint64_t adesc = make_smem_desc_sw128(smem_u32(smem_a + stage * kAStage), 1024, 0);
+                    const uint64_t bdesc = make_smem_desc_sw128(smem_u32(smem_b + stage * b_stage), 1024, 0);
+#pragma unroll
+                    for (int k = 0; k < kBK / 16; ++k) {
+                        // +32 B per K=16 step inside the 128 B swizzle row (start address is in 16 B units)
+                        umma_f16_ss(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);
+                    if (kb == kb1 - 1) umma_commit(&tmem_full[as]);
+                }
+                __syncwarp();
+                if (++stage == p.stages) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+        }
+    } else {
+        // ------------------------------- epilogue -----------------------------------
+        const int lane_group = warp & 3;  // TMEM lanes [32*lane_group, +32) are accessible to this warp
+        const int row = lane_group * 32 + lane;
+        int iter = 0;
+        for (int work = blockIdx.x; work < total_work; work += gridDim.x, ++iter) {
+            const TileCoord t = decode_work(p, work);
+            const int as = iter & 1;
+            const uint32_t aphase = (iter >> 1) & 1;
+            int out_row;
+            bool valid;
+            if (p.mode == 0) {
+                out_row = t.m_tile * kBM + row;
+                valid = out_row < p.M;
+            } else {
+                const int dw = row & ((1 << p.bw_log2) - 1);
+                const int dh = (row >> p.bw_log2) & ((1 << p.bh_log2) - 1);
+                const int dn = row >> (p.bw_log2 + p.bh_log2);
+                const int on = t.n0 + dn, oy = t.h0 + dh, ox = t.w0 + dw;
+                valid = (on < p.n_img) && (oy < p.Hout) && (ox < p.Wout);
+                out_row = (on * p.Hout + oy) * p.Wout + ox;
+            }
+            const int bias_base = (p.bias_rows > 0 && valid) ? (out_row / p.bias_rows) * p.N : 0;
+            mbar_wait(&tmem_full[as], aphase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_group * 32) << 16) + as * 256;
+            const int ncol0 = t.n_tile * p.block_n;
+            for (int c = 0; c < p.block_n; c += 16) {
+                uint32_t v[16];
+                tmem_ld16(taddr + c, v);
+                tmem_ld_wait();
+                if (valid && ncol0 + c < p.N) {
+                    float acc[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) acc[j] = __uint_as_float(v[j]);
+                    epilogue_store16(p, acc, out_row, ncol0 + c, t.split, bias_base);
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&tmem_empty[as]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// Sums split-K partials and applies the same epilogue (bias, residual); no GEGLU.
+__global__ void splitk_reduce_kernel(const float* __restrict__ partial, int splits, int M, int N,
+                                     const float* __restrict__ bias, int bias_rows,
+                                     const __half* __restrict__ residual, void* __restrict__ out, int out_f32) {
+    const size_t total4 = static_cast<size_t>(M) * N / 4;
+    const size_t stride = static_cast<size_t>(M) * N;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total4;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const size_t e = i * 4;
+        float4 acc = *reinterpret_cast<const float4*>(partial + e);
+        for (int s = 1; s < splits; ++s) {
+            const float4 v = *reinterpret_cast<const float4*>(partial + s * stride + e);
+            acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+        }
+        const int row = static_cast<int>(e / N);
+        const int col = static_cast<int>(e - static_cast<size_t>(row) * N);
+        if (bias != nullptr) {
+            const float* b = bias + (bias_rows > 0 ? (row / bias_rows) * N : 0) + col;
+            acc.x += b[0], acc.y += b[1], acc.z += b[2], acc.w += b[3];
+        }
+        if (residual != nullptr) {
+            const __half2* r = reinterpret_cast<const __half2*>(residual + e);
+            const float2 r0 = __half22float2(r[0]), r1 = __half22float2(r[1]);
+            acc.x += r0.x, acc.y += r0.y, acc.z += r1.x, acc.w += r1.y;
+        }
+        if (out_f32) {
+            *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + e) = acc;
+        } else {
+            uint2 pk;
+            pk.x = pack_half2(acc.x, acc.y);
+            pk.y = pack_half2(acc.z, acc.w);
+            *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(out) + e) = pk;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+struct GemmPlan {
+    int M, N, Kpt, taps, kc0, kc1, kb_total;
+    int m_tiles, n_tiles, block_n, splits, kb_per_split, stages;
+    int Hout, Wout, bw, bh, bn_img, tiles_w, tiles_h, tiles_n;
+};
+
+static int ilog2(int v) {
+    int l = 0;
+    while ((1 << l) < v) ++l;
+    return l;
+}
+
+static int plan_gemm(const b200sd_gemm_args& a, GemmPlan& pl) {
+    B200SD_REQUIRE(a.mode == 0 || a.mode == 1, "b200sd_gemm: bad mode %d", a.mode);
+    B200SD_REQUIRE(a.c0 > 0 && a.c0 % 8 == 0 && a.c1 >= 0 && a.c1 % 8 == 0,
+                   "b200sd_gemm: channel counts must be positive multiples of 8 (c0=%d c1=%d)", a.c0, a.c1);
+    B200SD_REQUIRE(a.n > 0, "b200sd_gemm: n=%d", a.n);
+    pl.N = a.n;
+    pl.Kpt = a.c0 + a.c1;
+    pl.kc0 = (a.c0 + kBK - 1) / kBK;
+    pl.kc1 = (a.c1 + kBK - 1) / kBK;
+    pl.taps = a.mode == 1 ? 9 : 1;
+    pl.kb_total = pl.taps * (pl.kc0 + pl.kc1);
+    if (a.mode == 0) {
+        B200SD_REQUIRE(a.m > 0, "b200sd_gemm: m=%d", a.m);
+        pl.M = a.m;
+        pl.m_tiles = (a.m + kBM - 1) / kBM;
+        pl.Hout = pl.Wout = pl.bw = pl.bh = pl.bn_img = pl.tiles_w = pl.tiles_h = pl.tiles_n = 1;
+    } else {
+        B200SD_REQUIRE(a.stride == 1 || a.stride == 2, "b200sd_gemm: stride %d", a.stride);
+        B200SD_REQUIRE(a.n_img > 0 && a.h > 0 && a.w > 0, "b200sd_gemm: bad image geometry");
+        B200SD_REQUIRE(a.stride == 1 || (a.h % 2 == 0 && a.w % 2 == 0), "b200sd_gemm: stride-2 needs even h, w");
+        pl.Hout = a.h / a.stride;
+        pl.Wout = a.w / a.stride;
+        pl.M = a.n_img * pl.Hout * pl.Wout;
+        // pick the 128-pixel box (bn_img x bh x bw, powers of two) with the least padding
+        long best = -1;
+        for (int bw = 128; bw >= 1; bw >>= 1) {
+            if (bw * a.stride > 256) continue;
+            for (int bh = 128 / bw; bh >= 1; bh >>= 1) {
+                if (bh * a.stride > 256) continue;
+                const int bn = 128 / (bw * bh);
+                const int tw = (pl.Wout + bw - 1) / bw, th = (pl.Hout + bh - 1) / bh, tn = (a.n_img + bn - 1) / bn;
+                const long tiles = static_cast<long>(tw) * th * tn;
+                // prefer fewer tiles, then wider rows
+                const long score = tiles * 1024 - bw;
+                if (best < 0 || score < best) {
+                    best = score;
+                    pl.bw = bw, pl.bh = bh, pl.bn_img = bn, pl.tiles_w = tw, pl.tiles_h = th, pl.tiles_n = tn;
+                }
+            }
+        }
+        pl.m_tiles = pl.tiles_w * pl.tiles_h * pl.tiles_n;
+    }
+    if (a.geglu) B200SD_REQUIRE(a.n % 16 == 0, "b200sd_gemm: GEGLU needs n %% 16 == 0");
+    // N tiling: fewest tiles, then least padding
+    if (a.block_n > 0) {
+        B200SD_REQUIRE(a.block_n % 16 == 0 && a.block_n <= 256, "b200sd_gemm: block_n %d", a.block_n);
+        pl.block_n = a.block_n;
+    } else {
+        const int nt = (a.n + 255) / 256;
+        pl.block_n = std::min(256, ((a.n + nt - 1) / nt + 15) / 16 * 16);
+    }
+    pl.n_tiles = (a.n + pl.block_n - 1) / pl.block_n;
+    // split-K: fill the machine when the output grid is small
+    const int tiles = pl.m_tiles * pl.n_tiles;
+    const int sms = num_sms();
+    int splits = 1;
+    if (a.split_k > 0) {
+        splits = a.split_k;
+    } else if (!a.geglu && tiles * 10 < sms * 7) {
+        splits = std::max(1, std::min(sms / tiles, pl.kb_total / 4));
+    }
+    splits = std::max(1, std::min(splits, pl.kb_total));
+    pl.kb_per_split = (pl.kb_total + splits - 1) / splits;
+    pl.splits = (pl.kb_total + pl.kb_per_split - 1) / pl.kb_per_split;
+    if (pl.splits > 1) {
+        B200SD_REQUIRE(!a.geglu, "b200sd_gemm: split-K with GEGLU is not supported");
+        B200SD_REQUIRE(a.n % 4 == 0, "b200sd_gemm: split-K needs n %% 4 == 0");
+    }
+    const int per_stage = kAStage + pl.block_n * kBK * 2;
+    pl.stages = std::max(2, std::min(kMaxStages, kSmemBudget / per_stage));
+    return 0;
+}
+
+static size_t plan_workspace(const GemmPlan& pl) {
+    return pl.splits > 1 ? static_cast<size_t>(pl.splits) * pl.M * pl.N * sizeof(float) : 0;
+}
+
+extern void count_launch(int n);
+
+static int launch_gemm(const b200sd_gemm_args& a, cudaStream_t stream) {
+    GemmPlan pl;
+    if (int rc = plan_gemm(a, pl)) return rc;
+    B200SD_REQUIRE(a.a0 && a.wgt && a.out, "b200sd_gemm: null pointer");
+    B200SD_REQUIRE(a.c1 == 0 || a.a1, "b200sd_gemm: a1 is null but c1 > 0");
+    const size_t ws = plan_workspace(pl);
+    B200SD_REQUIRE(ws == 0 || (a.workspace && a.workspace_bytes >= ws),
+                   "b200sd_gemm: split-K needs %zu workspace bytes, got %zu", ws, a.workspace_bytes);
+
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    // ---- tensor maps ----
+    const uint32_t es1[4] = {1, 1, 1, 1};
+    if (a.mode == 0) {
+        const uint32_t box[2] = {kBK, kBM};
+        {
+            const uint64_t dims[2] = {static_cast<uint64_t>(a.c0), static_cast<uint64_t>(a.m)};
+            const uint64_t str[1] = {static_cast<uint64_t>(a.c0) * 2};
+            if (int rc = encode_tmap_f16(&p.tmA0, a.a0, 2, dims, str, box, es1)) return rc;
+        }
+        if (a.c1 > 0) {
+            const uint64_t dims[2] = {static_cast<uint64_t>(a.c1), static_cast<uint64_t>(a.m)};
+            const uint64_t str[1] = {static_cast<uint64_t>(a.c1) * 2};
+            if (int rc = encode_tmap_f16(&p.tmA1, a.a1, 2, dims, str, box, es1)) return rc;
+        } else {
+            p.tmA1 = p.tmA0;
+        }
+    } else {
+        const uint32_t st = static_cast<uint32_t>(a.stride);
+        const uint32_t box[4] = {kBK, static_cast<uint32_t>(pl.bw) * st, static_cast<uint32_t>(pl.bh) * st,
+                                 static_cast<uint32_t>(pl.bn_img)};
+        const uint32_t es[4] = {1, st, st, 1};
+        for (int src = 0; src < 2; ++src) {
+            const int c = src == 0 ? a.c0 : a.c1;
+            if (c == 0) {
+                p.tmA1 = p.tmA0;
+                continue;
+            }
+            const uint64_t dims[4] = {static_cast<uint64_t>(c), static_cast<uint64_t>(a.w),
+                                      static_cast<uint64_t>(a.h), static_cast<uint64_t>(a.n_img)};
+            const uint64_t str[3] = {static_cast<uint64_t>(c) * 2, static_cast<uint64_t>(c) * 2 * a.w,
+                                     static_cast<uint64_t>(c) * 2 * a.w * a.h};
+            if (int rc = encode_tmap_f16(src == 0 ? &p.tmA0 : &p.tmA1, src == 0 ? a.a0 : a.a1, 4, dims, str, box, es))
+                return rc;
+        }
+    }
+    {
+        const uint64_t ktot = static_cast<uint64_t>(pl.taps) * pl.Kpt;
+        const uint64_t dims[2] = {ktot, static_cast<uint64_t>(a.n)};
+        const uint64_t str[1] = {ktot * 2};
+        const uint32_t box[2] = {kBK, static_cast<uint32_t>(pl.block_n)};
+        if (int rc = encode_tmap_f16(&p.tmB, a.wgt, 2, dims, str, box, es1)) return rc;
+    }
+    p.mode = a.mode;
+    p.M = pl.M;
+    p.N = a.n;
+    p.n_store = a.geglu ? a.n / 2 : a.n;
+    p.C0 = a.c0;
+    p.Kpt = pl.Kpt;
+    p.kc0 = pl.kc0;
+    p.kc = pl.kc0 + pl.kc1;
+    p.taps = pl.taps;
+    p.kb_total = pl.kb_total;
+    p.kb_per_split = pl.kb_per_split;
+    p.splits = pl.splits;
+    p.m_tiles = pl.m_tiles;
+    p.n_tiles = pl.n_tiles;
+    p.block_n = pl.block_n;
+    p.stages = pl.stages;
+    p.n_img = a.n_img;
+    p.Hout = pl.Hout;
+    p.Wout = pl.Wout;
+    p.stride = a.mode == 1 ? a.stride : 1;
+    p.bw_log2 = ilog2(pl.bw);
+    p.bh_log2 = ilog2(pl.bh);
+    p.tiles_w = pl.tiles_w;
+    p.tiles_h = pl.tiles_h;
+    p.bias_rows = a.bias_rows;
+    p.geglu = a.geglu;
+    p.out_f32 = a.out_f32;
+    p.out = a.out;
+    p.bias = pl.splits > 1 ? nullptr : a.bias;
+    p.residual = pl.splits > 1 ? nullptr : reinterpret_cast<const __half*>(a.residual);
+    p.partial = pl.splits > 1 ? a.workspace : nullptr;
+
+    const int smem_bytes = pl.stages * (kAStage + pl.block_n * kBK * 2) + (2 * kMaxStages + 4) * 8 + 16 + 1024;
+    static bool attr_set = false;
+    if (!attr_set) {
+        B200SD_CHECK_CUDA(cudaFuncSetAttribute(umma_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               227 * 1024));
+        attr_set = true;
+    }
+    const int total = pl.m_tiles * pl.n_tiles * pl.splits;
+    const int grid = std::min(total, num_sms());
+    umma_gemm_kernel<<<grid, kGemmThreads, smem_bytes, stream>>>(p);
+    B200SD_CHECK_CUDA(cudaGetLastError());
+    count_launch(1);
+    if (pl.splits > 1) {
+        const size_t total4 = static_cast<size_t>(pl.M) * a.n / 4;
+        const int rgrid = static_cast<int>(std::min<size_t>((total4 + 255) / 256, static_cast<size_t>(num_sms()) * 8));
+        splitk_reduce_kernel<<<rgrid, 256, 0, stream>>>(a.workspace, pl.splits, pl.M, a.n, a.bias, a.bias_rows,
+                                                        reinterpret_cast<const __half*>(a.residual), a.out, a.out_f32);
+        B200SD_CHECK_CUDA(cudaGetLastError());
+        count_launch(1);
+    }
+    return 0;
+}
+
+}  // namespace b200sd
+
+extern "C" int b200sd_gemm(const b200sd_gemm_args* args, void* stream) {
+    if (!args) {
+        b200sd::set_error("b200sd_gemm: args is null");
+        return 2;
+    }
+    return b200sd::launch_gemm(*args, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" size_t b200sd_gemm_workspace_bytes(const b200sd_gemm_args* args) {
+    if (!args) return 0;
+    b200sd::GemmPlan pl;
+    if (b200sd::plan_gemm(*args, pl)) return 0;
+    return b200sd::plan_workspace(pl);
+}

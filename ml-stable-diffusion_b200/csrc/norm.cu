@@ -1,0 +1,306 @@
+// b200sd -- GroupNorm (+SiLU, + channel concat of two sources) and LayerNorm for sm_100a.
+// HBM/L2-bound elementwise + reduction kernels: 16-byte vectorised, coalesced along channels.
+//
+// GroupNorm replaces torch.nn.GroupNorm in the reference (unet.py:430,448,528,966; eps 1e-5 in
+// ResnetBlock2D / conv_norm_out, 1e-6 in SpatialTransformer and the VAE decoder) together with the
+// SiLU that follows it (unet.py:472-473,480-481,1044-1045).  LayerNorm replaces LayerNormANE
+// (layer_norm.py:51-80).
+#include "common.cuh"
+#include "../../include/b200sd.h"
+
+#include <algorithm>
+
+namespace b200sd {
+
+extern void count_launch(int n);
+
+static constexpr int kGnThreads = 256;
+static constexpr int kGnMaxChunks = 64;
+
+// ---- GroupNorm pass 1: per (image, chunk-of-pixels) partial (count, mean, M2) per group ----
+// grid = (chunks, n_img); each block walks its pixels with all channels (coalesced 16 B loads),
+// thread t owns channel-vector (t % vecs_per_pixel) => a fixed group set; per-thread Welford-free
+// shifted sums are merged per group through shared memory.
+__global__ void __launch_bounds__(kGnThreads) gn_partial_kernel(const __half* __restrict__ x0,
+                                                                const __half* __restrict__ x1, int c0, int c1,
+                                                                int hw, int groups, int chunks,
+                                                                float* __restrict__ stats /* [n][chunks][groups][2] */) {
+    const int C = c0 + c1;
+    const int cpg = C / groups;
+    const int vecs = C / 8;  // 16-byte vectors per pixel
+    const int n = blockIdx.y, chunk = blockIdx.x;
+    const int px_per_chunk = (hw + chunks - 1) / chunks;
+    const int px0 = chunk * px_per_chunk;
+    const int px1 = min(hw, px0 + px_per_chunk);
+
+    extern __shared__ float sm[];  // [groups][2] sum, sumsq  then reused
+    float* s_sum = sm;
+    float* s_sq = sm + groups;
+    for (int g = threadIdx.x; g < 2 * groups; g += blockDim.x) sm[g] = 0.f;
+    __syncthreads();
+
+    // pass A: sums relative to 0 (fp32; inputs are fp16 so |x| <= 65504); the apply pass merges
+    // chunk statistics with Chan's formula, which keeps cancellation local to one chunk.
+    const int total = (px1 - px0) * vecs;
+    // threads stride so that a thread keeps the same vector column when blockDim % vecs == 0;
+    // otherwise fall back to per-element group lookup (still correct).
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        const int px = px0 + i / vecs;
+        const int v = i % vecs;
+        const int ch = v * 8;
+        const __half* src = (ch < c0) ? x0 + (static_cast<size_t>(n) * hw + px) * c0 + ch
+                                      : x1 + (static_cast<size_t>(n) * hw + px) * c1 + (ch - c0);
+        const uint4 raw = *reinterpret_cast<const uint4*>(src);
+        const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+        float f[8];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float2 t = __half22float2(h2[q]);
+            f[2 * q] = t.x;
+            f[2 * q + 1] = t.y;
+        }
+        // the 8 channels span at most 8 groups; accumulate runs of equal group
+        int g_cur = ch / cpg;
+        float s = 0.f, sq = 0.f;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int g = (ch + e) / cpg;
+            if (g != g_cur) {
+                atomicAdd(&s_sum[g_cur], s);
+                atomicAdd(&s_sq[g_cur], sq);
+                s = sq = 0.f;
+                g_cur = g;
+            }
+            s += f[e];
+            sq += f[e] * f[e];
+        }
+        atomicAdd(&s_sum[g_cur], s);
+        atomicAdd(&s_sq[g_cur], sq);
+    }
+    __syncthreads();
+    const float cnt = static_cast<float>((px1 - px0) * cpg);
+    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+        const float mean = cnt > 0.f ? s_sum[g] / cnt : 0.f;
+        const float m2 = cnt > 0.f ? fmaxf(s_sq[g] - s_sum[g] * mean, 0.f) : 0.f;
+        float* o = stats + ((static_cast<size_t>(n) * chunks + chunk) * groups + g) * 2;
+        o[0] = mean;
+        o[1] = m2;
+    }
+}
+
+// ---- GroupNorm pass 2: merge chunk stats (Chan), normalise, affine, optional SiLU -----------
+__global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const __half* __restrict__ x0,
+                                                              const __half* __restrict__ x1, int c0, int c1, int hw,
+                                                              int groups, int chunks, float eps,
+                                                              const float* __restrict__ stats,
+                                                              const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta, int silu,
+                                                              __half* __restrict__ out, int px_per_block) {
+    const int C = c0 + c1;
+    const int cpg = C / groups;
+    const int vecs = C / 8;
+    const int n = blockIdx.y;
+    extern __shared__ float sm[];  // scale[C], shift[C]
+    float* s_scale = sm;
+    float* s_shift = sm + C;
+    float* s_mean = sm + 2 * C;  // [groups]
+    float* s_rstd = s_mean + groups;
+
+    const int px_per_chunk = (hw + chunks - 1) / chunks;
+    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+        float cnt = 0.f, mean = 0.f, m2 = 0.f;
+        for (int k = 0; k < chunks; ++k) {
+            const int p0 = k * px_per_chunk;
+            const int p1 = min(hw, p0 + px_per_chunk);
+            const float cb = static_cast<float>(max(0, p1 - p0) * cpg);
+            if (cb <= 0.f) continue;
+            const float* s = stats + ((static_cast<size_t>(n) * chunks + k) * groups + g) * 2;
+            const float mb = s[0], m2b = s[1];
+            const float tot = cnt + cb;
+            const float delta = mb - mean;
+            mean += delta * (cb / tot);
+            m2 += m2b + delta * delta * (cnt * cb / tot);
+            cnt = tot;
+        }
+        s_mean[g] = mean;
+        s_rstd[g] = rsqrtf(m2 / cnt + eps);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const int g = c / cpg;
+        const float sc = gamma[c] * s_rstd[g];
+        s_scale[c] = sc;
+        s_shift[c] = beta[c] - s_mean[g] * sc;
+    }
+    __syncthreads();
+
+    const int px0 = blockIdx.x * px_per_block;
+    const int px1 = min(hw, px0 + px_per_block);
+    const int total = (px1 - px0) * vecs;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        const int px = px0 + i / vecs;
+        const int v = i % vecs;
+        const int ch = v * 8;
+        const __half* src = (ch < c0) ? x0 + (static_cast<size_t>(n) * hw + px) * c0 + ch
+                                      : x1 + (static_cast<size_t>(n) * hw + px) * c1 + (ch - c0);
+        const uint4 raw = *reinterpret_cast<const uint4*>(src);
+        const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+        float f[8];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float2 t = __half22float2(h2[q]);
+            f[2 * q] = t.x;
+            f[2 * q + 1] = t.y;
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            float y = f[e] * s_scale[ch + e] + s_shift[ch + e];
+            f[e] = silu ? silu_f(y) : y;
+        }
+        uint4 pk;
+        pk.x = pack_half2(f[0], f[1]);
+        pk.y = pack_half2(f[2], f[3]);
+        pk.z = pack_half2(f[4], f[5]);
+        pk.w = pack_half2(f[6], f[7]);
+        *reinterpret_cast<uint4*>(out + (static_cast<size_t>(n) * hw + px) * C + ch) = pk;
+    }
+}
+
+static int gn_chunks(int hw, int c) {
+    // enough blocks to fill the machine, at most kGnMaxChunks, at least ~32 pixels per chunk
+    int chunks = std::min(kGnMaxChunks, std::max(1, hw / 32));
+    (void)c;
+    return chunks;
+}
+
+// ---- LayerNorm over channels of [rows, c]; one warp per row, two-pass in registers -----------
+template <int kVecsPerLane>
+__global__ void __launch_bounds__(256) layer_norm_kernel(const __half* __restrict__ x, const float* __restrict__ gamma,
+                                                         const float* __restrict__ beta, __half* __restrict__ out,
+                                                         int rows, int c, float eps) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= rows) return;
+    const int vecs = c / 8;
+    const __half* src = x + static_cast<size_t>(warp) * c;
+    float f[kVecsPerLane][8];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < kVecsPerLane; ++k) {
+        const int v = lane + 32 * k;
+        if (v < vecs) {
+            const uint4 raw = *reinterpret_cast<const uint4*>(src + v * 8);
+            const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float2 t = __half22float2(h2[q]);
+                f[k][2 * q] = t.x;
+                f[k][2 * q + 1] = t.y;
+                s += t.x + t.y;
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[k][e] = 0.f;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / c;
+    float sq = 0.f;
+#pragma unroll
+    for (int k = 0; k < kVecsPerLane; ++k) {
+        const int v = lane + 32 * k;
+        if (v < vecs) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float d = f[k][e] - mean;
+                sq += d * d;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float rstd = rsqrtf(sq / c + eps);
+    __half* dst = out + static_cast<size_t>(warp) * c;
+#pragma unroll
+    for (int k = 0; k < kVecsPerLane; ++k) {
+        const int v = lane + 32 * k;
+        if (v < vecs) {
+            float y[8];
+            const float4 g0 = *reinterpret_cast<const float4*>(gamma + v * 8);
+            const float4 g1 = *reinterpret_cast<const float4*>(gamma + v * 8 + 4);
+            const float4 b0 = *reinterpret_cast<const float4*>(beta + v * 8);
+            const float4 b1 = *reinterpret_cast<const float4*>(beta + v * 8 + 4);
+            const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int e = 0; e < 8; ++e) y[e] = (f[k][e] - mean) * rstd * gg[e] + bb[e];
+            uint4 pk;
+            pk.x = pack_half2(y[0], y[1]);
+            pk.y = pack_half2(y[2], y[3]);
+            pk.z = pack_half2(y[4], y[5]);
+            pk.w = pack_half2(y[6], y[7]);
+            *reinterpret_cast<uint4*>(dst + v * 8) = pk;
+        }
+    }
+}
+
+}  // namespace b200sd
+
+using namespace b200sd;
+
+extern "C" size_t b200sd_group_norm_workspace_bytes(int32_t n_img, int32_t hw, int32_t c, int32_t groups) {
+    return static_cast<size_t>(n_img) * gn_chunks(hw, c) * groups * 2 * sizeof(float);
+}
+
+extern "C" int b200sd_group_norm(const void* x0, const void* x1, int32_t c0, int32_t c1, int32_t n_img, int32_t hw,
+                                 int32_t groups, float eps, const float* gamma, const float* beta, int32_t silu,
+                                 void* out, float* stats_ws, size_t stats_ws_bytes, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const int C = c0 + c1;
+    B200SD_REQUIRE(x0 && out && gamma && beta && stats_ws, "b200sd_group_norm: null pointer");
+    B200SD_REQUIRE(c0 > 0 && c0 % 8 == 0 && c1 >= 0 && c1 % 8 == 0 && (c1 == 0 || x1),
+                   "b200sd_group_norm: channels must be multiples of 8 (c0=%d c1=%d)", c0, c1);
+    B200SD_REQUIRE(groups > 0 && C % groups == 0, "b200sd_group_norm: %d channels not divisible by %d groups", C,
+                   groups);
+    const int chunks = gn_chunks(hw, C);
+    B200SD_REQUIRE(stats_ws_bytes >= b200sd_group_norm_workspace_bytes(n_img, hw, C, groups),
+                   "b200sd_group_norm: workspace too small");
+    gn_partial_kernel<<<dim3(chunks, n_img), kGnThreads, 2 * groups * sizeof(float), stream>>>(
+        reinterpret_cast<const __half*>(x0), reinterpret_cast<const __half*>(x1), c0, c1, hw, groups, chunks,
+        stats_ws);
+    B200SD_CHECK_CUDA(cudaGetLastError());
+    // apply: ~ (8 * SMs) blocks overall
+    const int want_blocks = std::max(1, (num_sms() * 4) / std::max(1, n_img));
+    int px_per_block = std::max(1, (hw + want_blocks - 1) / want_blocks);
+    const int blocks = (hw + px_per_block - 1) / px_per_block;
+    const size_t smem = (2 * static_cast<size_t>(C) + 2 * groups) * sizeof(float);
+    B200SD_REQUIRE(smem <= 48 * 1024, "b200sd_group_norm: too many channels (%d)", C);
+    gn_apply_kernel<<<dim3(blocks, n_img), kGnThreads, smem, stream>>>(
+        reinterpret_cast<const __half*>(x0), reinterpret_cast<const __half*>(x1), c0, c1, hw, groups, chunks, eps,
+        stats_ws, gamma, beta, silu, reinterpret_cast<__half*>(out), px_per_block);
+    B200SD_CHECK_CUDA(cudaGetLastError());
+    count_launch(2);
+    return 0;
+}
+
+extern "C" int b200sd_layer_norm(const void* x, const float* gamma, const float* beta, void* out, int32_t rows,
+                                 int32_t c, float eps, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    B200SD_REQUIRE(x && gamma && beta && out, "b200sd_layer_norm: null pointer");
+    B200SD_REQUIRE(c % 8 == 0 && c > 0 && c <= 2048, "b200sd_layer_norm: c=%d must be a multiple of 8, <= 2048", c);
+    const int vecs = c / 8;
+    const int per_lane = (vecs + 31) / 32;
+    const int blocks = (rows + 7) / 8;
+    const __half* xi = reinterpret_cast<const __half*>(x);
+    __half* xo = reinterpret_cast<__half*>(out);
+    if (per_lane <= 2)
+        layer_norm_kernel<2><<<blocks, 256, 0, stream>>>(xi, gamma, beta, xo, rows, c, eps);
+    else if (per_lane <= 5)
+        layer_norm_kernel<5><<<blocks, 256, 0, stream>>>(xi, gamma, beta, xo, rows, c, eps);
+    else
+        layer_norm_kernel<8><<<blocks, 256, 0, stream>>>(xi, gamma, beta, xo, rows, c, eps);
+    B200SD_CHECK_CUDA(cudaGetLastError());
+    count_launch(1);
+    return 0;
+}

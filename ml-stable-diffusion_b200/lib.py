@@ -1,0 +1,342 @@
+"""ctypes binding of ``libb200sd.so`` (the C-ABI in ``include/b200sd.h``) + thin torch-tensor
+wrappers.  PyTorch is plumbing here (device memory, streams); every compute call goes through
+the C-ABI.  There is NO fallback: a missing library or a failing call raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libb200sd.so")
+_lib = None
+
+
+class B200SDError(RuntimeError):
+    pass
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [
+        ("mode", C.c_int32), ("m", C.c_int32), ("n", C.c_int32), ("c0", C.c_int32), ("c1", C.c_int32),
+        ("n_img", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("stride", C.c_int32),
+        ("geglu", C.c_int32), ("out_f32", C.c_int32), ("bias_rows", C.c_int32), ("split_k", C.c_int32),
+        ("block_n", C.c_int32),
+        ("a0", C.c_void_p), ("a1", C.c_void_p), ("wgt", C.c_void_p), ("bias", C.c_void_p),
+        ("residual", C.c_void_p), ("out", C.c_void_p), ("workspace", C.c_void_p),
+        ("workspace_bytes", C.c_size_t),
+    ]
+
+
+class StepCoeffs(C.Structure):
+    _fields_ = [
+        ("guidance", C.c_float), ("cx", C.c_float), ("ce", C.c_float), ("ch", C.c_float * 4),
+        ("x0_cx", C.c_float), ("x0_ce", C.c_float), ("n_hist", C.c_int32), ("push_kind", C.c_int32),
+        ("hist_head", C.c_int32),
+    ]
+
+
+_SIGNATURES = {
+    "b200sd_last_error": (C.c_char_p, []),
+    "b200sd_version": (C.c_int, []),
+    "b200sd_launch_count": (C.c_uint64, []),
+    "b200sd_gemm": (C.c_int, [C.POINTER(GemmArgs), C.c_void_p]),
+    "b200sd_gemm_workspace_bytes": (C.c_size_t, [C.POINTER(GemmArgs)]),
+    "b200sd_linear_small": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                      C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "b200sd_timestep_embedding": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float,
+                                            C.c_void_p]),
+    "b200sd_group_norm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                    C.c_float, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
+                                    C.c_size_t, C.c_void_p]),
+    "b200sd_group_norm_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "b200sd_layer_norm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                    C.c_float, C.c_void_p]),
+    "b200sd_attention": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                   C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                   C.c_int32, C.c_float, C.c_int32, C.c_void_p]),
+    "b200sd_nchw_to_nhwc": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                      C.c_int32, C.c_int32, C.c_void_p]),
+    "b200sd_nhwc_to_nchw_f32": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                          C.c_int32, C.c_int32, C.c_void_p]),
+    "b200sd_upsample2x": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                    C.c_void_p]),
+    "b200sd_add": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "b200sd_ctx_to_tokens": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                       C.c_void_p]),
+    "b200sd_cfg_scheduler_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                            C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(StepCoeffs),
+                                            C.c_void_p]),
+    "b200sd_image_postprocess": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
+                                           C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+
+def lib_path() -> str:
+    return _LIB_PATH
+
+
+def load():
+    """Load the CUDA library; raise loudly if it has not been built (no CPU fallback exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise B200SDError(
+            f"{_LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). b200sd has no CPU or PyTorch fallback path.")
+    lib = C.CDLL(_LIB_PATH)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    return C.c_void_p(t.data_ptr())
+
+
+def _check(rc, what):
+    if rc != 0:
+        msg = load().b200sd_last_error().decode(errors="replace")
+        raise B200SDError(f"{what} failed (rc={rc}): {msg}")
+
+
+def launch_count() -> int:
+    return int(load().b200sd_launch_count())
+
+
+# ------------------------------------------------------------------------------------------------
+# op wrappers (torch tensors in, torch tensors out; all on the current CUDA stream)
+# ------------------------------------------------------------------------------------------------
+def _req(t, dtype, what):
+    if t.dtype != dtype or not t.is_cuda or not t.is_contiguous():
+        raise B200SDError(f"{what}: expected contiguous CUDA {dtype}, got {t.dtype} {t.device} "
+                          f"contiguous={t.is_contiguous()}")
+
+
+def gemm_args(mode, a0, wgt, out, *, a1=None, bias=None, residual=None, m=0, n=0, n_img=0, h=0, w=0, stride=1,
+              geglu=False, bias_rows=0, split_k=0, block_n=0, workspace=None):
+    args = GemmArgs()
+    args.mode = mode
+    args.m = m
+    args.n = n
+    args.c0 = a0.shape[-1]
+    args.c1 = 0 if a1 is None else a1.shape[-1]
+    args.n_img, args.h, args.w, args.stride = n_img, h, w, stride
+    args.geglu = int(geglu)
+    args.out_f32 = int(out.dtype == torch.float32)
+    args.bias_rows = bias_rows
+    args.split_k = split_k
+    args.block_n = block_n
+    args.a0 = a0.data_ptr()
+    args.a1 = None if a1 is None else a1.data_ptr()
+    args.wgt = wgt.data_ptr()
+    args.bias = None if bias is None else bias.data_ptr()
+    args.residual = None if residual is None else residual.data_ptr()
+    args.out = out.data_ptr()
+    args.workspace = None if workspace is None else workspace.data_ptr()
+    args.workspace_bytes = 0 if workspace is None else workspace.numel() * workspace.element_size()
+    return args
+
+
+def gemm_workspace_bytes(args) -> int:
+    return int(load().b200sd_gemm_workspace_bytes(C.byref(args)))
+
+
+def run_gemm(args):
+    _check(load().b200sd_gemm(C.byref(args), _stream()), "b200sd_gemm")
+
+
+_ws_cache = {}
+
+
+def _workspace(nbytes, device):
+    key = (device.index, torch.cuda.current_stream().cuda_stream)
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() * 4 < nbytes:
+        ws = torch.empty(max(nbytes // 4 + 1, 1 << 22), dtype=torch.float32, device=device)
+        _ws_cache[key] = ws
+    return ws
+
+
+def linear(x, wgt, bias=None, residual=None, *, x1=None, geglu=False, out_dtype=torch.float16, split_k=0,
+           block_n=0, bias_rows=0, out=None):
+    """out[M, N] = epilogue([x | x1] @ wgt^T).  x [M, C0] fp16, wgt [N, C0(+C1)] fp16, bias fp32 [N]."""
+    _req(x, torch.float16, "linear x")
+    _req(wgt, torch.float16, "linear wgt")
+    m, n = x.shape[0], wgt.shape[0]
+    n_out = n // 2 if geglu else n
+    if out is None:
+        out = torch.empty(m, n_out, dtype=out_dtype, device=x.device)
+    args = gemm_args(0, x, wgt, out, a1=x1, bias=bias, residual=residual, m=m, n=n, geglu=geglu,
+                     bias_rows=bias_rows, split_k=split_k, block_n=block_n)
+    need = gemm_workspace_bytes(args)
+    if need:
+        ws = _workspace(need, x.device)
+        args.workspace = ws.data_ptr()
+        args.workspace_bytes = ws.numel() * 4
+    run_gemm(args)
+    return out
+
+
+def conv3x3(x, wgt, bias=None, residual=None, *, x1=None, stride=1, out_dtype=torch.float16, split_k=0,
+            block_n=0, bias_rows=0, out=None):
+    """3x3 pad-1 convolution.  x NHWC fp16 [N, H, W, C0]; wgt [Cout, 9*(C0+C1)] fp16 (OHWI);
+    bias fp32 [Cout] or [N_img, Cout] with bias_rows = Hout*Wout."""
+    _req(x, torch.float16, "conv3x3 x")
+    _req(wgt, torch.float16, "conv3x3 wgt")
+    nimg, h, w, _ = x.shape
+    cout = wgt.shape[0]
+    ho, wo = h // stride, w // stride
+    if out is None:
+        out = torch.empty(nimg, ho, wo, cout, dtype=out_dtype, device=x.device)
+    args = gemm_args(1, x, wgt, out, a1=x1, bias=bias, residual=residual, n=cout, n_img=nimg, h=h, w=w,
+                     stride=stride, bias_rows=bias_rows, split_k=split_k, block_n=block_n)
+    need = gemm_workspace_bytes(args)
+    if need:
+        ws = _workspace(need, x.device)
+        args.workspace = ws.data_ptr()
+        args.workspace_bytes = ws.numel() * 4
+    run_gemm(args)
+    return out
+
+
+def linear_small(x, wgt, bias=None, add=None, act_in=False, act_out=False):
+    _req(x, torch.float32, "linear_small x")
+    _req(wgt, torch.float16, "linear_small wgt")
+    m, k = x.shape
+    n = wgt.shape[0]
+    out = torch.empty(m, n, dtype=torch.float32, device=x.device)
+    _check(load().b200sd_linear_small(_ptr(x), _ptr(wgt), _ptr(bias), _ptr(add), _ptr(out), m, n, k,
+                                      int(act_in), int(act_out), _stream()), "b200sd_linear_small")
+    return out
+
+
+def timestep_embedding(t, dim, flip_sin_to_cos=True, freq_shift=0.0):
+    _req(t, torch.float32, "timestep_embedding t")
+    out = torch.empty(t.shape[0], dim, dtype=torch.float32, device=t.device)
+    _check(load().b200sd_timestep_embedding(_ptr(t), _ptr(out), t.shape[0], dim, int(flip_sin_to_cos),
+                                            float(freq_shift), _stream()), "b200sd_timestep_embedding")
+    return out
+
+
+def group_norm(x, gamma, beta, groups, eps, silu=False, x1=None, out=None):
+    """x NHWC fp16 [N, H, W, C0] (optionally ++ x1 [N, H, W, C1]) -> normalised [N, H, W, C0+C1]."""
+    _req(x, torch.float16, "group_norm x")
+    nimg, h, w, c0 = x.shape
+    c1 = 0 if x1 is None else x1.shape[-1]
+    if out is None:
+        out = torch.empty(nimg, h, w, c0 + c1, dtype=torch.float16, device=x.device)
+    need = int(load().b200sd_group_norm_workspace_bytes(nimg, h * w, c0 + c1, groups))
+    ws = _workspace(need, x.device)
+    _check(load().b200sd_group_norm(_ptr(x), _ptr(x1), c0, c1, nimg, h * w, groups, float(eps), _ptr(gamma),
+                                    _ptr(beta), int(silu), _ptr(out), _ptr(ws), ws.numel() * 4, _stream()),
+           "b200sd_group_norm")
+    return out
+
+
+def layer_norm(x, gamma, beta, eps=1e-5, out=None):
+    _req(x, torch.float16, "layer_norm x")
+    rows, c = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    _check(load().b200sd_layer_norm(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(out), rows, c, float(eps), _stream()),
+           "b200sd_layer_norm")
+    return out
+
+
+def attention(q, k, v, batch, heads, sq, sk, d=64, mask=None, impl=0, out=None, scale=None):
+    """q: view [batch*sq, >=heads*d] (row stride = q.stride(0)), k/v: [batch*sk, ...]; out [batch*sq, heads*d]."""
+    for t, nm in ((q, "q"), (k, "k"), (v, "v")):
+        if t.dtype != torch.float16 or not t.is_cuda or t.stride(-1) != 1:
+            raise B200SDError(f"attention {nm}: expected CUDA fp16 with unit inner stride")
+    if out is None:
+        out = torch.empty(batch * sq, heads * d, dtype=torch.float16, device=q.device)
+    scale = float(d) ** -0.5 if scale is None else float(scale)
+    _check(load().b200sd_attention(_ptr(q), _ptr(k), _ptr(v), _ptr(out), _ptr(mask), batch, heads, sq, sk, d,
+                                   q.stride(0), k.stride(0), v.stride(0), out.stride(0), scale, int(impl),
+                                   _stream()), "b200sd_attention")
+    return out
+
+
+def nchw_to_nhwc(x, c_pad=None):
+    n, c, h, w = x.shape
+    c_pad = c if c_pad is None else c_pad
+    if x.dtype not in (torch.float16, torch.float32) or not x.is_contiguous():
+        raise B200SDError("nchw_to_nhwc: expected contiguous fp16/fp32")
+    out = torch.empty(n, h, w, c_pad, dtype=torch.float16, device=x.device)
+    _check(load().b200sd_nchw_to_nhwc(_ptr(x), int(x.dtype == torch.float32), _ptr(out), n, c, h, w, c_pad,
+                                      _stream()), "b200sd_nchw_to_nhwc")
+    return out
+
+
+def nhwc_to_nchw_f32(x, c=None, out=None):
+    n, h, w, c_pad = x.shape
+    c = c_pad if c is None else c
+    if out is None:
+        out = torch.empty(n, c, h, w, dtype=torch.float32, device=x.device)
+    _check(load().b200sd_nhwc_to_nchw_f32(_ptr(x), int(x.dtype == torch.float32), _ptr(out), n, c, h, w, c_pad,
+                                          _stream()), "b200sd_nhwc_to_nchw_f32")
+    return out
+
+
+def upsample2x(x, out=None):
+    _req(x, torch.float16, "upsample2x x")
+    n, h, w, c = x.shape
+    if out is None:
+        out = torch.empty(n, 2 * h, 2 * w, c, dtype=torch.float16, device=x.device)
+    _check(load().b200sd_upsample2x(_ptr(x), _ptr(out), n, h, w, c, _stream()), "b200sd_upsample2x")
+    return out
+
+
+def add(a, b, out=None):
+    _req(a, torch.float16, "add a")
+    _req(b, torch.float16, "add b")
+    if out is None:
+        out = torch.empty_like(a)
+    _check(load().b200sd_add(_ptr(a), _ptr(b), _ptr(out), a.numel(), _stream()), "b200sd_add")
+    return out
+
+
+def ctx_to_tokens(ctx, out=None):
+    """(B, D, 1, S) fp16/fp32 -> [B*S, D] fp16."""
+    b, d, _, s = ctx.shape
+    if not ctx.is_contiguous():
+        raise B200SDError("ctx_to_tokens: expected contiguous input")
+    if out is None:
+        out = torch.empty(b * s, d, dtype=torch.float16, device=ctx.device)
+    _check(load().b200sd_ctx_to_tokens(_ptr(ctx), int(ctx.dtype == torch.float32), _ptr(out), b, d, s, _stream()),
+           "b200sd_ctx_to_tokens")
+    return out
+
+
+def cfg_scheduler_step(noise_pred, latents, coeffs: StepCoeffs, hist=None, denoised=None, unet_in=None):
+    _req(noise_pred, torch.float32, "cfg_scheduler_step noise_pred")
+    _req(latents, torch.float32, "cfg_scheduler_step latents")
+    n, c, h, w = latents.shape
+    c_pad = 0 if unet_in is None else unet_in.shape[-1]
+    _check(load().b200sd_cfg_scheduler_step(_ptr(noise_pred), _ptr(latents), _ptr(hist), _ptr(denoised),
+                                            _ptr(unet_in), c_pad, n, c, h, w, C.byref(coeffs), _stream()),
+           "b200sd_cfg_scheduler_step")
+    return latents
+
+
+def image_postprocess(x, c=3, want_u8=False):
+    n, h, w, c_pad = x.shape
+    of = torch.empty(n, h, w, c, dtype=torch.float32, device=x.device)
+    ou = torch.empty(n, h, w, c, dtype=torch.uint8, device=x.device) if want_u8 else None
+    _check(load().b200sd_image_postprocess(_ptr(x), int(x.dtype == torch.float32), c_pad, _ptr(of), _ptr(ou), n, h,
+                                           w, c, _stream()), "b200sd_image_postprocess")
+    return (of, ou) if want_u8 else of
