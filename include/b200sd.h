@@ -47,7 +47,7 @@ uint64_t b200sd_launch_count(void);
  *                       a0 [n_img, h, w, c0] (optionally ++ a1 with c1 channels); the 9 taps are
  *                       9 shifted TMA boxes with hardware zero fill at the borders.
  *                       W is [N, 9 * (c0 + c1)] with k = (ky*3 + kx) * C + c  (OHWI).
- *   epilogue: + bias[(row / bias_rows) * N + col] (bias_rows = rows sharing one bias vector;
+ *   epilogue: + bias[(row / bias_rows) * bias_stride + col] (bias_rows = rows sharing one bias vector;
  *             0 = one vector for all rows; h*w adds the per-image time embedding, unet.py:476-478)
  *             ; GEGLU a*gelu_erf(g) on interleaved column pairs (unet.py:616-617), output N/2 cols
  *             ; + residual[row, col] (unet.py:484-487, :563, :587-589)
@@ -64,6 +64,7 @@ typedef struct {
     int32_t geglu;         /* 1: GEGLU epilogue */
     int32_t out_f32;       /* 1: store fp32 */
     int32_t bias_rows;     /* see above */
+    int32_t bias_stride;   /* elements between consecutive bias vectors (0 = n) */
     int32_t split_k;       /* 0 = auto */
     int32_t block_n;       /* 0 = auto; else multiple of 16 in [16, 256] */
     const void* a0;
@@ -138,20 +139,24 @@ int b200sd_ctx_to_tokens(const void* in, int32_t in_f32, void* out, int32_t b, i
  *                                            StableDiffusionPipeline.swift:469-483)
  * then one scheduler update written as a linear combination
  *     x_prev = cx * x + ce * eps' + sum_i ch[i] * hist[i]
+ *     x0     = x0_cx * x + x0_ce * eps' + sum_i x0_ch[i] * hist[i]     (denoised estimate)
  * whose fp32 coefficients the host derives per step for DDIM (eta=0), DPM-Solver++(2M) and
- * PNDM/PLMS (Scheduler.swift:218-343, DPMSolverMultistepScheduler.swift:135-244); `hist` holds
- * past eps (PNDM) or past x0 (DPM).  kind selects what is pushed into the history ring:
- * 0 nothing (DDIM), 1 eps (PNDM), 2 x0 = (x - sigma_t eps)/alpha_t (DPM).
- * noise_pred: fp32 NCHW [2*n, c, h, w] (uncond batch first); latents fp32 [n, c, h, w] updated in
- * place; `unet_in` (fp16 NHWC [2n, h, w, c_pad], may be NULL) receives the duplicated next input. */
+ * PNDM/PLMS (Scheduler.swift:218-343, DPMSolverMultistepScheduler.swift:135-244).  `hist` is a
+ * 4-slot ring of latent-sized fp32 buffers holding past eps' (PLMS `ets`), past x0
+ * (DPM `modelOutputs`) or a saved sample (PLMS `currentSample`); all history reads of a step happen
+ * before its pushes.  noise_pred: fp32 NCHW [2*n, c, h, w] (uncond batch first); latents fp32
+ * [n, c, h, w] updated in place; `unet_in` (fp16 NHWC [2n, h, w, c_pad], may be NULL) receives the
+ * duplicated next UNet input (pipeline.py:502: np.concatenate([latents] * 2)). */
 typedef struct {
     float guidance;
     float cx, ce;
     float ch[4];
-    float x0_cx, x0_ce;      /* x0 = x0_cx * x + x0_ce * eps  (kind 2 history / denoised output) */
-    int32_t n_hist;          /* history entries used this step */
-    int32_t push_kind;       /* 0 none, 1 eps, 2 x0 */
-    int32_t hist_head;       /* ring slot to overwrite when pushing */
+    float x0_cx, x0_ce;
+    float x0_ch[4];
+    int32_t n_hist;          /* history slots read this step (0..4) */
+    int32_t push_eps_slot;   /* >= 0: hist[slot] = eps'  */
+    int32_t push_x0_slot;    /* >= 0: hist[slot] = x0    */
+    int32_t push_x_slot;     /* >= 0: hist[slot] = x (sample before this update) */
 } b200sd_step_coeffs;
 
 int b200sd_cfg_scheduler_step(const float* noise_pred, float* latents, float* hist /* [4][numel] */,

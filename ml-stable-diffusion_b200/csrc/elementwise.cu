@@ -170,12 +170,18 @@ __global__ void cfg_step_kernel(const float* __restrict__ noise_pred, float* __r
     const float eps = eu + k.guidance * (ec - eu);
     const float x = latents[i];
     float xp = k.cx * x + k.ce * eps;
+    float x0 = k.x0_cx * x + k.x0_ce * eps;
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-        if (j < k.n_hist) xp += k.ch[j] * hist[static_cast<size_t>(j) * numel + i];
-    const float x0 = k.x0_cx * x + k.x0_ce * eps;
-    if (k.push_kind == 1) hist[static_cast<size_t>(k.hist_head) * numel + i] = eps;
-    if (k.push_kind == 2) hist[static_cast<size_t>(k.hist_head) * numel + i] = x0;
+    for (int j = 0; j < 4; ++j) {
+        if (j < k.n_hist) {
+            const float hv = hist[static_cast<size_t>(j) * numel + i];
+            xp += k.ch[j] * hv;
+            x0 += k.x0_ch[j] * hv;
+        }
+    }
+    if (k.push_eps_slot >= 0) hist[static_cast<size_t>(k.push_eps_slot) * numel + i] = eps;
+    if (k.push_x0_slot >= 0) hist[static_cast<size_t>(k.push_x0_slot) * numel + i] = x0;
+    if (k.push_x_slot >= 0) hist[static_cast<size_t>(k.push_x_slot) * numel + i] = x;
     if (denoised) denoised[i] = x0;
     latents[i] = xp;
     if (unet_in) {
@@ -323,7 +329,8 @@ extern "C" int b200sd_cfg_scheduler_step(const float* noise_pred, float* latents
     B200SD_REQUIRE(noise_pred && latents && coeffs, "b200sd_cfg_scheduler_step: null pointer");
     B200SD_REQUIRE(coeffs->n_hist >= 0 && coeffs->n_hist <= 4 && (coeffs->n_hist == 0 || hist),
                    "b200sd_cfg_scheduler_step: bad history arguments");
-    B200SD_REQUIRE(coeffs->push_kind == 0 || (hist && coeffs->hist_head >= 0 && coeffs->hist_head < 4),
+    B200SD_REQUIRE(coeffs->push_eps_slot < 4 && coeffs->push_x0_slot < 4 && coeffs->push_x_slot < 4 &&
+                       (hist || (coeffs->push_eps_slot < 0 && coeffs->push_x0_slot < 0 && coeffs->push_x_slot < 0)),
                    "b200sd_cfg_scheduler_step: bad history ring slot");
     const int numel = n * c * h * w;
     cfg_step_kernel<<<(numel + 255) / 256, 256, 0, stream>>>(noise_pred, latents, hist, denoised,

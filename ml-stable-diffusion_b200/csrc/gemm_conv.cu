@@ -32,7 +32,7 @@ struct __align__(64) GemmParams {
     int kb_total, kb_per_split, splits;
     int m_tiles, n_tiles, block_n, stages;
     int n_img, Hout, Wout, stride, bw_log2, bh_log2, tiles_w, tiles_h;
-    int bias_rows, geglu, out_f32;
+    int bias_rows, bias_stride, geglu, out_f32;
     void* out;
     const float* bias;
     const __half* residual;
@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) umma_gemm_kernel(const __grid
                 valid = (on < p.n_img) && (oy < p.Hout) && (ox < p.Wout);
                 out_row = (on * p.Hout + oy) * p.Wout + ox;
             }
-            const int bias_base = (p.bias_rows > 0 && valid) ? (out_row / p.bias_rows) * p.N : 0;
+            const int bias_base = (p.bias_rows > 0 && valid) ? (out_row / p.bias_rows) * p.bias_stride : 0;
             mbar_wait(&tmem_full[as], aphase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_group * 32) << 16) + as * 256;
@@ -326,7 +326,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) umma_gemm_kernel(const __grid
 
 // Sums split-K partials and applies the same epilogue (bias, residual); no GEGLU.
 __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int splits, int M, int N,
-                                     const float* __restrict__ bias, int bias_rows,
+                                     const float* __restrict__ bias, int bias_rows, int bias_stride,
                                      const __half* __restrict__ residual, void* __restrict__ out, int out_f32) {
     const size_t total4 = static_cast<size_t>(M) * N / 4;
     const size_t stride = static_cast<size_t>(M) * N;
@@ -341,7 +341,7 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int spli
         const int row = static_cast<int>(e / N);
         const int col = static_cast<int>(e - static_cast<size_t>(row) * N);
         if (bias != nullptr) {
-            const float* b = bias + (bias_rows > 0 ? (row / bias_rows) * N : 0) + col;
+            const float* b = bias + (bias_rows > 0 ? (row / bias_rows) * bias_stride : 0) + col;
             acc.x += b[0], acc.y += b[1], acc.z += b[2], acc.w += b[3];
         }
         if (residual != nullptr) {
@@ -532,6 +532,7 @@ static int launch_gemm(const b200sd_gemm_args& a, cudaStream_t stream) {
     p.tiles_w = pl.tiles_w;
     p.tiles_h = pl.tiles_h;
     p.bias_rows = a.bias_rows;
+    p.bias_stride = a.bias_stride > 0 ? a.bias_stride : a.n;
     p.geglu = a.geglu;
     p.out_f32 = a.out_f32;
     p.out = a.out;
@@ -555,6 +556,7 @@ static int launch_gemm(const b200sd_gemm_args& a, cudaStream_t stream) {
         const size_t total4 = static_cast<size_t>(pl.M) * a.n / 4;
         const int rgrid = static_cast<int>(std::min<size_t>((total4 + 255) / 256, static_cast<size_t>(num_sms()) * 8));
         splitk_reduce_kernel<<<rgrid, 256, 0, stream>>>(a.workspace, pl.splits, pl.M, a.n, a.bias, a.bias_rows,
+                                                        a.bias_stride > 0 ? a.bias_stride : a.n,
                                                         reinterpret_cast<const __half*>(a.residual), a.out, a.out_f32);
         B200SD_CHECK_CUDA(cudaGetLastError());
         count_launch(1);

@@ -21,7 +21,8 @@ class GemmArgs(C.Structure):
     _fields_ = [
         ("mode", C.c_int32), ("m", C.c_int32), ("n", C.c_int32), ("c0", C.c_int32), ("c1", C.c_int32),
         ("n_img", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("stride", C.c_int32),
-        ("geglu", C.c_int32), ("out_f32", C.c_int32), ("bias_rows", C.c_int32), ("split_k", C.c_int32),
+        ("geglu", C.c_int32), ("out_f32", C.c_int32), ("bias_rows", C.c_int32), ("bias_stride", C.c_int32),
+        ("split_k", C.c_int32),
         ("block_n", C.c_int32),
         ("a0", C.c_void_p), ("a1", C.c_void_p), ("wgt", C.c_void_p), ("bias", C.c_void_p),
         ("residual", C.c_void_p), ("out", C.c_void_p), ("workspace", C.c_void_p),
@@ -32,8 +33,8 @@ class GemmArgs(C.Structure):
 class StepCoeffs(C.Structure):
     _fields_ = [
         ("guidance", C.c_float), ("cx", C.c_float), ("ce", C.c_float), ("ch", C.c_float * 4),
-        ("x0_cx", C.c_float), ("x0_ce", C.c_float), ("n_hist", C.c_int32), ("push_kind", C.c_int32),
-        ("hist_head", C.c_int32),
+        ("x0_cx", C.c_float), ("x0_ce", C.c_float), ("x0_ch", C.c_float * 4), ("n_hist", C.c_int32),
+        ("push_eps_slot", C.c_int32), ("push_x0_slot", C.c_int32), ("push_x_slot", C.c_int32),
     ]
 
 
@@ -127,7 +128,7 @@ def _req(t, dtype, what):
 
 
 def gemm_args(mode, a0, wgt, out, *, a1=None, bias=None, residual=None, m=0, n=0, n_img=0, h=0, w=0, stride=1,
-              geglu=False, bias_rows=0, split_k=0, block_n=0, workspace=None):
+              geglu=False, bias_rows=0, bias_stride=0, split_k=0, block_n=0, workspace=None):
     args = GemmArgs()
     args.mode = mode
     args.m = m
@@ -138,6 +139,7 @@ def gemm_args(mode, a0, wgt, out, *, a1=None, bias=None, residual=None, m=0, n=0
     args.geglu = int(geglu)
     args.out_f32 = int(out.dtype == torch.float32)
     args.bias_rows = bias_rows
+    args.bias_stride = bias_stride
     args.split_k = split_k
     args.block_n = block_n
     args.a0 = a0.data_ptr()
@@ -163,16 +165,22 @@ _ws_cache = {}
 
 
 def _workspace(nbytes, device):
-    key = (device.index, torch.cuda.current_stream().cuda_stream)
+    """Process-wide scratch (split-K partials, GroupNorm statistics).  Kernels that use it are
+    stream-ordered on the single compute stream of the process; it only ever grows (outside of
+    CUDA-graph capture: the warm-up pass sizes it), so captured pointers stay valid."""
+    key = device.index
     ws = _ws_cache.get(key)
     if ws is None or ws.numel() * 4 < nbytes:
-        ws = torch.empty(max(nbytes // 4 + 1, 1 << 22), dtype=torch.float32, device=device)
+        if torch.cuda.is_current_stream_capturing():
+            raise B200SDError("workspace would have to grow during CUDA-graph capture; run one eager "
+                              "warm-up call with the same shapes first")
+        ws = torch.empty(max(nbytes // 4 + 1, 1 << 24), dtype=torch.float32, device=device)
         _ws_cache[key] = ws
     return ws
 
 
 def linear(x, wgt, bias=None, residual=None, *, x1=None, geglu=False, out_dtype=torch.float16, split_k=0,
-           block_n=0, bias_rows=0, out=None):
+           block_n=0, bias_rows=0, bias_stride=0, out=None):
     """out[M, N] = epilogue([x | x1] @ wgt^T).  x [M, C0] fp16, wgt [N, C0(+C1)] fp16, bias fp32 [N]."""
     _req(x, torch.float16, "linear x")
     _req(wgt, torch.float16, "linear wgt")
@@ -181,7 +189,7 @@ def linear(x, wgt, bias=None, residual=None, *, x1=None, geglu=False, out_dtype=
     if out is None:
         out = torch.empty(m, n_out, dtype=out_dtype, device=x.device)
     args = gemm_args(0, x, wgt, out, a1=x1, bias=bias, residual=residual, m=m, n=n, geglu=geglu,
-                     bias_rows=bias_rows, split_k=split_k, block_n=block_n)
+                     bias_rows=bias_rows, bias_stride=bias_stride, split_k=split_k, block_n=block_n)
     need = gemm_workspace_bytes(args)
     if need:
         ws = _workspace(need, x.device)
@@ -192,7 +200,7 @@ def linear(x, wgt, bias=None, residual=None, *, x1=None, geglu=False, out_dtype=
 
 
 def conv3x3(x, wgt, bias=None, residual=None, *, x1=None, stride=1, out_dtype=torch.float16, split_k=0,
-            block_n=0, bias_rows=0, out=None):
+            block_n=0, bias_rows=0, bias_stride=0, out=None):
     """3x3 pad-1 convolution.  x NHWC fp16 [N, H, W, C0]; wgt [Cout, 9*(C0+C1)] fp16 (OHWI);
     bias fp32 [Cout] or [N_img, Cout] with bias_rows = Hout*Wout."""
     _req(x, torch.float16, "conv3x3 x")
@@ -203,7 +211,7 @@ def conv3x3(x, wgt, bias=None, residual=None, *, x1=None, stride=1, out_dtype=to
     if out is None:
         out = torch.empty(nimg, ho, wo, cout, dtype=out_dtype, device=x.device)
     args = gemm_args(1, x, wgt, out, a1=x1, bias=bias, residual=residual, n=cout, n_img=nimg, h=h, w=w,
-                     stride=stride, bias_rows=bias_rows, split_k=split_k, block_n=block_n)
+                     stride=stride, bias_rows=bias_rows, bias_stride=bias_stride, split_k=split_k, block_n=block_n)
     need = gemm_workspace_bytes(args)
     if need:
         ws = _workspace(need, x.device)

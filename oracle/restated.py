@@ -296,7 +296,8 @@ class DPMSolverPP2M:
         self.x0_hist.append(x0)
         self.x0_hist = self.x0_hist[-2:]
         lower_final = (i == self.n - 1) and self.lower_order_final
-        order1 = self.lower_order_nums < 1 or lower_final
+        lower_second = (i == self.n - 2) and self.lower_order_final  # Swift :221-222
+        order1 = self.lower_order_nums < 1 or lower_final or lower_second
         h = self.lam[p] - self.lam[t]
         if order1:
             out = (self.sigma[p] / self.sigma[t]) * x - self.alpha[p] * (torch.exp(-h) - 1.0) * x0

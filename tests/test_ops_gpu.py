@@ -228,7 +228,7 @@ def test_cfg_scheduler_step(cuda_lib):
     k.guidance, k.cx, k.ce = 7.5, 0.9, -0.2
     k.ch[0], k.ch[1] = 0.3, -0.1
     k.x0_cx, k.x0_ce = 1.1, -0.4
-    k.n_hist, k.push_kind, k.hist_head = 2, 2, 3
+    k.n_hist, k.push_eps_slot, k.push_x0_slot, k.push_x_slot = 2, -1, 3, 2
     e = eps[:n] + 7.5 * (eps[n:] - eps[:n])
     ref = 0.9 * x - 0.2 * e + 0.3 * hist[0] - 0.1 * hist[1]
     ref_x0 = 1.1 * x - 0.4 * e
@@ -240,6 +240,6 @@ def test_cfg_scheduler_step(cuda_lib):
     _close(lat, ref, 1e-5, 1e-5, "step latents")
     _close(den, ref_x0, 1e-5, 1e-5, "step x0")
     _close(hist2[3], ref_x0, 1e-5, 1e-5, "history push")
-    assert torch.equal(hist2[:3], hist[:3])
+    assert torch.equal(hist2[:2], hist[:2]) and torch.equal(hist2[2], x)
     want = ref.permute(0, 2, 3, 1).half()
     assert torch.equal(unet_in[:n, ..., :4], want) and torch.equal(unet_in[n:, ..., :4], want)

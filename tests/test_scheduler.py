@@ -1,0 +1,116 @@
+"""Host logic of the fused CFG+scheduler step: the per-step linear coefficients must reproduce the
+oracle's step-by-step scheduler arithmetic (oracle/restated.py, which restates the Swift twins) and
+the closed-form identities available without a runnable reference (parity unpinned)."""
+import numpy as np
+import pytest
+import torch
+
+from b200sd import scheduler as S
+from oracle import restated as R
+
+
+def _run_plan(sched, eps_fn, x0, guidance=7.5):
+    x = x0.copy()
+    hist = [np.zeros_like(x) for _ in range(4)]
+    xs, x0s = [], []
+    for st in sched.plan():
+        eu, ec = eps_fn(x, st.timestep)
+        x, den = S.apply_plan_host(st, guidance, eu, ec, x, hist)
+        xs.append(x.copy())
+        x0s.append(den.copy())
+    return xs, x0s
+
+
+def _eps_fn(seed):
+    rng = np.random.RandomState(seed)
+    w = rng.randn(2, 8).astype(np.float64)
+
+    def f(x, t):
+        base = np.tanh(x * 0.7 + t / 1000.0)
+        return base * w[0, 0] + 0.1, base * w[1, 1] - 0.05
+    return f
+
+
+def test_alphas_cumprod_matches_oracle():
+    a = S.alphas_cumprod()
+    b = R.alphas_cumprod().numpy()
+    assert np.allclose(a, b, rtol=2e-6, atol=0)
+    assert a.shape == (1000,) and 0.99 < a[0] < 1 and a[-1] < 0.01
+
+
+def test_ddim_timesteps_and_identity():
+    s = S.DDIMScheduler(20)
+    s.abar = R.alphas_cumprod().double().numpy()  # same fp32 table on both sides
+    assert s.timesteps == R.leading_timesteps(20) == list(range(951, 0, -50))
+    assert S.DDIMScheduler(50).timesteps[0] == 981  # BASELINE config 1 timestep
+    abar = R.alphas_cumprod().double()
+    rng = np.random.RandomState(0)
+    x = rng.randn(4, 8, 8)
+    f = _eps_fn(1)
+    xs, x0s = _run_plan(s, f, x)
+    xr = torch.from_numpy(x.copy())
+    for i, t in enumerate(s.timesteps):
+        eu, ec = f(xr.numpy(), t)
+        eps = torch.from_numpy(R.cfg_combine(eu, ec, 7.5))
+        a_t = abar[t]
+        x0_ref = (xr - (1 - a_t).sqrt() * eps) / a_t.sqrt()
+        xr = R.ddim_step(eps, t, xr, abar, 20)
+        assert np.allclose(xs[i], xr.numpy(), rtol=1e-9, atol=1e-9)
+        assert np.allclose(x0s[i], x0_ref.numpy(), rtol=1e-9, atol=1e-9)
+
+
+@pytest.mark.parametrize("n", [20, 10, 50, 14, 15])
+def test_dpm_matches_oracle(n):
+    s = S.DPMSolverMultistepScheduler(n)
+    s.abar = R.alphas_cumprod().double().numpy()
+    ref = R.DPMSolverPP2M(n, abar=R.alphas_cumprod().double())
+    assert s.timesteps == ref.timesteps
+    rng = np.random.RandomState(0)
+    x = rng.randn(4, 8, 8)
+    f = _eps_fn(2)
+    xs, x0s = _run_plan(s, f, x)
+    xr = torch.from_numpy(x.copy())
+    for i, t in enumerate(ref.timesteps):
+        eu, ec = f(xr.numpy(), t)
+        xr = ref.step(torch.from_numpy(R.cfg_combine(eu, ec, 7.5)), i, xr)
+        assert np.allclose(xs[i], xr.numpy(), rtol=1e-8, atol=1e-8), (n, i)
+        assert np.allclose(x0s[i], ref.x0_hist[-1].numpy(), rtol=1e-8, atol=1e-8)
+
+
+def test_dpm_first_order_equals_ddim_update():
+    # DPMSolverMultistepScheduler.swift:153-174 "equivalent to DDIM": with the same (t, t_prev) pair the
+    # first-order DPM-Solver++ update and the DDIM eta=0 update coincide
+    abar = S.alphas_cumprod().astype(np.float64)
+    for t, p in [(951, 901), (501, 451), (51, 1)]:
+        a, s = np.sqrt(abar), np.sqrt(1 - abar)
+        lam = np.log(a) - np.log(s)
+        h = lam[p] - lam[t]
+        x, eps = 0.37, -1.2
+        x0 = (x - s[t] * eps) / a[t]
+        dpm = (s[p] / s[t]) * x - a[p] * (np.exp(-h) - 1) * x0
+        ddim = a[p] * x0 + s[p] * eps
+        assert abs(dpm - ddim) < 1e-12
+
+
+@pytest.mark.parametrize("n", [20, 10, 50, 4])
+def test_pndm_matches_oracle(n):
+    s = S.PNDMScheduler(n)
+    s.abar = R.alphas_cumprod().double().numpy()
+    ref = R.PNDM(n, abar=R.alphas_cumprod().double())
+    assert s.timesteps == ref.timesteps and len(s.timesteps) == n + 1
+    if n == 20:
+        assert s.timesteps[:4] == [951, 901, 901, 851]
+    rng = np.random.RandomState(0)
+    x = rng.randn(4, 8, 8)
+    f = _eps_fn(3)
+    xs, _ = _run_plan(s, f, x)
+    xr = torch.from_numpy(x.copy())
+    for i, t in enumerate(ref.timesteps):
+        eu, ec = f(xr.numpy(), t)
+        xr = ref.step(torch.from_numpy(R.cfg_combine(eu, ec, 7.5)), t, xr)
+        assert np.allclose(xs[i], xr.numpy(), rtol=1e-8, atol=1e-8), (n, i)
+
+
+def test_unknown_scheduler():
+    with pytest.raises(ValueError):
+        S.make_scheduler("Euler", 20)
