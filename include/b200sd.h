@@ -107,6 +107,11 @@ size_t b200sd_group_norm_workspace_bytes(int32_t n_img, int32_t hw, int32_t c, i
 int b200sd_layer_norm(const void* x, const float* gamma, const float* beta, void* out, int32_t rows,
                       int32_t c, float eps, void* stream);
 
+/* row softmax of fp32 scores [rows, cols] -> fp16 probabilities, exp2 domain; used only for the VAE
+ * decoder's single-head d=512 mid-block attention (diffusers AutoencoderKL via torch2coreml.py:584-594),
+ * whose Q K^T and P V products run on b200sd_gemm. */
+int b200sd_softmax_rows(const float* in, void* out, int32_t rows, int32_t cols, float scale, void* stream);
+
 /* ---- attention ------------------------------------------------------------------------------
  * softmax(q k^T / sqrt(d) [+ mask]) v per (batch, head): attention.py:24-168 (all three
  * AttentionImplementations compute this function) via Einsum (unet.py:45-59).
@@ -163,6 +168,12 @@ int b200sd_cfg_scheduler_step(const float* noise_pred, float* latents, float* hi
                               float* denoised /* x0 out or NULL */, void* unet_in, int32_t c_pad,
                               int32_t n, int32_t c, int32_t h, int32_t w,
                               const b200sd_step_coeffs* coeffs /* host */, void* stream);
+
+/* VAE decoder input: out = post_quant_conv(z * inv_scale) as NHWC fp16 padded to c_pad channels
+ * (pipeline.py:313-316 `z / 0.18215`; torch2coreml.py:590-594 post_quant_conv); z fp32 NCHW, c <= 8,
+ * w fp32 [c, c], b fp32 [c]. */
+int b200sd_latent_prep(const float* z, const float* w, const float* b, float inv_scale, void* out, int32_t n,
+                       int32_t c, int32_t h, int32_t wd, int32_t c_pad, void* stream);
 
 /* VAE post-process: clip(x/2+0.5,0,1) (pipeline.py:317) NHWC fp16/32 -> NHWC fp32 [n,h,w,3] and/or u8 */
 int b200sd_image_postprocess(const void* in, int32_t in_f32, int32_t c_pad, float* out_f32, uint8_t* out_u8,

@@ -211,6 +211,27 @@ __global__ void image_post_kernel(const T* __restrict__ in, int c_pad, float* __
     }
 }
 
+
+// ---- latent prep for the VAE decoder: z/scaling -> post_quant_conv (1x1, <= 8 channels) -> NHWC fp16 ----
+__global__ void latent_prep_kernel(const float* __restrict__ z, const float* __restrict__ w /* [c, c] */,
+                                   const float* __restrict__ b, float inv_scale, __half* __restrict__ out, int n, int c,
+                                   int hw, int c_pad) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * hw) return;
+    const int p = i % hw, img = i / hw;
+    float v[8];
+#pragma unroll
+    for (int ci = 0; ci < 8; ++ci) v[ci] = ci < c ? z[(static_cast<size_t>(img) * c + ci) * hw + p] * inv_scale : 0.f;
+    for (int co = 0; co < c_pad; ++co) {
+        float acc = 0.f;
+        if (co < c) {
+            acc = b ? b[co] : 0.f;
+            for (int ci = 0; ci < c; ++ci) acc += w[co * c + ci] * v[ci];
+        }
+        out[static_cast<size_t>(i) * c_pad + co] = __float2half_rn(acc);
+    }
+}
+
 }  // namespace b200sd
 
 using namespace b200sd;
@@ -352,6 +373,18 @@ extern "C" int b200sd_image_postprocess(const void* in, int32_t in_f32, int32_t 
     else
         image_post_kernel<__half><<<grid_for(pixels * c, 256), 256, 0, stream>>>(reinterpret_cast<const __half*>(in),
                                                                                  c_pad, out_f32, out_u8, pixels, c);
+    B200SD_CHECK_CUDA(cudaGetLastError());
+    count_launch(1);
+    return 0;
+}
+
+extern "C" int b200sd_latent_prep(const float* z, const float* w, const float* b, float inv_scale, void* out,
+                                  int32_t n, int32_t c, int32_t h, int32_t wd, int32_t c_pad, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    B200SD_REQUIRE(z && w && out && c >= 1 && c <= 8 && c_pad >= c, "b200sd_latent_prep: bad arguments");
+    const int total = n * h * wd;
+    latent_prep_kernel<<<(total + 255) / 256, 256, 0, stream>>>(z, w, b, inv_scale, reinterpret_cast<__half*>(out), n,
+                                                               c, h * wd, c_pad);
     B200SD_CHECK_CUDA(cudaGetLastError());
     count_launch(1);
     return 0;

@@ -15,7 +15,7 @@ namespace b200sd {
 extern void count_launch(int n);
 
 static constexpr int kGnThreads = 256;
-static constexpr int kGnMaxChunks = 64;
+static constexpr int kGnMaxChunks = 256;
 
 // ---- GroupNorm pass 1: per (image, chunk-of-pixels) partial (count, mean, M2) per group ----
 // grid = (chunks, n_img); each block walks its pixels with all channels (coalesced 16 B loads),
@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const __half* __re
 
 static int gn_chunks(int hw, int c) {
     // enough blocks to fill the machine, at most kGnMaxChunks, at least ~32 pixels per chunk
-    int chunks = std::min(kGnMaxChunks, std::max(1, hw / 32));
+    int chunks = std::min(kGnMaxChunks, std::max(1, hw / 64));
     (void)c;
     return chunks;
 }
@@ -245,6 +245,35 @@ __global__ void __launch_bounds__(256) layer_norm_kernel(const __half* __restric
     }
 }
 
+
+// ---- row softmax: fp32 scores [rows, cols] -> fp16 probabilities (VAE mid-block attention, d=512) ----
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ in, __half* __restrict__ out,
+                                                           int cols, float scale_log2) {
+    const size_t row = blockIdx.x;
+    const float* src = in + row * cols;
+    __half* dst = out + row * cols;
+    __shared__ float red[8];
+    float m = -INFINITY;
+    for (int c = threadIdx.x; c < cols; c += blockDim.x) m = fmaxf(m, src[c] * scale_log2);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    m = red[0];
+    for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
+    __syncthreads();
+    float s = 0.f;
+    for (int c = threadIdx.x; c < cols; c += blockDim.x) s += exp2f(src[c] * scale_log2 - m);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    s = 0.f;
+    for (int i = 0; i < 8; ++i) s += red[i];
+    const float inv = 1.0f / s;
+    for (int c = threadIdx.x; c < cols; c += blockDim.x) dst[c] = __float2half_rn(exp2f(src[c] * scale_log2 - m) * inv);
+}
+
 }  // namespace b200sd
 
 using namespace b200sd;
@@ -300,6 +329,17 @@ extern "C" int b200sd_layer_norm(const void* x, const float* gamma, const float*
         layer_norm_kernel<5><<<blocks, 256, 0, stream>>>(xi, gamma, beta, xo, rows, c, eps);
     else
         layer_norm_kernel<8><<<blocks, 256, 0, stream>>>(xi, gamma, beta, xo, rows, c, eps);
+    B200SD_CHECK_CUDA(cudaGetLastError());
+    count_launch(1);
+    return 0;
+}
+
+extern "C" int b200sd_softmax_rows(const float* in, void* out, int32_t rows, int32_t cols, float scale,
+                                   void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    B200SD_REQUIRE(in && out && rows > 0 && cols > 0, "b200sd_softmax_rows: bad arguments");
+    softmax_rows_kernel<<<rows, 256, 0, stream>>>(in, reinterpret_cast<__half*>(out), cols,
+                                                  scale * 1.4426950408889634f);
     B200SD_CHECK_CUDA(cudaGetLastError());
     count_launch(1);
     return 0;

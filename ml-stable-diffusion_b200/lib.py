@@ -54,6 +54,9 @@ _SIGNATURES = {
     "b200sd_group_norm_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "b200sd_layer_norm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                     C.c_float, C.c_void_p]),
+    "b200sd_softmax_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_void_p]),
+    "b200sd_latent_prep": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_int32, C.c_int32,
+                                     C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "b200sd_attention": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                    C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                    C.c_int32, C.c_float, C.c_int32, C.c_void_p]),
@@ -348,3 +351,22 @@ def image_postprocess(x, c=3, want_u8=False):
     _check(load().b200sd_image_postprocess(_ptr(x), int(x.dtype == torch.float32), c_pad, _ptr(of), _ptr(ou), n, h,
                                            w, c, _stream()), "b200sd_image_postprocess")
     return (of, ou) if want_u8 else of
+
+
+def softmax_rows(scores, scale, out=None):
+    _req(scores, torch.float32, "softmax_rows scores")
+    rows, cols = scores.shape
+    if out is None:
+        out = torch.empty(rows, cols, dtype=torch.float16, device=scores.device)
+    _check(load().b200sd_softmax_rows(_ptr(scores), _ptr(out), rows, cols, float(scale), _stream()),
+           "b200sd_softmax_rows")
+    return out
+
+
+def latent_prep(z, w, b, inv_scale, c_pad=8):
+    _req(z, torch.float32, "latent_prep z")
+    n, c, h, wd = z.shape
+    out = torch.empty(n, h, wd, c_pad, dtype=torch.float16, device=z.device)
+    _check(load().b200sd_latent_prep(_ptr(z), _ptr(w), _ptr(b), float(inv_scale), _ptr(out), n, c, h, wd, c_pad,
+                                     _stream()), "b200sd_latent_prep")
+    return out

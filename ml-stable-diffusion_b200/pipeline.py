@@ -1,0 +1,238 @@
+"""Text-to-image pipeline with the reference's call surface, running on the B200 kernels.
+
+Mirrors ``CoreMLStableDiffusionPipeline.__call__`` (``python_coreml_stable_diffusion/pipeline.py:403-589``):
+same keyword arguments, same order of operations (encode -> latents -> [CFG-duplicated UNet ->
+guidance -> scheduler.step] x N -> VAE decode -> clip -> NHWC -> PIL), same
+``StableDiffusionPipelineOutput(images, nsfw_content_detected)`` result.  Differences, all by design:
+
+* the loop body stays on the GPU: UNet (CUDA graph), then ONE fused kernel for guidance + scheduler
+  step; there is no per-step host round trip (the reference crosses numpy<->Core ML twice per step);
+* batches of prompts are accepted (the reference raises ``NotImplementedError``, pipeline.py:434-438;
+  BASELINE config 3 needs 8 prompts per GPU);
+* the CLIP text encoder / tokenizer are not part of this round's hot path: prompts
+  are turned into *synthetic* 77-token embeddings by ``SyntheticTextEncoder`` unless the caller
+  passes ``prompt_embeds`` or installs a real ``text_encoder`` callable with the reference contract
+  (``input_ids`` float32 (1, 77) -> ``last_hidden_state`` (1, 77, D), pipeline.py:151-175).
+"""
+from __future__ import annotations
+
+import dataclasses
+import hashlib
+from typing import List, Optional, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import config as C
+from . import lib as L
+from . import scheduler as S
+from .model import UNetModel
+from .vae import VAEDecoderModel
+
+
+@dataclasses.dataclass
+class StableDiffusionPipelineOutput:
+    images: Union[List, np.ndarray]
+    nsfw_content_detected: Optional[List[bool]]
+
+
+class SyntheticTokenizer:
+    """Deterministic stand-in for the CLIP BPE tokenizer: whitespace words -> ids by hash, padded to
+    ``model_max_length`` with the end-of-text id (same padding convention as pipeline.py:151-158)."""
+    model_max_length = 77
+    bos, eos, vocab = 49406, 49407, 49408
+
+    def __call__(self, text: str):
+        ids = [self.bos]
+        for wd in text.lower().split()[: self.model_max_length - 2]:
+            ids.append(int.from_bytes(hashlib.sha256(wd.encode()).digest()[:4], "little") % (self.bos - 1) + 1)
+        ids.append(self.eos)
+        ids += [self.eos] * (self.model_max_length - len(ids))
+        return np.array([ids], dtype=np.float32)  # the reference feeds input_ids as float32 (pipeline.py:173)
+
+
+class SyntheticTextEncoder:
+    """Maps token ids to fixed pseudo-random unit-variance embeddings (no weights exist offline)."""
+
+    def __init__(self, hidden=1024, seq=77):
+        self.hidden, self.seq = hidden, seq
+        self.expected_inputs = {"input_ids": {"shape": (1, seq), "dtype": np.dtype(np.float32)}}
+
+    def __call__(self, input_ids):
+        out = np.empty((1, self.seq, self.hidden), dtype=np.float32)
+        for i, tok in enumerate(np.asarray(input_ids).reshape(-1).astype(np.int64)):
+            out[0, i] = np.random.RandomState(int(tok) * 131 + i).standard_normal(self.hidden)
+        return {"last_hidden_state": out}
+
+
+class B200StableDiffusionPipeline:
+    """Drop-in for ``CoreMLStableDiffusionPipeline`` on one B200."""
+
+    def __init__(self, unet: UNetModel, vae_decoder: VAEDecoderModel, scheduler="DDIM", text_encoder=None,
+                 tokenizer=None, force_zeros_for_empty_prompt=True, xl=False):
+        self.unet = unet
+        self.vae_decoder = vae_decoder
+        self.scheduler_name = scheduler
+        self.device = unet.device
+        self.xl = xl
+        d_ctx = unet.engine.cfg["cross_attention_dim"]
+        self.text_encoder = text_encoder or SyntheticTextEncoder(d_ctx, unet.seq)
+        self.tokenizer = tokenizer or SyntheticTokenizer()
+        self.force_zeros_for_empty_prompt = force_zeros_for_empty_prompt
+        self.vae_scale_factor = vae_decoder.scale
+        self.height = unet.h * self.vae_scale_factor
+        self.width = unet.w * self.vae_scale_factor
+        self.images_per_call = unet.batch // 2
+        n, c, h, w = self.images_per_call, unet.in_channels, unet.h, unet.w
+        dev = self.device
+        self._latents = torch.zeros(n, c, h, w, dtype=torch.float32, device=dev)
+        self._hist = torch.zeros(4, n, c, h, w, dtype=torch.float32, device=dev)
+        self._denoised = torch.zeros(n, c, h, w, dtype=torch.float32, device=dev)
+        self._ctx = torch.zeros(2 * n, d_ctx, 1, unet.seq, dtype=torch.float16, device=dev)
+        self._t = torch.zeros(2 * n, dtype=torch.float32, device=dev)
+
+    # ---------------------------------------------------------------- factory
+    @classmethod
+    def from_random_init(cls, model_version="sd21-base", images_per_call=1, device="cuda", seed=0,
+                         scheduler="DDIM", height=512, width=512, unet_cfg=None, vae_cfg=None):
+        """Random-init weights of the named architecture (no checkpoints exist offline)."""
+        unet_cfg = unet_cfg or {"sd21-base": C.SD21_BASE_UNET, "sdxl-base": C.SDXL_BASE_UNET,
+                                "tiny": C.TINY_UNET}[model_version]
+        vae_cfg = vae_cfg or (C.TINY_VAE if model_version == "tiny" else C.SD_VAE)
+        f = 2 ** (len(vae_cfg["block_out_channels"]) - 1)
+        usd = C.random_state_dict(C.unet_param_shapes(unet_cfg), seed=seed, dtype=torch.float16)
+        vsd = C.random_state_dict(C.vae_decoder_param_shapes(vae_cfg), seed=seed + 1, dtype=torch.float16)
+        unet = UNetModel(unet_cfg, usd, batch=2 * images_per_call, height=height // f, width=width // f,
+                         device=device)
+        vae = VAEDecoderModel(vae_cfg, vsd, batch=images_per_call, height=height // f, width=width // f,
+                              device=device)
+        return cls(unet, vae, scheduler=scheduler, xl=unet.engine.xl)
+
+    # ---------------------------------------------------------------- reference-named helpers
+    def check_inputs(self, prompt, height, width, callback_steps):
+        """pipeline.py:359-382."""
+        if not isinstance(prompt, (str, list)):
+            raise ValueError(f"`prompt` has to be of type `str` or `list` but is {type(prompt)}")
+        if height % 8 != 0 or width % 8 != 0:
+            raise ValueError(f"`height` and `width` have to be divisible by 8 but are {height} and {width}.")
+        if callback_steps is None or not isinstance(callback_steps, int) or callback_steps <= 0:
+            raise ValueError(f"`callback_steps` has to be a positive integer but is {callback_steps} of type "
+                             f"{type(callback_steps)}.")
+
+    def _encode_one(self, text):
+        ids = self.tokenizer(text)
+        return np.asarray(self.text_encoder(input_ids=ids)["last_hidden_state"], dtype=np.float32)[0]  # (S, D)
+
+    def _encode_prompt(self, prompts, do_cfg, negative_prompt):
+        """-> (2B, D, 1, S) fp16 array, uncond half first (pipeline.py:123-257: concat [neg, pos], :252 transpose)."""
+        conds = [self._encode_one(p) for p in prompts]
+        negs = negative_prompt if isinstance(negative_prompt, list) else [negative_prompt or ""] * len(prompts)
+        unconds = []
+        for ng, cnd in zip(negs, conds):
+            if not do_cfg:
+                unconds.append(cnd)
+            elif ng == "" and self.force_zeros_for_empty_prompt:
+                unconds.append(np.zeros_like(cnd))  # pipeline.py:183-184
+            else:
+                unconds.append(self._encode_one(ng))
+        emb = np.stack(unconds + conds, 0)  # (2B, S, D)
+        return np.ascontiguousarray(emb.transpose(0, 2, 1)[:, :, None, :]).astype(np.float16)
+
+    def prepare_latents(self, batch, channels, height, width, latents=None):
+        """pipeline.py:322-344: np.random.randn(...).astype(fp16) * init_noise_sigma."""
+        shape = (batch, channels, height // self.vae_scale_factor, width // self.vae_scale_factor)
+        if latents is None:
+            latents = np.random.randn(*shape).astype(np.float16)
+        elif tuple(latents.shape) != shape:
+            raise ValueError(f"Unexpected latents shape, got {latents.shape}, expected {shape}")
+        return latents.astype(np.float32) * 1.0
+
+    @staticmethod
+    def numpy_to_pil(images):
+        from PIL import Image
+        images = (images * 255).round().astype("uint8")
+        return [Image.fromarray(im) for im in images]
+
+    # ---------------------------------------------------------------- device loop
+    def denoise(self, text_embeddings, latents, num_inference_steps, guidance_scale, callback=None,
+                callback_steps=1, time_ids=None, text_embeds=None, return_denoised=False):
+        """Runs the N-step loop entirely on the device.  ``text_embeddings`` (2B, D, 1, S) and ``latents``
+        (B, C, h, w) may be numpy (copied once, before the loop) or CUDA tensors."""
+        sched = S.make_scheduler(self.scheduler_name, num_inference_steps)
+        n = self.images_per_call
+        self._ctx.copy_(torch.as_tensor(text_embeddings), non_blocking=True)
+        self._latents.copy_(torch.as_tensor(latents), non_blocking=True)
+        self._hist.zero_()
+        k = L.StepCoeffs()
+        for i, st in enumerate(sched.plan()):
+            self._t.fill_(float(st.timestep))
+            sample = torch.cat([self._latents, self._latents], 0)  # pipeline.py:502
+            noise_pred = self.unet.forward_device(sample, self._t, self._ctx, time_ids, text_embeds)
+            k.guidance = float(guidance_scale)
+            k.cx, k.ce, k.x0_cx, k.x0_ce = st.cx, st.ce, st.x0_cx, st.x0_ce
+            for j in range(4):
+                k.ch[j] = st.ch[j]
+                k.x0_ch[j] = st.x0_ch[j]
+            k.n_hist, k.push_eps_slot, k.push_x0_slot, k.push_x_slot = (st.n_hist, st.push_eps_slot,
+                                                                        st.push_x0_slot, st.push_x_slot)
+            L.cfg_scheduler_step(noise_pred, self._latents, k, hist=self._hist, denoised=self._denoised)
+            if callback is not None and i % callback_steps == 0:
+                callback(i, st.timestep, self._latents)
+        return self._denoised if return_denoised else self._latents
+
+    def decode_latents(self, latents):
+        """pipeline.py:313-320 on the device: z / scaling -> decoder -> clip(x/2+0.5, 0, 1) -> NHWC fp32."""
+        eng = self.vae_decoder.engine
+        self.vae_decoder._z.copy_(latents)
+        self.vae_decoder._z.mul_(1.0 / eng.scaling)
+        img = eng.forward(self.vae_decoder._z)
+        return L.image_postprocess(img, c=eng.out_ch)
+
+    # ---------------------------------------------------------------- public API
+    def __call__(self, prompt, height=512, width=512, num_inference_steps=50, guidance_scale=7.5,
+                 negative_prompt=None, num_images_per_prompt=1, eta=0.0, latents=None, output_type="pil",
+                 return_dict=True, callback=None, callback_steps=1, controlnet_cond=None,
+                 original_size: Optional[Tuple[int, int]] = None, crops_coords_top_left: Tuple[int, int] = (0, 0),
+                 target_size: Optional[Tuple[int, int]] = None, unet_batch_one=False, prompt_embeds=None, **kwargs):
+        self.check_inputs(prompt, height, width, callback_steps)
+        height = height or self.height
+        width = width or self.width
+        if (height, width) != (self.height, self.width):
+            raise ValueError(f"this pipeline instance was built for {self.height}x{self.width} images")
+        if eta != 0.0:
+            raise ValueError("only eta = 0 (deterministic DDIM) is implemented")
+        if controlnet_cond is not None:
+            raise NotImplementedError("ControlNet conditioning is not wired into this pipeline yet")
+        prompts = [prompt] if isinstance(prompt, str) else list(prompt)
+        prompts = [p for p in prompts for _ in range(num_images_per_prompt)]
+        if len(prompts) != self.images_per_call:
+            raise ValueError(f"this pipeline instance generates {self.images_per_call} image(s) per call, "
+                             f"got {len(prompts)} prompt(s)")
+        do_cfg = guidance_scale > 1.0  # pipeline.py:443
+        if prompt_embeds is None:
+            text_embeddings = self._encode_prompt(prompts, do_cfg, negative_prompt)
+        else:
+            text_embeddings = prompt_embeds
+        time_ids = text_embeds = None
+        if self.xl:
+            original_size = original_size or (height, width)
+            target_size = target_size or (height, width)
+            ids = list(original_size) + list(crops_coords_top_left) + list(target_size)
+            time_ids = torch.tensor([ids] * (2 * self.images_per_call), dtype=torch.float32, device=self.device)
+            text_embeds = kwargs.get("pooled_prompt_embeds")
+            if text_embeds is None:
+                text_embeds = torch.zeros(2 * self.images_per_call, 1280, device=self.device)
+        lat = self.prepare_latents(len(prompts), self.unet.in_channels, height, width, latents)
+        final = self.denoise(text_embeddings, lat, num_inference_steps, guidance_scale, callback, callback_steps,
+                             time_ids, text_embeds)
+        image = self.decode_latents(final).cpu().numpy()  # single device->host copy of the result
+        has_nsfw = None  # the safety checker is out of scope
+        if output_type == "pil":
+            image = self.numpy_to_pil(image)
+        if not return_dict:
+            return (image, has_nsfw)
+        return StableDiffusionPipelineOutput(images=image, nsfw_content_detected=has_nsfw)
+
+    def generate(self, prompt, num_inference_steps=50, guidance_scale=7.5, **kwargs):
+        """Alias named in BASELINE.json's north_star."""
+        return self(prompt, num_inference_steps=num_inference_steps, guidance_scale=guidance_scale, **kwargs)

@@ -1,0 +1,159 @@
+"""GPU parity of the whole hot path against the oracle: UNet forward (tiny config vs the oracle run
+live; SD-2.1-base vs the golden output produced by the unmodified reference), the model-call boundary,
+the VAE decoder and the end-to-end pipeline.  Tolerances: north_star's 1e-2 max-abs (fp16 storage,
+fp32 accumulate) and the reference's own PSNR >= 35 dB criterion (torch2coreml.py:77-97)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from b200sd import config
+from oracle import restated as R
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+MAX_ABS, MIN_PSNR = 1e-2, 35.0
+
+
+def _inputs(cfg, seed, batch=2, seq=77):
+    g = torch.Generator().manual_seed(seed)
+    s = cfg["sample_size"]
+    x = torch.randn(batch, cfg["in_channels"], s, s, generator=g)
+    c = torch.randn(batch, cfg["cross_attention_dim"], 1, seq, generator=g)
+    return x, c
+
+
+def _check(out, ref, what, max_abs=MAX_ABS):
+    err = float(np.abs(out - ref).max())
+    psnr = R.compute_psnr(torch.from_numpy(np.asarray(out)), torch.from_numpy(np.asarray(ref)))
+    print(f"{what}: max_abs={err:.3e} psnr={psnr:.1f} dB (ref absmax {np.abs(ref).max():.3f})")
+    assert np.isfinite(out).all(), what
+    assert err <= max_abs and psnr >= MIN_PSNR, f"{what}: max_abs={err:.3e} psnr={psnr:.1f}"
+
+
+@pytest.mark.parametrize("impl", ["ORIGINAL", "SPLIT_EINSUM", "SPLIT_EINSUM_V2"])
+def test_unet_tiny_vs_oracle_and_golden(cuda_lib, impl):
+    from b200sd import unet as U
+    from b200sd.model import UNetModel
+
+    U.ATTENTION_IMPLEMENTATION_IN_EFFECT = U.AttentionImplementations[impl]
+    cfg = config.TINY_UNET
+    gold = np.load(os.path.join(GOLD, "unet_tiny.npz"))
+    sd = config.random_state_dict(config.unet_param_shapes(cfg), seed=int(gold["weight_seed"]))
+    x, c = _inputs(cfg, int(gold["input_seed"]))
+    t = np.array([float(gold["timestep"])] * 2, np.float16)
+    m = UNetModel(cfg, sd, batch=2, height=16, width=16, use_cuda_graph=False)
+    out = m(sample=x.half().numpy(), timestep=t, encoder_hidden_states=c.half().numpy())["noise_pred"]
+    assert out.dtype == np.float32 and out.shape == (2, 4, 16, 16)
+    _check(out, gold[f"noise_pred_{impl}"], f"tiny unet vs reference golden [{impl}]")
+    with torch.no_grad():
+        live = R.unet_forward(sd, cfg, x, torch.tensor([981.0, 981.0]), c).numpy()
+    _check(out, live, f"tiny unet vs live oracle [{impl}]")
+
+
+def test_unet_tiny_cuda_graph_equals_eager_and_validates(cuda_lib):
+    from b200sd.model import UNetModel
+
+    cfg = config.TINY_UNET
+    sd = config.random_state_dict(config.unet_param_shapes(cfg), seed=3)
+    x, c = _inputs(cfg, 4)
+    t = np.array([501.0, 21.0], np.float16)
+    kw = dict(sample=x.half().numpy(), timestep=t, encoder_hidden_states=c.half().numpy())
+    eager = UNetModel(cfg, sd, batch=2, height=16, width=16, use_cuda_graph=False)(**kw)["noise_pred"]
+    gm = UNetModel(cfg, sd, batch=2, height=16, width=16, use_cuda_graph=True)
+    g1 = gm(**kw)["noise_pred"]
+    g2 = gm(**kw)["noise_pred"]
+    assert np.array_equal(eager, g1) and np.array_equal(g1, g2)
+    assert gm.launches_per_call and gm.launches_per_call > 50
+    # per-row timesteps really differ
+    kw2 = dict(kw, timestep=np.array([501.0, 501.0], np.float16))
+    assert not np.array_equal(gm(**kw2)["noise_pred"][1], g1[1])
+    # boundary validation mirrors CoreMLModel._verify_inputs (coreml_model.py:97-116)
+    with pytest.raises(TypeError):
+        gm(**dict(kw, sample=x.numpy()))  # fp32 instead of fp16
+    with pytest.raises(TypeError):
+        gm(**dict(kw, sample=x.half().numpy()[:1]))
+    with pytest.raises(ValueError):
+        gm(bogus=np.zeros(1, np.float16), **kw)
+    with pytest.raises(TypeError):
+        gm(**dict(kw, sample=[1, 2, 3]))
+
+
+def test_unet_sd21_base_vs_reference_golden(cuda_lib):
+    """BASELINE configs[0] parity case: SD-2.1-base, bs=2, 64x64 latents, t=981."""
+    from b200sd.model import UNetModel
+
+    cfg = config.SD21_BASE_UNET
+    gold = np.load(os.path.join(GOLD, "unet_sd21.npz"))
+    sd = config.random_state_dict(config.unet_param_shapes(cfg), seed=int(gold["weight_seed"]))
+    x, c = _inputs(cfg, int(gold["input_seed"]))
+    t = np.array([float(gold["timestep"])] * 2, np.float16)
+    m = UNetModel(cfg, sd, batch=2, height=64, width=64, use_cuda_graph=True)
+    out = m(sample=x.half().numpy(), timestep=t, encoder_hidden_states=c.half().numpy())["noise_pred"]
+    _check(out, gold["noise_pred_ORIGINAL"], "SD-2.1-base unet vs reference golden")
+
+
+def test_unet_tiny_controlnet_residuals(cuda_lib):
+    from b200sd.model import UNetModel
+
+    cfg = dict(config.TINY_UNET, support_controlnet=True)
+    sd = config.random_state_dict(config.unet_param_shapes(cfg), seed=5)
+    x, c = _inputs(cfg, 6)
+    m = UNetModel(cfg, sd, batch=2, height=16, width=16, use_cuda_graph=False)
+    g = torch.Generator().manual_seed(7)
+    res = [torch.randn(s, generator=g) * 0.5 for s in m.residual_shapes()]
+    assert len(res) == 7  # conv_in + (res[, down]) per level + mid (controlnet.py:218-229 order)
+    kw = {f"additional_residual_{i}": r.half().numpy() for i, r in enumerate(res)}
+    out = m(sample=x.half().numpy(), timestep=np.array([301.0, 301.0], np.float16),
+            encoder_hidden_states=c.half().numpy(), **kw)["noise_pred"]
+    with torch.no_grad():
+        ref = R.unet_forward(sd, cfg, x, torch.tensor([301.0, 301.0]), c, additional_residuals=res).numpy()
+    _check(out, ref, "tiny control-unet")
+
+
+def test_vae_decoder_tiny_vs_oracle(cuda_lib):
+    from b200sd.vae import VAEDecoderModel
+
+    cfg = config.TINY_VAE
+    sd = config.random_state_dict(config.vae_decoder_param_shapes(cfg), seed=3)
+    z = torch.randn(1, 4, 16, 16, generator=torch.Generator().manual_seed(1))
+    m = VAEDecoderModel(cfg, sd, batch=1, height=16, width=16)
+    img = m(z=z.half().numpy())["image"]
+    assert img.shape == (1, 3, 64, 64)
+    with torch.no_grad():
+        ref = R.vae_decode(sd, cfg, z).numpy()
+    _check(img, ref, "tiny vae decoder", max_abs=2e-2 * max(1.0, float(np.abs(ref).max())))
+
+
+def test_pipeline_tiny_end_to_end_vs_oracle(cuda_lib):
+    """20-step DDIM txt2img on the tiny models vs the same loop run with the oracle on the CPU."""
+    from b200sd.pipeline import B200StableDiffusionPipeline
+    from b200sd import scheduler as S
+
+    pipe = B200StableDiffusionPipeline.from_random_init("tiny", images_per_call=1, height=64, width=64, seed=11)
+    np.random.seed(93)
+    lat0 = np.random.randn(1, 4, 16, 16).astype(np.float16)
+    steps, g = 6, 7.5
+    res = pipe("a photo of an astronaut riding a horse", height=64, width=64, num_inference_steps=steps,
+               guidance_scale=g, latents=lat0, output_type="np")
+    img = res.images
+    assert img.shape == (1, 64, 64, 3) and img.min() >= 0 and img.max() <= 1
+    # oracle loop
+    ucfg, vcfg = config.TINY_UNET, config.TINY_VAE
+    usd = config.random_state_dict(config.unet_param_shapes(ucfg), seed=11, dtype=torch.float16)
+    vsd = config.random_state_dict(config.vae_decoder_param_shapes(vcfg), seed=12, dtype=torch.float16)
+    emb = torch.from_numpy(pipe._encode_prompt(["a photo of an astronaut riding a horse"], True, None)).float()
+    x = torch.from_numpy(lat0.astype(np.float32))
+    abar = R.alphas_cumprod()
+    with torch.no_grad():
+        for t in S.DDIMScheduler(steps).timesteps:
+            eps = R.unet_forward(usd, ucfg, torch.cat([x, x]).half().float(), torch.tensor([float(t)] * 2), emb)
+            x = R.ddim_step(R.cfg_combine(eps[:1], eps[1:], g), t, x, abar, steps)
+        ref = R.postprocess_image(R.vae_decode(vsd, vcfg, x / 0.18215)).numpy()
+    err = float(np.abs(img - ref).max())
+    print(f"pipeline tiny: image max_abs={err:.3e}")
+    assert err < 3e-2
+    # PIL output + generate() alias + return_dict=False
+    out = pipe.generate("x", num_inference_steps=2, guidance_scale=7.5, height=64, width=64, return_dict=False)
+    assert out[1] is None and out[0][0].size == (64, 64)
