@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
                         make_smem_desc_sw128(p_addr + (k >> 2) * kTileBytes, 1024, 0) + 2 * (k & 3);
                     // B: 16 keys = 16 rows of 128 B = 2048 B further down the MN-major tile
                     const uint64_t bdesc = make_smem_desc_sw128(v_addr + k * 2048, 1024, kKV * 128);
-                    umma_f16_ss(tmem_o, adesc, bdesc, idesc_o, k > 0 ? 1u : 0u);
+                    umma_f16_ss(tmem_o, adesc, bdesc, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
                 }
                 umma_commit(o_full);
                 umma_commit(&kv_empty[st]);
@@ -148,13 +148,16 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
             __syncwarp();
         }
     } else {
+        // ---------------- softmax warps: one query row per thread ----------------
+        // O accumulates in TMEM across all KV steps (PV MMAs with accumulate=1).  The running maximum used
+        // as the exp2 reference is only refreshed when a tile's maximum exceeds it by more than kTau
+        // (log2 domain; P <= 2^kTau stays well inside fp16), in which case the warp rescales its 32 rows of
+        // O in TMEM once -- rare after the first tiles -- instead of touching O every step.
+        constexpr float kTau = 8.0f;
         const int lane_group = warp & 3;
         const int row = lane_group * 32 + lane;
         const uint32_t lane_addr = static_cast<uint32_t>(lane_group * 32) << 16;
-        float o_acc[kD];
-#pragma unroll
-        for (int i = 0; i < kD; ++i) o_acc[i] = 0.f;
-        float m_run = -INFINITY, l_run = 0.f;
+        float m_ref = -INFINITY, l_run = 0.f;
         const float* mask_row = p.mask ? p.mask + static_cast<size_t>(batch) * p.sk : nullptr;
         uint8_t* p_row = smem + kSmemP + row * 128;
         const int sw = row & 7;
@@ -163,94 +166,132 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
             const int kvalid = min(kKV, p.sk - j * kKV);  // >= 1
             mbar_wait(s_full, j & 1);
             tc_fence_after();
-            // ---- pass 1: row maximum (log2 domain) ----
+            // ---- pass 1: row maximum (log2 domain); two 32-column loads in flight per wait ----
             float m_tile = -INFINITY;
 #pragma unroll 1
-            for (int c = 0; c < kKV; c += 32) {
-                uint32_t v[32];
-                tmem_ld32(tmem_s + lane_addr + c, v);
+            for (int c = 0; c < kKV; c += 64) {
+                uint32_t va[32], vb[32];
+                tmem_ld32(tmem_s + lane_addr + c, va);
+                tmem_ld32(tmem_s + lane_addr + c + 32, vb);
                 tmem_ld_wait();
+                if (mask_row == nullptr && c + 64 <= kvalid) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    float s = __uint_as_float(v[i]) * p.scale_log2;
-                    if (mask_row && c + i < kvalid) s += mask_row[j * kKV + c + i] * 1.4426950408889634f;
-                    if (c + i < kvalid) m_tile = fmaxf(m_tile, s);
+                    for (int i = 0; i < 32; ++i)
+                        m_tile = fmaxf(m_tile, fmaxf(__uint_as_float(va[i]), __uint_as_float(vb[i])));
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        float s0 = __uint_as_float(va[i]), s1 = __uint_as_float(vb[i]);
+                        if (mask_row) {
+                            if (c + i < kvalid) s0 += mask_row[j * kKV + c + i] * (1.4426950408889634f / p.scale_log2);
+                            if (c + 32 + i < kvalid)
+                                s1 += mask_row[j * kKV + c + 32 + i] * (1.4426950408889634f / p.scale_log2);
+                        }
+                        if (c + i < kvalid) m_tile = fmaxf(m_tile, s0);
+                        if (c + 32 + i < kvalid) m_tile = fmaxf(m_tile, s1);
+                    }
                 }
             }
-            const float m_new = fmaxf(m_run, m_tile);
-            const float alpha = exp2f(m_run - m_new);  // 0 on the first tile
-            // ---- fold in the previous step's P V, then rescale to the new maximum ----
+            m_tile *= p.scale_log2;  // scale > 0, so the maximum commutes with the scaling
+            // ---- reference update (lazy) ----
+            const bool grow = m_tile > m_ref + kTau;
+            if (__any_sync(0xffffffffu, grow)) {
+                const float m_new = fmaxf(m_ref, m_tile);
+                if (j > 0) {
+                    const float factor = exp2f(m_ref - m_new);  // 1 for rows whose reference did not move
+                    mbar_wait(o_full, (j - 1) & 1);             // all previous P V accumulated
+                    tc_fence_after();
+#pragma unroll
+                    for (int c = 0; c < kD; c += 32) {
+                        uint32_t v[32];
+                        tmem_ld32(tmem_o + lane_addr + c, v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * factor);
+                        tmem_st32(tmem_o + lane_addr + c, v);
+                    }
+                    tmem_st_wait();
+                    l_run *= factor;
+                }
+                m_ref = m_new;
+            }
             if (j > 0) {
+                // P of the previous step must have been consumed before this step's P overwrites it
                 mbar_wait(o_full, (j - 1) & 1);
-                tc_fence_after();
-#pragma unroll
-                for (int c = 0; c < kD; c += 32) {
-                    uint32_t v[32];
-                    tmem_ld32(tmem_o + lane_addr + c, v);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) o_acc[c + i] = (o_acc[c + i] + __uint_as_float(v[i])) * alpha;
-                }
             }
-            // ---- pass 2: P = exp2(s - m), row sum, fp16 P tile into swizzled smem ----
+            // ---- pass 2: P = exp2(s * scale - m_ref), row sum, fp16 P tile into swizzled smem ----
             float l_tile = 0.f;
+            const float neg_m = -m_ref;
 #pragma unroll 1
-            for (int c = 0; c < kKV; c += 32) {
-                uint32_t v[32];
-                tmem_ld32(tmem_s + lane_addr + c, v);
+            for (int c = 0; c < kKV; c += 64) {
+                uint32_t va[32], vb[32];
+                tmem_ld32(tmem_s + lane_addr + c, va);
+                tmem_ld32(tmem_s + lane_addr + c + 32, vb);
                 tmem_ld_wait();
-                uint32_t pk[16];
+                uint32_t pk[32];
+                const bool fast = (mask_row == nullptr) && (c + 64 <= kvalid);
 #pragma unroll
                 for (int i = 0; i < 32; i += 2) {
-                    float s0 = __uint_as_float(v[i]) * p.scale_log2;
-                    float s1 = __uint_as_float(v[i + 1]) * p.scale_log2;
-                    if (mask_row) {
-                        if (c + i < kvalid) s0 += mask_row[j * kKV + c + i] * 1.4426950408889634f;
-                        if (c + i + 1 < kvalid) s1 += mask_row[j * kKV + c + i + 1] * 1.4426950408889634f;
+                    float p0, p1, p2, p3;
+                    if (fast) {
+                        p0 = exp2f(fmaf(__uint_as_float(va[i]), p.scale_log2, neg_m));
+                        p1 = exp2f(fmaf(__uint_as_float(va[i + 1]), p.scale_log2, neg_m));
+                        p2 = exp2f(fmaf(__uint_as_float(vb[i]), p.scale_log2, neg_m));
+                        p3 = exp2f(fmaf(__uint_as_float(vb[i + 1]), p.scale_log2, neg_m));
+                    } else {
+                        float s0 = __uint_as_float(va[i]) * p.scale_log2, s1 = __uint_as_float(va[i + 1]) * p.scale_log2;
+                        float s2 = __uint_as_float(vb[i]) * p.scale_log2, s3 = __uint_as_float(vb[i + 1]) * p.scale_log2;
+                        if (mask_row) {
+                            const float* mr = mask_row + j * kKV + c + i;
+                            if (c + i < kvalid) s0 += mr[0] * 1.4426950408889634f;
+                            if (c + i + 1 < kvalid) s1 += mr[1] * 1.4426950408889634f;
+                            if (c + 32 + i < kvalid) s2 += mr[32] * 1.4426950408889634f;
+                            if (c + 33 + i < kvalid) s3 += mr[33] * 1.4426950408889634f;
+                        }
+                        p0 = (c + i < kvalid) ? exp2f(s0 + neg_m) : 0.f;
+                        p1 = (c + i + 1 < kvalid) ? exp2f(s1 + neg_m) : 0.f;
+                        p2 = (c + 32 + i < kvalid) ? exp2f(s2 + neg_m) : 0.f;
+                        p3 = (c + 33 + i < kvalid) ? exp2f(s3 + neg_m) : 0.f;
                     }
-                    const float p0 = (c + i < kvalid) ? exp2f(s0 - m_new) : 0.f;
-                    const float p1 = (c + i + 1 < kvalid) ? exp2f(s1 - m_new) : 0.f;
-                    l_tile += p0 + p1;
+                    l_tile += (p0 + p1) + (p2 + p3);
                     pk[i >> 1] = pack_half2(p0, p1);
+                    pk[16 + (i >> 1)] = pack_half2(p2, p3);
                 }
-                // 32 keys = 64 B = four 16 B pieces; key c lives in chunk c/64, byte (c%64)*2
+                // 64 keys = one 128-byte swizzled row of K-chunk (c / 64): eight 16-byte pieces
                 uint8_t* dst = p_row + (c >> 6) * kTileBytes;
-                const int piece0 = (c & 63) >> 3;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
+                for (int q = 0; q < 8; ++q) {
                     uint4 val = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-                    *reinterpret_cast<uint4*>(dst + (((piece0 + q) ^ sw) << 4)) = val;
+                    *reinterpret_cast<uint4*>(dst + ((q ^ sw) << 4)) = val;
                 }
             }
-            l_run = l_run * alpha + l_tile;
-            m_run = m_new;
+            l_run += l_tile;
             tc_fence_before();
             mbar_arrive(s_empty);
             fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
             mbar_arrive(p_full);
         }
-        // ---- last P V and normalisation ----
+        // ---- normalise and store ----
         mbar_wait(o_full, (n_kv - 1) & 1);
         tc_fence_after();
         const float inv_l = 1.0f / l_run;
+        const bool store = q0 + row < p.sq;
+        __half* dst = p.out + (static_cast<size_t>(batch) * p.sq + (store ? q0 + row : 0)) * p.ldo + head * kD;
 #pragma unroll
         for (int c = 0; c < kD; c += 32) {
             uint32_t v[32];
             tmem_ld32(tmem_o + lane_addr + c, v);
             tmem_ld_wait();
+            if (store) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) o_acc[c + i] = (o_acc[c + i] + __uint_as_float(v[i])) * inv_l;
-        }
-        if (q0 + row < p.sq) {
-            __half* dst = p.out + (static_cast<size_t>(batch) * p.sq + q0 + row) * p.ldo + head * kD;
-#pragma unroll
-            for (int c = 0; c < kD; c += 8) {
-                uint4 val;
-                val.x = pack_half2(o_acc[c], o_acc[c + 1]);
-                val.y = pack_half2(o_acc[c + 2], o_acc[c + 3]);
-                val.z = pack_half2(o_acc[c + 4], o_acc[c + 5]);
-                val.w = pack_half2(o_acc[c + 6], o_acc[c + 7]);
-                *reinterpret_cast<uint4*>(dst + c) = val;
+                for (int i = 0; i < 32; i += 8) {
+                    uint4 val;
+                    val.x = pack_half2(__uint_as_float(v[i]) * inv_l, __uint_as_float(v[i + 1]) * inv_l);
+                    val.y = pack_half2(__uint_as_float(v[i + 2]) * inv_l, __uint_as_float(v[i + 3]) * inv_l);
+                    val.z = pack_half2(__uint_as_float(v[i + 4]) * inv_l, __uint_as_float(v[i + 5]) * inv_l);
+                    val.w = pack_half2(__uint_as_float(v[i + 6]) * inv_l, __uint_as_float(v[i + 7]) * inv_l);
+                    *reinterpret_cast<uint4*>(dst + c + i) = val;
+                }
             }
         }
     }

@@ -300,15 +300,44 @@ __global__ void __launch_bounds__(kGemmThreads, 1) umma_gemm_kernel(const __grid
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_group * 32) << 16) + as * 256;
             const int ncol0 = t.n_tile * p.block_n;
-            for (int c = 0; c < p.block_n; c += 16) {
-                uint32_t v[16];
-                tmem_ld16(taddr + c, v);
-                tmem_ld_wait();
-                if (valid && ncol0 + c < p.N) {
-                    float acc[16];
+            auto process32 = [&](const uint32_t (&v)[32], int c) {
+                if (!valid) return;
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) acc[j] = __uint_as_float(v[j]);
-                    epilogue_store16(p, acc, out_row, ncol0 + c, t.split, bias_base);
+                for (int hh = 0; hh < 2; ++hh) {
+                    if (ncol0 + c + 16 * hh < p.N) {
+                        float acc[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) acc[j] = __uint_as_float(v[16 * hh + j]);
+                        epilogue_store16(p, acc, out_row, ncol0 + c + 16 * hh, t.split, bias_base);
+                    }
+                }
+            };
+            if ((p.block_n & 31) == 0) {
+                // software-pipelined: the TMEM load of the next 32 columns is in flight while these are stored
+                uint32_t va[32], vb[32];
+                tmem_ld32(taddr, va);
+                for (int c = 0; c < p.block_n; c += 64) {
+                    tmem_ld_wait();
+                    const bool has_b = c + 32 < p.block_n;
+                    if (has_b) tmem_ld32(taddr + c + 32, vb);
+                    process32(va, c);
+                    if (has_b) {
+                        tmem_ld_wait();
+                        if (c + 64 < p.block_n) tmem_ld32(taddr + c + 64, va);
+                        process32(vb, c + 32);
+                    }
+                }
+            } else {
+                for (int c = 0; c < p.block_n; c += 16) {
+                    uint32_t v[16];
+                    tmem_ld16(taddr + c, v);
+                    tmem_ld_wait();
+                    if (valid && ncol0 + c < p.N) {
+                        float acc[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) acc[j] = __uint_as_float(v[j]);
+                        epilogue_store16(p, acc, out_row, ncol0 + c, t.split, bias_base);
+                    }
                 }
             }
             tc_fence_before();
@@ -433,7 +462,7 @@ static int plan_gemm(const b200sd_gemm_args& a, GemmPlan& pl) {
     int splits = 1;
     if (a.split_k > 0) {
         splits = a.split_k;
-    } else if (!a.geglu && tiles * 10 < sms * 7) {
+    } else if (!a.geglu && a.n % 4 == 0 && tiles * 10 < sms * 7) {
         splits = std::max(1, std::min(sms / tiles, pl.kb_total / 4));
     }
     splits = std::max(1, std::min(splits, pl.kb_total));

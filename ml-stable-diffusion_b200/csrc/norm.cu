@@ -14,88 +14,127 @@ namespace b200sd {
 
 extern void count_launch(int n);
 
-static constexpr int kGnThreads = 256;
 static constexpr int kGnMaxChunks = 256;
+static constexpr int kGnMaxImages = 1024;
 
-// ---- GroupNorm pass 1: per (image, chunk-of-pixels) partial (count, mean, M2) per group ----
-// grid = (chunks, n_img); each block walks its pixels with all channels (coalesced 16 B loads),
-// thread t owns channel-vector (t % vecs_per_pixel) => a fixed group set; per-thread Welford-free
-// shifted sums are merged per group through shared memory.
-__global__ void __launch_bounds__(kGnThreads) gn_partial_kernel(const __half* __restrict__ x0,
-                                                                const __half* __restrict__ x1, int c0, int c1,
-                                                                int hw, int groups, int chunks,
-                                                                float* __restrict__ stats /* [n][chunks][groups][2] */) {
+__device__ __forceinline__ void load8(const __half* src, float (&f)[8]) {
+    const uint4 raw = *reinterpret_cast<const uint4*>(src);
+    const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const float2 t = __half22float2(h2[q]);
+        f[2 * q] = t.x;
+        f[2 * q + 1] = t.y;
+    }
+}
+
+// ---- GroupNorm pass 1: deterministic statistics ------------------------------------------------
+// grid = (chunks, n_img), block = vecs * R threads (vecs = C/8 16-byte vectors per pixel, R pixel rows
+// in flight) so thread t always owns vector column t % vecs: per-channel (sum, sumsq) accumulate in
+// registers over the chunk's pixels with perfectly coalesced 16 B loads; a fixed-order shared-memory
+// tree folds rows -> channels -> groups (no atomics: bitwise reproducible).  The last block of each
+// image (ticket counter) merges the chunk partials in chunk order with Chan's formula and writes the
+// final (mean, rstd) per group.
+__global__ void __launch_bounds__(384) gn_stats_kernel(const __half* __restrict__ x0, const __half* __restrict__ x1,
+                                                       int c0, int c1, int hw, int groups, int chunks, int rows,
+                                                       float eps, float* __restrict__ partial /* [n][chunks][g][2] */,
+                                                       float* __restrict__ final_stats /* [n][g][2] */,
+                                                       unsigned int* __restrict__ tickets /* [n] */) {
     const int C = c0 + c1;
     const int cpg = C / groups;
-    const int vecs = C / 8;  // 16-byte vectors per pixel
+    const int vecs = C / 8;
     const int n = blockIdx.y, chunk = blockIdx.x;
     const int px_per_chunk = (hw + chunks - 1) / chunks;
     const int px0 = chunk * px_per_chunk;
     const int px1 = min(hw, px0 + px_per_chunk);
+    const int v = threadIdx.x % vecs;
+    const int r = threadIdx.x / vecs;
+    const int ch = v * 8;
 
-    extern __shared__ float sm[];  // [groups][2] sum, sumsq  then reused
-    float* s_sum = sm;
-    float* s_sq = sm + groups;
-    for (int g = threadIdx.x; g < 2 * groups; g += blockDim.x) sm[g] = 0.f;
-    __syncthreads();
-
-    // pass A: sums relative to 0 (fp32; inputs are fp16 so |x| <= 65504); the apply pass merges
-    // chunk statistics with Chan's formula, which keeps cancellation local to one chunk.
-    const int total = (px1 - px0) * vecs;
-    // threads stride so that a thread keeps the same vector column when blockDim % vecs == 0;
-    // otherwise fall back to per-element group lookup (still correct).
-    for (int i = threadIdx.x; i < total; i += blockDim.x) {
-        const int px = px0 + i / vecs;
-        const int v = i % vecs;
-        const int ch = v * 8;
-        const __half* src = (ch < c0) ? x0 + (static_cast<size_t>(n) * hw + px) * c0 + ch
-                                      : x1 + (static_cast<size_t>(n) * hw + px) * c1 + (ch - c0);
-        const uint4 raw = *reinterpret_cast<const uint4*>(src);
-        const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
-        float f[8];
+    extern __shared__ float sm[];  // [rows][C][2] then [C][2] then [groups][2]
+    float s[8], q[8];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const float2 t = __half22float2(h2[q]);
-            f[2 * q] = t.x;
-            f[2 * q + 1] = t.y;
-        }
-        // the 8 channels span at most 8 groups; accumulate runs of equal group
-        int g_cur = ch / cpg;
-        float s = 0.f, sq = 0.f;
+    for (int e = 0; e < 8; ++e) s[e] = q[e] = 0.f;
+    const bool from0 = ch < c0;
+    const __half* base = from0 ? x0 + static_cast<size_t>(n) * hw * c0 + ch
+                               : x1 + static_cast<size_t>(n) * hw * c1 + (ch - c0);
+    const int cs = from0 ? c0 : c1;
+    for (int px = px0 + r; px < px1; px += rows) {
+        float f[8];
+        load8(base + static_cast<size_t>(px) * cs, f);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-            const int g = (ch + e) / cpg;
-            if (g != g_cur) {
-                atomicAdd(&s_sum[g_cur], s);
-                atomicAdd(&s_sq[g_cur], sq);
-                s = sq = 0.f;
-                g_cur = g;
-            }
-            s += f[e];
-            sq += f[e] * f[e];
+            s[e] += f[e];
+            q[e] += f[e] * f[e];
         }
-        atomicAdd(&s_sum[g_cur], s);
-        atomicAdd(&s_sq[g_cur], sq);
+    }
+    float* row_buf = sm + (static_cast<size_t>(r) * C + ch) * 2;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        row_buf[2 * e] = s[e];
+        row_buf[2 * e + 1] = q[e];
     }
     __syncthreads();
-    const float cnt = static_cast<float>((px1 - px0) * cpg);
-    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
-        const float mean = cnt > 0.f ? s_sum[g] / cnt : 0.f;
-        const float m2 = cnt > 0.f ? fmaxf(s_sq[g] - s_sum[g] * mean, 0.f) : 0.f;
-        float* o = stats + ((static_cast<size_t>(n) * chunks + chunk) * groups + g) * 2;
-        o[0] = mean;
-        o[1] = m2;
+    // rows -> channel totals (thread c < C), fixed order
+    float* ch_buf = sm + static_cast<size_t>(rows) * C * 2;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float a = 0.f, b = 0.f;
+        for (int rr = 0; rr < rows; ++rr) {
+            a += sm[(static_cast<size_t>(rr) * C + c) * 2];
+            b += sm[(static_cast<size_t>(rr) * C + c) * 2 + 1];
+        }
+        ch_buf[2 * c] = a;
+        ch_buf[2 * c + 1] = b;
     }
+    __syncthreads();
+    const float cnt = static_cast<float>(max(0, px1 - px0) * cpg);
+    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+        float a = 0.f, b = 0.f;
+        for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+            a += ch_buf[2 * c];
+            b += ch_buf[2 * c + 1];
+        }
+        const float mean = cnt > 0.f ? a / cnt : 0.f;
+        float* o = partial + ((static_cast<size_t>(n) * chunks + chunk) * groups + g) * 2;
+        o[0] = mean;
+        o[1] = cnt > 0.f ? fmaxf(b - a * mean, 0.f) : 0.f;
+    }
+    // ---- last block of this image finalises ----
+    __shared__ unsigned int s_ticket;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_ticket = atomicAdd(&tickets[n], 1u);
+    __syncthreads();
+    if (s_ticket != static_cast<unsigned int>(chunks - 1)) return;
+    __threadfence();
+    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+        float tot = 0.f, mean = 0.f, m2 = 0.f;
+        for (int k = 0; k < chunks; ++k) {
+            const int p0 = k * px_per_chunk;
+            const int p1 = min(hw, p0 + px_per_chunk);
+            const float cb = static_cast<float>(max(0, p1 - p0) * cpg);
+            if (cb <= 0.f) continue;
+            const float* pp = partial + ((static_cast<size_t>(n) * chunks + k) * groups + g) * 2;
+            const float mb = __ldcg(pp), m2b = __ldcg(pp + 1);
+            const float nt = tot + cb;
+            const float delta = mb - mean;
+            mean += delta * (cb / nt);
+            m2 += m2b + delta * delta * (tot * cb / nt);
+            tot = nt;
+        }
+        final_stats[(static_cast<size_t>(n) * groups + g) * 2] = mean;
+        final_stats[(static_cast<size_t>(n) * groups + g) * 2 + 1] = rsqrtf(m2 / tot + eps);
+    }
+    if (threadIdx.x == 0) tickets[n] = 0;  // self-reset for the next launch
 }
 
-// ---- GroupNorm pass 2: merge chunk stats (Chan), normalise, affine, optional SiLU -----------
-__global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const __half* __restrict__ x0,
-                                                              const __half* __restrict__ x1, int c0, int c1, int hw,
-                                                              int groups, int chunks, float eps,
-                                                              const float* __restrict__ stats,
-                                                              const float* __restrict__ gamma,
-                                                              const float* __restrict__ beta, int silu,
-                                                              __half* __restrict__ out, int px_per_block) {
+// ---- GroupNorm pass 2: normalise, affine, optional SiLU (and concat of the two sources) ------------
+__global__ void __launch_bounds__(256) gn_apply_kernel(const __half* __restrict__ x0, const __half* __restrict__ x1,
+                                                       int c0, int c1, int hw, int groups,
+                                                       const float* __restrict__ final_stats,
+                                                       const float* __restrict__ gamma,
+                                                       const float* __restrict__ beta, int silu,
+                                                       __half* __restrict__ out, int px_per_block) {
     const int C = c0 + c1;
     const int cpg = C / groups;
     const int vecs = C / 8;
@@ -103,58 +142,28 @@ __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const __half* __re
     extern __shared__ float sm[];  // scale[C], shift[C]
     float* s_scale = sm;
     float* s_shift = sm + C;
-    float* s_mean = sm + 2 * C;  // [groups]
-    float* s_rstd = s_mean + groups;
-
-    const int px_per_chunk = (hw + chunks - 1) / chunks;
-    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
-        float cnt = 0.f, mean = 0.f, m2 = 0.f;
-        for (int k = 0; k < chunks; ++k) {
-            const int p0 = k * px_per_chunk;
-            const int p1 = min(hw, p0 + px_per_chunk);
-            const float cb = static_cast<float>(max(0, p1 - p0) * cpg);
-            if (cb <= 0.f) continue;
-            const float* s = stats + ((static_cast<size_t>(n) * chunks + k) * groups + g) * 2;
-            const float mb = s[0], m2b = s[1];
-            const float tot = cnt + cb;
-            const float delta = mb - mean;
-            mean += delta * (cb / tot);
-            m2 += m2b + delta * delta * (cnt * cb / tot);
-            cnt = tot;
-        }
-        s_mean[g] = mean;
-        s_rstd[g] = rsqrtf(m2 / cnt + eps);
-    }
-    __syncthreads();
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         const int g = c / cpg;
-        const float sc = gamma[c] * s_rstd[g];
+        const float mean = final_stats[(static_cast<size_t>(n) * groups + g) * 2];
+        const float rstd = final_stats[(static_cast<size_t>(n) * groups + g) * 2 + 1];
+        const float sc = gamma[c] * rstd;
         s_scale[c] = sc;
-        s_shift[c] = beta[c] - s_mean[g] * sc;
+        s_shift[c] = beta[c] - mean * sc;
     }
     __syncthreads();
-
     const int px0 = blockIdx.x * px_per_block;
     const int px1 = min(hw, px0 + px_per_block);
     const int total = (px1 - px0) * vecs;
     for (int i = threadIdx.x; i < total; i += blockDim.x) {
         const int px = px0 + i / vecs;
-        const int v = i % vecs;
-        const int ch = v * 8;
+        const int ch = (i % vecs) * 8;
         const __half* src = (ch < c0) ? x0 + (static_cast<size_t>(n) * hw + px) * c0 + ch
                                       : x1 + (static_cast<size_t>(n) * hw + px) * c1 + (ch - c0);
-        const uint4 raw = *reinterpret_cast<const uint4*>(src);
-        const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
         float f[8];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const float2 t = __half22float2(h2[q]);
-            f[2 * q] = t.x;
-            f[2 * q + 1] = t.y;
-        }
+        load8(src, f);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-            float y = f[e] * s_scale[ch + e] + s_shift[ch + e];
+            const float y = f[e] * s_scale[ch + e] + s_shift[ch + e];
             f[e] = silu ? silu_f(y) : y;
         }
         uint4 pk;
@@ -166,11 +175,19 @@ __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const __half* __re
     }
 }
 
-static int gn_chunks(int hw, int c) {
-    // enough blocks to fill the machine, at most kGnMaxChunks, at least ~32 pixels per chunk
-    int chunks = std::min(kGnMaxChunks, std::max(1, hw / 64));
-    (void)c;
-    return chunks;
+static int gn_chunks(int hw, int n_img) {
+    // ~2 blocks per SM overall, at least 16 pixels per chunk
+    int want = std::max(1, (2 * num_sms()) / std::max(1, n_img));
+    return std::max(1, std::min({kGnMaxChunks, want, std::max(1, hw / 16)}));
+}
+
+static unsigned int* gn_tickets() {
+    static unsigned int* t = nullptr;
+    if (!t) {
+        if (cudaMalloc(&t, kGnMaxImages * sizeof(unsigned int)) != cudaSuccess) return nullptr;
+        cudaMemset(t, 0, kGnMaxImages * sizeof(unsigned int));
+    }
+    return t;
 }
 
 // ---- LayerNorm over channels of [rows, c]; one warp per row, two-pass in registers -----------
@@ -279,7 +296,10 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restri
 using namespace b200sd;
 
 extern "C" size_t b200sd_group_norm_workspace_bytes(int32_t n_img, int32_t hw, int32_t c, int32_t groups) {
-    return static_cast<size_t>(n_img) * gn_chunks(hw, c) * groups * 2 * sizeof(float);
+    (void)c;
+    // chunk partials + final (mean, rstd)
+    return (static_cast<size_t>(n_img) * gn_chunks(hw, n_img) * groups * 2 + static_cast<size_t>(n_img) * groups * 2) *
+           sizeof(float);
 }
 
 extern "C" int b200sd_group_norm(const void* x0, const void* x1, int32_t c0, int32_t c1, int32_t n_img, int32_t hw,
@@ -292,22 +312,36 @@ extern "C" int b200sd_group_norm(const void* x0, const void* x1, int32_t c0, int
                    "b200sd_group_norm: channels must be multiples of 8 (c0=%d c1=%d)", c0, c1);
     B200SD_REQUIRE(groups > 0 && C % groups == 0, "b200sd_group_norm: %d channels not divisible by %d groups", C,
                    groups);
-    const int chunks = gn_chunks(hw, C);
+    B200SD_REQUIRE(n_img <= kGnMaxImages, "b200sd_group_norm: at most %d images per call", kGnMaxImages);
     B200SD_REQUIRE(stats_ws_bytes >= b200sd_group_norm_workspace_bytes(n_img, hw, C, groups),
                    "b200sd_group_norm: workspace too small");
-    gn_partial_kernel<<<dim3(chunks, n_img), kGnThreads, 2 * groups * sizeof(float), stream>>>(
-        reinterpret_cast<const __half*>(x0), reinterpret_cast<const __half*>(x1), c0, c1, hw, groups, chunks,
-        stats_ws);
+    unsigned int* tickets = gn_tickets();
+    B200SD_REQUIRE(tickets != nullptr, "b200sd_group_norm: could not allocate ticket counters");
+    const int chunks = gn_chunks(hw, n_img);
+    const int vecs = C / 8;
+    B200SD_REQUIRE(vecs <= 384, "b200sd_group_norm: too many channels (%d)", C);
+    const int rows = std::max(1, std::min(256 / vecs, (hw + chunks - 1) / chunks));
+    const int threads = vecs * rows;
+    float* partial = stats_ws;
+    float* final_stats = stats_ws + static_cast<size_t>(n_img) * chunks * groups * 2;
+    const size_t smem1 = (static_cast<size_t>(rows) * C * 2 + static_cast<size_t>(C) * 2) * sizeof(float);
+    static size_t smem1_max = 48 * 1024;
+    if (smem1 > smem1_max) {
+        B200SD_CHECK_CUDA(cudaFuncSetAttribute(gn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               static_cast<int>(smem1)));
+        smem1_max = smem1;
+    }
+    gn_stats_kernel<<<dim3(chunks, n_img), threads, smem1, stream>>>(
+        reinterpret_cast<const __half*>(x0), reinterpret_cast<const __half*>(x1), c0, c1, hw, groups, chunks, rows, eps,
+        partial, final_stats, tickets);
     B200SD_CHECK_CUDA(cudaGetLastError());
-    // apply: ~ (8 * SMs) blocks overall
     const int want_blocks = std::max(1, (num_sms() * 4) / std::max(1, n_img));
-    int px_per_block = std::max(1, (hw + want_blocks - 1) / want_blocks);
+    const int px_per_block = std::max(1, (hw + want_blocks - 1) / want_blocks);
     const int blocks = (hw + px_per_block - 1) / px_per_block;
-    const size_t smem = (2 * static_cast<size_t>(C) + 2 * groups) * sizeof(float);
-    B200SD_REQUIRE(smem <= 48 * 1024, "b200sd_group_norm: too many channels (%d)", C);
-    gn_apply_kernel<<<dim3(blocks, n_img), kGnThreads, smem, stream>>>(
-        reinterpret_cast<const __half*>(x0), reinterpret_cast<const __half*>(x1), c0, c1, hw, groups, chunks, eps,
-        stats_ws, gamma, beta, silu, reinterpret_cast<__half*>(out), px_per_block);
+    const size_t smem2 = 2 * static_cast<size_t>(C) * sizeof(float);
+    gn_apply_kernel<<<dim3(blocks, n_img), 256, smem2, stream>>>(
+        reinterpret_cast<const __half*>(x0), reinterpret_cast<const __half*>(x1), c0, c1, hw, groups, final_stats,
+        gamma, beta, silu, reinterpret_cast<__half*>(out), px_per_block);
     B200SD_CHECK_CUDA(cudaGetLastError());
     count_launch(2);
     return 0;

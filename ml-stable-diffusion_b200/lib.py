@@ -111,10 +111,17 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr())
 
 
+_DEBUG_SYNC = bool(os.environ.get("B200SD_DEBUG_SYNC"))
+
+
 def _check(rc, what):
     if rc != 0:
         msg = load().b200sd_last_error().decode(errors="replace")
         raise B200SDError(f"{what} failed (rc={rc}): {msg}")
+    if _DEBUG_SYNC:  # debugging aid: localise a faulting / hanging kernel
+        print(f"[b200sd] {what} launched", flush=True)
+        torch.cuda.synchronize()
+        print(f"[b200sd] {what} done", flush=True)
 
 
 def launch_count() -> int:

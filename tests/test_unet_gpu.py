@@ -64,7 +64,9 @@ def test_unet_tiny_cuda_graph_equals_eager_and_validates(cuda_lib):
     gm = UNetModel(cfg, sd, batch=2, height=16, width=16, use_cuda_graph=True)
     g1 = gm(**kw)["noise_pred"]
     g2 = gm(**kw)["noise_pred"]
-    assert np.array_equal(eager, g1) and np.array_equal(g1, g2)
+    # GroupNorm statistics use shared-memory float atomics (summation order varies run to run), so two
+    # executions agree to rounding, not bitwise
+    assert np.abs(eager - g1).max() < 2e-3 and np.abs(g1 - g2).max() < 2e-3
     assert gm.launches_per_call and gm.launches_per_call > 50
     # per-row timesteps really differ
     kw2 = dict(kw, timestep=np.array([501.0, 501.0], np.float16))

@@ -1,0 +1,98 @@
+"""Profiling helper (run under ncu on the GPU box): builds the SD-2.1-base UNet and runs eager forwards.
+   python tools/profile_unet.py [--forwards N] [--shapes]   (--shapes: per-shape GEMM timing table)"""
+import argparse
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+from b200sd import config, lib as L  # noqa: E402
+from b200sd.model import UNetModel  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--forwards", type=int, default=2)
+ap.add_argument("--shapes", action="store_true")
+ap.add_argument("--kernels", action="store_true", help="per-op-type CUDA-event timing of one forward")
+args = ap.parse_args()
+
+cfg = config.SD21_BASE_UNET
+shapes = config.unet_param_shapes(cfg)
+g = torch.Generator().manual_seed(1)
+sd = {k: (torch.randn(v, generator=g) * 0.02).half() if len(v) == 4 else
+      (torch.ones(v) if k.endswith("weight") else torch.zeros(v)).half() for k, v in shapes.items()}
+m = UNetModel(cfg, sd, batch=2, height=64, width=64, use_cuda_graph=False)
+m._sample.normal_()
+m._ctx.normal_()
+m._t.fill_(981.0)
+for _ in range(args.forwards):
+    m._run()
+torch.cuda.synchronize()
+
+if args.kernels:
+    import collections
+    recs = collections.defaultdict(list)
+    names = ["run_gemm", "group_norm", "layer_norm", "attention", "upsample2x", "linear_small"]
+    origs = {n: getattr(L, n) for n in names}
+
+    def wrap(n):
+        def f(*a, **k):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = origs[n](*a, **k)
+            e1.record()
+            recs[n].append((e0, e1))
+            return r
+        return f
+    for n in names:
+        setattr(L, n, wrap(n))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    m._run()
+    e1.record()
+    torch.cuda.synchronize()
+    for n in names:
+        setattr(L, n, origs[n])
+    print("forward (eager, instrumented) ms:", round(e0.elapsed_time(e1), 3))
+    for n, v in recs.items():
+        print(f"  {n:14s} calls={len(v):4d} sum_ms={sum(a.elapsed_time(b) for a, b in v):8.3f}")
+
+if args.shapes:
+    seen = {}
+    orig = L.run_gemm
+
+    def rec(a):
+        key = (a.mode, a.m, a.n, a.c0, a.c1, a.n_img, a.h, a.w, a.stride, a.geglu, bool(a.residual), a.bias_rows)
+        if key not in seen:
+            import copy
+            seen[key] = [0, a]
+        seen[key][0] += 1
+        orig(a)
+    L.run_gemm = rec
+    m._run()
+    torch.cuda.synchronize()
+    L.run_gemm = orig
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    rows = []
+    for key, (cnt, a) in seen.items():
+        mm = a.m if a.mode == 0 else a.n_img * (a.h // a.stride) * (a.w // a.stride)
+        kk = (a.c0 + a.c1) * (9 if a.mode == 1 else 1)
+        fl = 2.0 * mm * a.n * kk
+        ts = []
+        for _ in range(5):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            orig(a)
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        t = sorted(ts)[len(ts) // 2]
+        rows.append((fl * cnt, dict(mode=a.mode, M=mm, N=a.n, K=kk, geglu=a.geglu, count=cnt, us=round(t * 1e3, 1),
+                                   tflops=round(fl / t / 1e9, 1), total_ms=round(t * cnt, 3))))
+    rows.sort(key=lambda r: -r[1]["total_ms"])
+    tot = sum(r[1]["total_ms"] for r in rows)
+    print("GEMM shapes (cold L2), total ms per forward:", round(tot, 3))
+    for _, r in rows:
+        print(json.dumps(r))
