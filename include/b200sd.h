@@ -30,6 +30,9 @@ extern "C" {
 
 const char* b200sd_last_error(void);
 int b200sd_version(void);
+/* Programmatic dependent launch on/off (default off; env B200SD_PDL=1 enables): lets each kernel's
+ * prologue overlap the previous kernel's tail inside the captured CUDA graph. */
+void b200sd_set_pdl(int enabled);
 /* number of kernels launched by this library since load (bench.py's gpu_launches) */
 uint64_t b200sd_launch_count(void);
 

@@ -84,6 +84,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    pdl_wait();  // PDL: the prologue above overlapped the previous kernel's tail
     const uint32_t tmem_s = tmem_base;        // 128 columns
     const uint32_t tmem_o = tmem_base + 128;  // 64 columns
 
@@ -149,111 +150,64 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
         }
     } else {
         // ---------------- softmax warps: one query row per thread ----------------
-        // O accumulates in TMEM across all KV steps (PV MMAs with accumulate=1).  The running maximum used
-        // as the exp2 reference is only refreshed when a tile's maximum exceeds it by more than kTau
-        // (log2 domain; P <= 2^kTau stays well inside fp16), in which case the warp rescales its 32 rows of
-        // O in TMEM once -- rare after the first tiles -- instead of touching O every step.
+        // O accumulates in TMEM across all KV steps (PV MMAs with accumulate=1).  The exp2 reference m_ref
+        // is refreshed lazily: a full, unmasked tile is exponentiated optimistically against the current
+        // m_ref in ONE pass over S (row maximum tracked on the side); only if some row's maximum exceeds
+        // m_ref by more than kTau (log2 domain; P <= 2^kTau stays inside fp16) does the warp rescale its 32
+        // rows of O in TMEM and redo the tile -- rare after the first tiles.
         constexpr float kTau = 8.0f;
         const int lane_group = warp & 3;
         const int row = lane_group * 32 + lane;
         const uint32_t lane_addr = static_cast<uint32_t>(lane_group * 32) << 16;
+        const uint32_t s_addr = tmem_s + lane_addr;
+        const uint32_t o_addr = tmem_o + lane_addr;
+        const float sl2 = p.scale_log2;
         float m_ref = -INFINITY, l_run = 0.f;
         const float* mask_row = p.mask ? p.mask + static_cast<size_t>(batch) * p.sk : nullptr;
         uint8_t* p_row = smem + kSmemP + row * 128;
         const int sw = row & 7;
 
-        for (int j = 0; j < n_kv; ++j) {
-            const int kvalid = min(kKV, p.sk - j * kKV);  // >= 1
-            mbar_wait(s_full, j & 1);
-            tc_fence_after();
-            // ---- pass 1: row maximum (log2 domain); two 32-column loads in flight per wait ----
-            float m_tile = -INFINITY;
+        // lean row maximum of a full unmasked tile (raw scores)
+        auto row_max_lean = [&]() {
+            float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll 1
             for (int c = 0; c < kKV; c += 64) {
                 uint32_t va[32], vb[32];
-                tmem_ld32(tmem_s + lane_addr + c, va);
-                tmem_ld32(tmem_s + lane_addr + c + 32, vb);
+                tmem_ld32(s_addr + c, va);
+                tmem_ld32(s_addr + c + 32, vb);
                 tmem_ld_wait();
-                if (mask_row == nullptr && c + 64 <= kvalid) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        m_tile = fmaxf(m_tile, fmaxf(__uint_as_float(va[i]), __uint_as_float(vb[i])));
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        float s0 = __uint_as_float(va[i]), s1 = __uint_as_float(vb[i]);
-                        if (mask_row) {
-                            if (c + i < kvalid) s0 += mask_row[j * kKV + c + i] * (1.4426950408889634f / p.scale_log2);
-                            if (c + 32 + i < kvalid)
-                                s1 += mask_row[j * kKV + c + 32 + i] * (1.4426950408889634f / p.scale_log2);
-                        }
-                        if (c + i < kvalid) m_tile = fmaxf(m_tile, s0);
-                        if (c + 32 + i < kvalid) m_tile = fmaxf(m_tile, s1);
-                    }
-                }
-            }
-            m_tile *= p.scale_log2;  // scale > 0, so the maximum commutes with the scaling
-            // ---- reference update (lazy) ----
-            const bool grow = m_tile > m_ref + kTau;
-            if (__any_sync(0xffffffffu, grow)) {
-                const float m_new = fmaxf(m_ref, m_tile);
-                if (j > 0) {
-                    const float factor = exp2f(m_ref - m_new);  // 1 for rows whose reference did not move
-                    mbar_wait(o_full, (j - 1) & 1);             // all previous P V accumulated
-                    tc_fence_after();
-#pragma unroll
-                    for (int c = 0; c < kD; c += 32) {
-                        uint32_t v[32];
-                        tmem_ld32(tmem_o + lane_addr + c, v);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * factor);
-                        tmem_st32(tmem_o + lane_addr + c, v);
-                    }
-                    tmem_st_wait();
-                    l_run *= factor;
-                }
-                m_ref = m_new;
-            }
-            if (j > 0) {
-                // P of the previous step must have been consumed before this step's P overwrites it
-                mbar_wait(o_full, (j - 1) & 1);
-            }
-            // ---- pass 2: P = exp2(s * scale - m_ref), row sum, fp16 P tile into swizzled smem ----
-            float l_tile = 0.f;
-            const float neg_m = -m_ref;
-#pragma unroll 1
-            for (int c = 0; c < kKV; c += 64) {
-                uint32_t va[32], vb[32];
-                tmem_ld32(tmem_s + lane_addr + c, va);
-                tmem_ld32(tmem_s + lane_addr + c + 32, vb);
-                tmem_ld_wait();
-                uint32_t pk[32];
-                const bool fast = (mask_row == nullptr) && (c + 64 <= kvalid);
 #pragma unroll
                 for (int i = 0; i < 32; i += 2) {
-                    float p0, p1, p2, p3;
-                    if (fast) {
-                        p0 = exp2f(fmaf(__uint_as_float(va[i]), p.scale_log2, neg_m));
-                        p1 = exp2f(fmaf(__uint_as_float(va[i + 1]), p.scale_log2, neg_m));
-                        p2 = exp2f(fmaf(__uint_as_float(vb[i]), p.scale_log2, neg_m));
-                        p3 = exp2f(fmaf(__uint_as_float(vb[i + 1]), p.scale_log2, neg_m));
-                    } else {
-                        float s0 = __uint_as_float(va[i]) * p.scale_log2, s1 = __uint_as_float(va[i + 1]) * p.scale_log2;
-                        float s2 = __uint_as_float(vb[i]) * p.scale_log2, s3 = __uint_as_float(vb[i + 1]) * p.scale_log2;
-                        if (mask_row) {
-                            const float* mr = mask_row + j * kKV + c + i;
-                            if (c + i < kvalid) s0 += mr[0] * 1.4426950408889634f;
-                            if (c + i + 1 < kvalid) s1 += mr[1] * 1.4426950408889634f;
-                            if (c + 32 + i < kvalid) s2 += mr[32] * 1.4426950408889634f;
-                            if (c + 33 + i < kvalid) s3 += mr[33] * 1.4426950408889634f;
-                        }
-                        p0 = (c + i < kvalid) ? exp2f(s0 + neg_m) : 0.f;
-                        p1 = (c + i + 1 < kvalid) ? exp2f(s1 + neg_m) : 0.f;
-                        p2 = (c + 32 + i < kvalid) ? exp2f(s2 + neg_m) : 0.f;
-                        p3 = (c + 33 + i < kvalid) ? exp2f(s3 + neg_m) : 0.f;
-                    }
-                    l_tile += (p0 + p1) + (p2 + p3);
+                    m0 = fmaxf(m0, fmaxf(__uint_as_float(va[i]), __uint_as_float(vb[i])));
+                    m1 = fmaxf(m1, fmaxf(__uint_as_float(va[i + 1]), __uint_as_float(vb[i + 1])));
+                }
+            }
+            return fmaxf(m0, m1);
+        };
+        // lean probabilities of a full unmasked tile against reference `ref`: writes the fp16 P tile,
+        // returns the row sum and (through tmax) the raw row maximum
+        auto probs_lean = [&](float ref, float& tmax) {
+            const float neg_m = -ref;
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+            float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll 1
+            for (int c = 0; c < kKV; c += 64) {
+                uint32_t va[32], vb[32];
+                tmem_ld32(s_addr + c, va);
+                tmem_ld32(s_addr + c + 32, vb);
+                tmem_ld_wait();
+                uint32_t pk[32];
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    const float a0 = __uint_as_float(va[i]), a1 = __uint_as_float(va[i + 1]);
+                    const float b0 = __uint_as_float(vb[i]), b1 = __uint_as_float(vb[i + 1]);
+                    m0 = fmaxf(m0, fmaxf(a0, b0));
+                    m1 = fmaxf(m1, fmaxf(a1, b1));
+                    const float p0 = ex2_approx(fmaf(a0, sl2, neg_m));
+                    const float p1 = ex2_approx(fmaf(a1, sl2, neg_m));
+                    const float p2 = ex2_approx(fmaf(b0, sl2, neg_m));
+                    const float p3 = ex2_approx(fmaf(b1, sl2, neg_m));
+                    s0 += p0, s1 += p1, s2 += p2, s3 += p3;
                     pk[i >> 1] = pack_half2(p0, p1);
                     pk[16 + (i >> 1)] = pack_half2(p2, p3);
                 }
@@ -263,6 +217,95 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
                 for (int q = 0; q < 8; ++q) {
                     uint4 val = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
                     *reinterpret_cast<uint4*>(dst + ((q ^ sw) << 4)) = val;
+                }
+            }
+            tmax = fmaxf(m0, m1);
+            return (s0 + s1) + (s2 + s3);
+        };
+        // rescale this warp's rows of O (TMEM) and the running sum from reference m_ref to m_new
+        auto rescale_o = [&](float m_new) {
+            const float factor = ex2_approx(m_ref - m_new);  // 1 for rows whose reference did not move
+#pragma unroll
+            for (int c = 0; c < kD; c += 32) {
+                uint32_t v[32];
+                tmem_ld32(o_addr + c, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * factor);
+                tmem_st32(o_addr + c, v);
+            }
+            tmem_st_wait();
+            l_run *= factor;
+        };
+
+        for (int j = 0; j < n_kv; ++j) {
+            const int kvalid = min(kKV, p.sk - j * kKV);  // >= 1
+            mbar_wait(s_full, j & 1);
+            if (j > 0) mbar_wait(o_full, (j - 1) & 1);  // P V of the previous step done: P buffer and O are quiescent
+            tc_fence_after();
+            float l_tile;
+            if (mask_row == nullptr && kvalid == kKV) {
+                if (j == 0) {
+                    m_ref = row_max_lean() * sl2;
+                    float unused;
+                    l_tile = probs_lean(m_ref, unused);
+                } else {
+                    float tmax;
+                    l_tile = probs_lean(m_ref, tmax);
+                    const float m_tile = tmax * sl2;
+                    if (__any_sync(0xffffffffu, m_tile > m_ref + kTau)) {
+                        const float m_new = fmaxf(m_ref, m_tile);
+                        rescale_o(m_new);
+                        m_ref = m_new;
+                        l_tile = probs_lean(m_ref, tmax);
+                    }
+                }
+            } else {
+                // ---- general tile (additive mask and/or ragged tail): two passes with per-key predicates ----
+                float m_tile = -INFINITY;
+#pragma unroll 1
+                for (int c = 0; c < kKV; c += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(s_addr + c, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        float sc = __uint_as_float(v[i]) * sl2;
+                        if (mask_row && c + i < kvalid) sc += mask_row[j * kKV + c + i] * 1.4426950408889634f;
+                        if (c + i < kvalid) m_tile = fmaxf(m_tile, sc);
+                    }
+                }
+                if (__any_sync(0xffffffffu, m_tile > m_ref + kTau)) {
+                    const float m_new = fmaxf(m_ref, m_tile);
+                    if (j > 0) rescale_o(m_new);
+                    m_ref = m_new;
+                }
+                l_tile = 0.f;
+#pragma unroll 1
+                for (int c = 0; c < kKV; c += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(s_addr + c, v);
+                    tmem_ld_wait();
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int i = 0; i < 32; i += 2) {
+                        float s0 = __uint_as_float(v[i]) * sl2, s1 = __uint_as_float(v[i + 1]) * sl2;
+                        if (mask_row) {
+                            if (c + i < kvalid) s0 += mask_row[j * kKV + c + i] * 1.4426950408889634f;
+                            if (c + i + 1 < kvalid) s1 += mask_row[j * kKV + c + i + 1] * 1.4426950408889634f;
+                        }
+                        const float p0 = (c + i < kvalid) ? ex2_approx(s0 - m_ref) : 0.f;
+                        const float p1 = (c + i + 1 < kvalid) ? ex2_approx(s1 - m_ref) : 0.f;
+                        l_tile += p0 + p1;
+                        pk[i >> 1] = pack_half2(p0, p1);
+                    }
+                    uint8_t* dst = p_row + (c >> 6) * kTileBytes;
+                    const int piece0 = (c & 63) >> 3;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        uint4 val = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                        *reinterpret_cast<uint4*>(dst + (((piece0 + q) ^ sw) << 4)) = val;
+                    }
                 }
             }
             l_run += l_tile;
@@ -280,7 +323,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
 #pragma unroll
         for (int c = 0; c < kD; c += 32) {
             uint32_t v[32];
-            tmem_ld32(tmem_o + lane_addr + c, v);
+            tmem_ld32(o_addr + c, v);
             tmem_ld_wait();
             if (store) {
 #pragma unroll
@@ -296,6 +339,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
         }
     }
 
+    pdl_trigger();
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
@@ -356,7 +400,7 @@ extern "C" int b200sd_attention(const void* q, const void* k, const void* v, voi
         attr_set = true;
     }
     dim3 grid((sq + kQ - 1) / kQ, heads, batch);
-    attention_kernel<<<grid, kAttnThreads, kAttnSmemBytes, stream>>>(p);
+    B200SD_CHECK_CUDA(launch_kernel(attention_kernel, dim3(grid), dim3(kAttnThreads), kAttnSmemBytes, stream, p));
     B200SD_CHECK_CUDA(cudaGetLastError());
     count_launch(1);
     return 0;

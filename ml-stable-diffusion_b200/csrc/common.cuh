@@ -41,10 +41,41 @@ int encode_tmap_f16(CUtensorMap* map, const void* base, int rank, const uint64_t
 
 int num_sms();
 
+// Programmatic dependent launch (PDL): when enabled every kernel is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so the next kernel's CTAs may start (and run their
+// prologue: barrier init, TMEM allocation, tensor-map prefetch) while the previous grid drains; every kernel
+// executes griddepcontrol.wait before it reads or writes global memory.
+bool pdl_enabled();
+
 #ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                 Args&&... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    if (pdl_enabled()) {
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+    }
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---------------------------------------------------------------------------------------
 // PTX wrappers
 // ---------------------------------------------------------------------------------------
+// griddepcontrol.wait: block until the preceding grid in the stream has completed and its memory is visible
+// (no-op when the kernel was not launched as a programmatic dependent).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// griddepcontrol.launch_dependents: this CTA no longer objects to the next grid being scheduled.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
@@ -247,6 +278,13 @@ __host__ __device__ __forceinline__ uint32_t make_idesc_f16(uint32_t m, uint32_t
     return (1u << 4)                 // D format: F32
            | (0u << 7) | (0u << 10)  // A, B format: F16
            | (a_major << 15) | (b_major << 16) | ((n >> 3) << 17) | ((m >> 4) << 24);
+}
+
+// 2^x, single MUFU op, denormal results flushed to zero (softmax probabilities)
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
 
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }

@@ -17,6 +17,7 @@ static inline int grid_for(size_t n, int threads) {
 template <typename T>
 __global__ void nchw_to_nhwc_kernel(const T* __restrict__ in, __half* __restrict__ out, int n, int c, int hw,
                                     int c_pad) {
+    pdl_wait();
     const size_t total = static_cast<size_t>(n) * hw * c_pad;
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -33,6 +34,7 @@ __global__ void nchw_to_nhwc_kernel(const T* __restrict__ in, __half* __restrict
 template <typename T>
 __global__ void nhwc_to_nchw_f32_kernel(const T* __restrict__ in, float* __restrict__ out, int n, int c, int hw,
                                         int c_pad) {
+    pdl_wait();
     const size_t total = static_cast<size_t>(n) * c * hw;
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -47,6 +49,7 @@ __global__ void nhwc_to_nchw_f32_kernel(const T* __restrict__ in, float* __restr
 // ---- (B, D, 1, S) -> [B*S, D] fp16 (tiled transpose through shared memory) -------------------
 template <typename T>
 __global__ void ctx_to_tokens_kernel(const T* __restrict__ in, __half* __restrict__ out, int d, int s) {
+    pdl_wait();
     __shared__ float tile[32][33];
     const int b = blockIdx.z;
     const int d0 = blockIdx.y * 32, s0 = blockIdx.x * 32;
@@ -64,6 +67,7 @@ __global__ void ctx_to_tokens_kernel(const T* __restrict__ in, __half* __restric
 // ---- nearest x2 upsample, NHWC fp16, 16-byte vectors ------------------------------------------
 __global__ void upsample2x_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int n, int h, int w,
                                   int vecs) {
+    pdl_wait();
     const size_t total = static_cast<size_t>(n) * (2 * h) * (2 * w) * vecs;
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -79,6 +83,7 @@ __global__ void upsample2x_kernel(const uint4* __restrict__ in, uint4* __restric
 
 __global__ void add_kernel(const __half2* __restrict__ a, const __half2* __restrict__ b, __half2* __restrict__ out,
                            size_t n2) {
+    pdl_wait();
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n2;
          i += static_cast<size_t>(gridDim.x) * blockDim.x) {
         const float2 x = __half22float2(a[i]), y = __half22float2(b[i]);
@@ -92,6 +97,7 @@ __global__ void __launch_bounds__(256) linear_small_kernel(const float* __restri
                                                            const float* __restrict__ bias,
                                                            const float* __restrict__ add, float* __restrict__ out,
                                                            int m, int n, int k, int act_in, int act_out) {
+    pdl_wait();
     const int col = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (col >= n) return;
@@ -140,6 +146,7 @@ __global__ void __launch_bounds__(256) linear_small_kernel(const float* __restri
 // ---- sinusoidal timestep embedding (unet.py:703-728) -------------------------------------------
 __global__ void timestep_embedding_kernel(const float* __restrict__ t, float* __restrict__ out, int m, int dim,
                                           int flip, float freq_shift) {
+    pdl_wait();
     const int half = dim / 2;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m * half) return;
@@ -162,6 +169,7 @@ __global__ void timestep_embedding_kernel(const float* __restrict__ t, float* __
 __global__ void cfg_step_kernel(const float* __restrict__ noise_pred, float* __restrict__ latents,
                                 float* __restrict__ hist, float* __restrict__ denoised, __half* __restrict__ unet_in,
                                 int c_pad, int n, int c, int hw, b200sd_step_coeffs k) {
+    pdl_wait();
     const int numel = n * c * hw;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= numel) return;
@@ -199,6 +207,7 @@ __global__ void cfg_step_kernel(const float* __restrict__ noise_pred, float* __r
 template <typename T>
 __global__ void image_post_kernel(const T* __restrict__ in, int c_pad, float* __restrict__ of, uint8_t* __restrict__ ou,
                                   size_t pixels, int c) {
+    pdl_wait();
     const size_t total = pixels * c;
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -216,6 +225,7 @@ __global__ void image_post_kernel(const T* __restrict__ in, int c_pad, float* __
 __global__ void latent_prep_kernel(const float* __restrict__ z, const float* __restrict__ w /* [c, c] */,
                                    const float* __restrict__ b, float inv_scale, __half* __restrict__ out, int n, int c,
                                    int hw, int c_pad) {
+    pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n * hw) return;
     const int p = i % hw, img = i / hw;
@@ -242,13 +252,13 @@ extern "C" int b200sd_nchw_to_nhwc(const void* in, int32_t in_f32, void* out, in
     B200SD_REQUIRE(in && out && c_pad >= c, "b200sd_nchw_to_nhwc: bad arguments");
     const size_t total = static_cast<size_t>(n) * h * w * c_pad;
     if (in_f32)
-        nchw_to_nhwc_kernel<float><<<grid_for(total, 256), 256, 0, stream>>>(reinterpret_cast<const float*>(in),
+        B200SD_CHECK_CUDA(launch_kernel(nchw_to_nhwc_kernel<float>, dim3(grid_for(total, 256)), dim3(256), 0, stream, reinterpret_cast<const float*>(in),
                                                                              reinterpret_cast<__half*>(out), n, c,
-                                                                             h * w, c_pad);
+                                                                             h * w, c_pad));
     else
-        nchw_to_nhwc_kernel<__half><<<grid_for(total, 256), 256, 0, stream>>>(reinterpret_cast<const __half*>(in),
+        B200SD_CHECK_CUDA(launch_kernel(nchw_to_nhwc_kernel<__half>, dim3(grid_for(total, 256)), dim3(256), 0, stream, reinterpret_cast<const __half*>(in),
                                                                               reinterpret_cast<__half*>(out), n, c,
-                                                                              h * w, c_pad);
+                                                                              h * w, c_pad));
     B200SD_CHECK_CUDA(cudaGetLastError());
     count_launch(1);
     return 0;
@@ -260,11 +270,11 @@ extern "C" int b200sd_nhwc_to_nchw_f32(const void* in, int32_t in_f32, float* ou
     B200SD_REQUIRE(in && out && c_pad >= c, "b200sd_nhwc_to_nchw_f32: bad arguments");
     const size_t total = static_cast<size_t>(n) * c * h * w;
     if (in_f32)
-        nhwc_to_nchw_f32_kernel<float><<<grid_for(total, 256), 256, 0, stream>>>(reinterpret_cast<const float*>(in),
-                                                                                 out, n, c, h * w, c_pad);
+        B200SD_CHECK_CUDA(launch_kernel(nhwc_to_nchw_f32_kernel<float>, dim3(grid_for(total, 256)), dim3(256), 0, stream, reinterpret_cast<const float*>(in),
+                                                                                 out, n, c, h * w, c_pad));
     else
-        nhwc_to_nchw_f32_kernel<__half><<<grid_for(total, 256), 256, 0, stream>>>(reinterpret_cast<const __half*>(in),
-                                                                                  out, n, c, h * w, c_pad);
+        B200SD_CHECK_CUDA(launch_kernel(nhwc_to_nchw_f32_kernel<__half>, dim3(grid_for(total, 256)), dim3(256), 0, stream, reinterpret_cast<const __half*>(in),
+                                                                                  out, n, c, h * w, c_pad));
     B200SD_CHECK_CUDA(cudaGetLastError());
     count_launch(1);
     return 0;
@@ -276,11 +286,11 @@ extern "C" int b200sd_ctx_to_tokens(const void* in, int32_t in_f32, void* out, i
     B200SD_REQUIRE(in && out, "b200sd_ctx_to_tokens: null pointer");
     dim3 grid((s + 31) / 32, (d + 31) / 32, b), block(32, 8);
     if (in_f32)
-        ctx_to_tokens_kernel<float><<<grid, block, 0, stream>>>(reinterpret_cast<const float*>(in),
-                                                                reinterpret_cast<__half*>(out), d, s);
+        B200SD_CHECK_CUDA(launch_kernel(ctx_to_tokens_kernel<float>, dim3(grid), dim3(block), 0, stream, reinterpret_cast<const float*>(in),
+                                                                reinterpret_cast<__half*>(out), d, s));
     else
-        ctx_to_tokens_kernel<__half><<<grid, block, 0, stream>>>(reinterpret_cast<const __half*>(in),
-                                                                 reinterpret_cast<__half*>(out), d, s);
+        B200SD_CHECK_CUDA(launch_kernel(ctx_to_tokens_kernel<__half>, dim3(grid), dim3(block), 0, stream, reinterpret_cast<const __half*>(in),
+                                                                 reinterpret_cast<__half*>(out), d, s));
     B200SD_CHECK_CUDA(cudaGetLastError());
     count_launch(1);
     return 0;
@@ -291,8 +301,8 @@ extern "C" int b200sd_upsample2x(const void* in, void* out, int32_t n, int32_t h
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     B200SD_REQUIRE(in && out && c % 8 == 0, "b200sd_upsample2x: c=%d must be a multiple of 8", c);
     const size_t total = static_cast<size_t>(n) * 4 * h * w * (c / 8);
-    upsample2x_kernel<<<grid_for(total, 256), 256, 0, stream>>>(reinterpret_cast<const uint4*>(in),
-                                                                reinterpret_cast<uint4*>(out), n, h, w, c / 8);
+    B200SD_CHECK_CUDA(launch_kernel(upsample2x_kernel, dim3(grid_for(total, 256)), dim3(256), 0, stream, reinterpret_cast<const uint4*>(in),
+                                                                reinterpret_cast<uint4*>(out), n, h, w, c / 8));
     B200SD_CHECK_CUDA(cudaGetLastError());
     count_launch(1);
     return 0;
@@ -301,9 +311,9 @@ extern "C" int b200sd_upsample2x(const void* in, void* out, int32_t n, int32_t h
 extern "C" int b200sd_add(const void* a, const void* b, void* out, size_t numel, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     B200SD_REQUIRE(a && b && out && numel % 2 == 0, "b200sd_add: bad arguments");
-    add_kernel<<<grid_for(numel / 2, 256), 256, 0, stream>>>(reinterpret_cast<const __half2*>(a),
+    B200SD_CHECK_CUDA(launch_kernel(add_kernel, dim3(grid_for(numel / 2, 256)), dim3(256), 0, stream, reinterpret_cast<const __half2*>(a),
                                                              reinterpret_cast<const __half2*>(b),
-                                                             reinterpret_cast<__half2*>(out), numel / 2);
+                                                             reinterpret_cast<__half2*>(out), numel / 2));
     B200SD_CHECK_CUDA(cudaGetLastError());
     count_launch(1);
     return 0;
@@ -322,9 +332,9 @@ extern "C" int b200sd_linear_small(const float* x, const void* wgt, const float*
         const float* xr = x + static_cast<size_t>(r0) * k;
         float* orow = out + static_cast<size_t>(r0) * n;
         if (mm <= 2)
-            linear_small_kernel<2><<<blocks, 256, 0, stream>>>(xr, w, bias, add, orow, mm, n, k, act_in, act_out);
+            B200SD_CHECK_CUDA(launch_kernel(linear_small_kernel<2>, dim3(blocks), dim3(256), 0, stream, xr, w, bias, add, orow, mm, n, k, act_in, act_out));
         else
-            linear_small_kernel<8><<<blocks, 256, 0, stream>>>(xr, w, bias, add, orow, mm, n, k, act_in, act_out);
+            B200SD_CHECK_CUDA(launch_kernel(linear_small_kernel<8>, dim3(blocks), dim3(256), 0, stream, xr, w, bias, add, orow, mm, n, k, act_in, act_out));
         B200SD_CHECK_CUDA(cudaGetLastError());
         count_launch(1);
     }
@@ -336,8 +346,8 @@ extern "C" int b200sd_timestep_embedding(const float* timesteps, float* out, int
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     B200SD_REQUIRE(timesteps && out && dim % 2 == 0, "b200sd_timestep_embedding: bad arguments");
     const int total = m * (dim / 2);
-    timestep_embedding_kernel<<<(total + 127) / 128, 128, 0, stream>>>(timesteps, out, m, dim, flip_sin_to_cos,
-                                                                      freq_shift);
+    B200SD_CHECK_CUDA(launch_kernel(timestep_embedding_kernel, dim3((total + 127) / 128), dim3(128), 0, stream, timesteps, out, m, dim, flip_sin_to_cos,
+                                                                      freq_shift));
     B200SD_CHECK_CUDA(cudaGetLastError());
     count_launch(1);
     return 0;
@@ -354,9 +364,9 @@ extern "C" int b200sd_cfg_scheduler_step(const float* noise_pred, float* latents
                        (hist || (coeffs->push_eps_slot < 0 && coeffs->push_x0_slot < 0 && coeffs->push_x_slot < 0)),
                    "b200sd_cfg_scheduler_step: bad history ring slot");
     const int numel = n * c * h * w;
-    cfg_step_kernel<<<(numel + 255) / 256, 256, 0, stream>>>(noise_pred, latents, hist, denoised,
+    B200SD_CHECK_CUDA(launch_kernel(cfg_step_kernel, dim3((numel + 255) / 256), dim3(256), 0, stream, noise_pred, latents, hist, denoised,
                                                              reinterpret_cast<__half*>(unet_in), c_pad, n, c, h * w,
-                                                             *coeffs);
+                                                             *coeffs));
     B200SD_CHECK_CUDA(cudaGetLastError());
     count_launch(1);
     return 0;
@@ -368,11 +378,11 @@ extern "C" int b200sd_image_postprocess(const void* in, int32_t in_f32, int32_t 
     B200SD_REQUIRE(in && (out_f32 || out_u8), "b200sd_image_postprocess: null pointer");
     const size_t pixels = static_cast<size_t>(n) * h * w;
     if (in_f32)
-        image_post_kernel<float><<<grid_for(pixels * c, 256), 256, 0, stream>>>(reinterpret_cast<const float*>(in),
-                                                                                c_pad, out_f32, out_u8, pixels, c);
+        B200SD_CHECK_CUDA(launch_kernel(image_post_kernel<float>, dim3(grid_for(pixels * c, 256)), dim3(256), 0, stream, reinterpret_cast<const float*>(in),
+                                                                                c_pad, out_f32, out_u8, pixels, c));
     else
-        image_post_kernel<__half><<<grid_for(pixels * c, 256), 256, 0, stream>>>(reinterpret_cast<const __half*>(in),
-                                                                                 c_pad, out_f32, out_u8, pixels, c);
+        B200SD_CHECK_CUDA(launch_kernel(image_post_kernel<__half>, dim3(grid_for(pixels * c, 256)), dim3(256), 0, stream, reinterpret_cast<const __half*>(in),
+                                                                                 c_pad, out_f32, out_u8, pixels, c));
     B200SD_CHECK_CUDA(cudaGetLastError());
     count_launch(1);
     return 0;
@@ -383,8 +393,8 @@ extern "C" int b200sd_latent_prep(const float* z, const float* w, const float* b
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     B200SD_REQUIRE(z && w && out && c >= 1 && c <= 8 && c_pad >= c, "b200sd_latent_prep: bad arguments");
     const int total = n * h * wd;
-    latent_prep_kernel<<<(total + 255) / 256, 256, 0, stream>>>(z, w, b, inv_scale, reinterpret_cast<__half*>(out), n,
-                                                               c, h * wd, c_pad);
+    B200SD_CHECK_CUDA(launch_kernel(latent_prep_kernel, dim3((total + 255) / 256), dim3(256), 0, stream, z, w, b, inv_scale, reinterpret_cast<__half*>(out), n,
+                                                               c, h * wd, c_pad));
     B200SD_CHECK_CUDA(cudaGetLastError());
     count_launch(1);
     return 0;

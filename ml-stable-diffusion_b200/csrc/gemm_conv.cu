@@ -23,7 +23,7 @@ static constexpr int kBK = 64;
 static constexpr int kAStage = kBM * kBK * 2;  // 16 KiB
 static constexpr int kGemmThreads = 192;
 static constexpr int kMaxStages = 8;
-static constexpr int kSmemBudget = 200 * 1024;
+static constexpr int kSmemBudget = 220 * 1024;
 
 struct __align__(64) GemmParams {
     CUtensorMap tmA0, tmA1, tmB;
@@ -33,6 +33,8 @@ struct __align__(64) GemmParams {
     int m_tiles, n_tiles, block_n, stages;
     int n_img, Hout, Wout, stride, bw_log2, bh_log2, tiles_w, tiles_h;
     int bias_rows, bias_stride, geglu, out_f32;
+    int bias_mode;   // 0 none, 1 staged in smem (<= 2 vectors per tile), 2 read from global per chunk
+    int res_smem;    // 1: residual tile prefetched into smem with cp.async
     void* out;
     const float* bias;
     const __half* residual;
@@ -64,11 +66,18 @@ __device__ __forceinline__ TileCoord decode_work(const GemmParams& p, int work) 
 }
 
 // Applies the epilogue to 16 consecutive accumulator columns of one output row and stores them.
+// `bias` / `res` are already resolved to this row and column (shared or global memory); null = absent.
+// kGeneric = false: compile-time variant for the hot shapes (N % 16 == 0, 16-byte aligned rows): straight-line
+// vector code only, which keeps the kernel small enough for the instruction cache of these microsecond kernels.
+template <bool kGeneric, bool kGeglu, bool kOutF32, bool kPartial>
 __device__ __forceinline__ void epilogue_store16(const GemmParams& p, float (&acc)[16], int out_row, int col0,
-                                                 int split, int bias_base) {
-    if (p.partial != nullptr) {
+                                                 int split, const float* bias, const __half* res) {
+    const bool partial = kGeneric ? (p.partial != nullptr) : kPartial;
+    const bool geglu = kGeneric ? (p.geglu != 0) : kGeglu;
+    const bool out_f32 = kGeneric ? (p.out_f32 != 0) : kOutF32;
+    if (partial) {
         float* dst = p.partial + (static_cast<size_t>(split) * p.M + out_row) * p.N + col0;
-        if (col0 + 16 <= p.N && (p.N & 3) == 0) {
+        if (!kGeneric || (col0 + 16 <= p.N && (p.N & 3) == 0)) {
 #pragma unroll
             for (int j = 0; j < 16; j += 4)
                 *reinterpret_cast<float4*>(dst + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
@@ -79,43 +88,40 @@ __device__ __forceinline__ void epilogue_store16(const GemmParams& p, float (&ac
         }
         return;
     }
-    const bool full = (col0 + 16 <= p.N);
-    if (p.bias != nullptr) {
-        const float* b = p.bias + bias_base + col0;
-        if (full && (p.N & 3) == 0) {
+    if (bias != nullptr) {
+        if (!kGeneric || (col0 + 16 <= p.N && (p.N & 3) == 0)) {
 #pragma unroll
             for (int j = 0; j < 16; j += 4) {
-                float4 bv = *reinterpret_cast<const float4*>(b + j);
+                const float4 bv = *reinterpret_cast<const float4*>(bias + j);
                 acc[j] += bv.x, acc[j + 1] += bv.y, acc[j + 2] += bv.z, acc[j + 3] += bv.w;
             }
         } else {
 #pragma unroll
             for (int j = 0; j < 16; ++j)
-                if (col0 + j < p.N) acc[j] += b[j];
+                if (col0 + j < p.N) acc[j] += bias[j];
         }
     }
-    int ocol0 = col0, nvals = 16;
-    if (p.geglu) {
+    int ocol0 = col0;
+    const int nvals = geglu ? 8 : 16;
+    if (geglu) {
         // interleaved columns: even = value, odd = gate  (unet.py:616-617: a * gelu(g))
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] = acc[2 * j] * gelu_erf_f(acc[2 * j + 1]);
         ocol0 = col0 >> 1;
-        nvals = 8;
     }
     const int ld = p.n_store;
     const size_t off = static_cast<size_t>(out_row) * ld + ocol0;
-    const bool vec_ok = (ocol0 + nvals <= ld) && ((ld & 7) == 0);
-    if (p.residual != nullptr) {
-        const __half* r = p.residual + off;
+    const bool vec_ok = !kGeneric || ((ocol0 + nvals <= ld) && ((ld & 7) == 0));
+    if (res != nullptr) {
         if (vec_ok) {
 #pragma unroll
             for (int j = 0; j < 16; j += 8) {
                 if (j < nvals) {
-                    uint4 rv = *reinterpret_cast<const uint4*>(r + j);
+                    const uint4 rv = *reinterpret_cast<const uint4*>(res + j);
                     const __half2* h2 = reinterpret_cast<const __half2*>(&rv);
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        float2 f = __half22float2(h2[q]);
+                        const float2 f = __half22float2(h2[q]);
                         acc[j + 2 * q] += f.x;
                         acc[j + 2 * q + 1] += f.y;
                     }
@@ -124,10 +130,10 @@ __device__ __forceinline__ void epilogue_store16(const GemmParams& p, float (&ac
         } else {
 #pragma unroll
             for (int j = 0; j < 16; ++j)
-                if (j < nvals && ocol0 + j < ld) acc[j] += __half2float(r[j]);
+                if (j < nvals && ocol0 + j < ld) acc[j] += __half2float(res[j]);
         }
     }
-    if (p.out_f32) {
+    if (out_f32) {
         float* o = reinterpret_cast<float*>(p.out) + off;
         if (vec_ok) {
 #pragma unroll
@@ -161,6 +167,27 @@ __device__ __forceinline__ void epilogue_store16(const GemmParams& p, float (&ac
     }
 }
 
+// tile-local row -> (global output row, in-bounds)
+__device__ __forceinline__ bool tile_row(const GemmParams& p, const TileCoord& t, int row, int& out_row) {
+    if (p.mode == 0) {
+        out_row = t.m_tile * kBM + row;
+        return out_row < p.M;
+    }
+    const int dw = row & ((1 << p.bw_log2) - 1);
+    const int dh = (row >> p.bw_log2) & ((1 << p.bh_log2) - 1);
+    const int dn = row >> (p.bw_log2 + p.bh_log2);
+    const int on = t.n0 + dn, oy = t.h0 + dh, ox = t.w0 + dw;
+    out_row = (on * p.Hout + oy) * p.Wout + ox;
+    return (on < p.n_img) && (oy < p.Hout) && (ox < p.Wout);
+}
+
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+template <bool kGeneric, bool kGeglu, bool kOutF32, bool kPartial>
 __global__ void __launch_bounds__(kGemmThreads, 1) umma_gemm_kernel(const __grid_constant__ GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -172,6 +199,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) umma_gemm_kernel(const __grid
     uint64_t* tmem_full = empty_bar + kMaxStages;
     uint64_t* tmem_empty = tmem_full + 2;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    float* bias_s = reinterpret_cast<float*>(tmem_ptr + 4);           // [2][block_n] (16 B aligned)
+    __half* res_s = reinterpret_cast<__half*>(bias_s + 2 * 256);      // [128][block_n + 8]
+    const int ldr = p.block_n + 8;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -198,6 +228,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) umma_gemm_kernel(const __grid
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    // PDL: everything above overlapped the previous kernel's tail; from here on we touch its outputs
+    pdl_wait();
+    pdl_trigger();
 
     const int total_work = p.m_tiles * p.n_tiles * p.splits;
 
@@ -277,29 +310,59 @@ __global__ void __launch_bounds__(kGemmThreads, 1) umma_gemm_kernel(const __grid
         // ------------------------------- epilogue -----------------------------------
         const int lane_group = warp & 3;  // TMEM lanes [32*lane_group, +32) are accessible to this warp
         const int row = lane_group * 32 + lane;
+        const int tid_e = threadIdx.x - 64;  // 0..127 among the epilogue warps
         int iter = 0;
         for (int work = blockIdx.x; work < total_work; work += gridDim.x, ++iter) {
             const TileCoord t = decode_work(p, work);
             const int as = iter & 1;
             const uint32_t aphase = (iter >> 1) & 1;
+            const int ncol0 = t.n_tile * p.block_n;
             int out_row;
-            bool valid;
-            if (p.mode == 0) {
-                out_row = t.m_tile * kBM + row;
-                valid = out_row < p.M;
-            } else {
-                const int dw = row & ((1 << p.bw_log2) - 1);
-                const int dh = (row >> p.bw_log2) & ((1 << p.bh_log2) - 1);
-                const int dn = row >> (p.bw_log2 + p.bh_log2);
-                const int on = t.n0 + dn, oy = t.h0 + dh, ox = t.w0 + dw;
-                valid = (on < p.n_img) && (oy < p.Hout) && (ox < p.Wout);
-                out_row = (on * p.Hout + oy) * p.Wout + ox;
+            const bool valid = tile_row(p, t, row, out_row);
+            // ---- operand prefetch, overlapped with this tile's main loop: bias -> smem, residual -> smem ----
+            epi_bar_sync();  // everyone is done reading the staging buffers of the previous tile
+            int bias_sel = 0;
+            if (p.bias_mode == 1) {
+                int row0;
+                tile_row(p, t, 0, row0);
+                const int img0 = p.bias_rows > 0 ? row0 / p.bias_rows : 0;
+                const int nvec = p.bias_rows > 0 ? (p.M + p.bias_rows - 1) / p.bias_rows : 1;
+                for (int c = tid_e; c < 2 * p.block_n; c += 128) {
+                    const int which = c >= p.block_n ? 1 : 0;
+                    const int cc = c - which * p.block_n;
+                    const int col = ncol0 + cc;
+                    float v = 0.f;
+                    if (col < p.N && img0 + which < nvec && (which == 0 || p.bias_rows > 0))
+                        v = p.bias[static_cast<size_t>(img0 + which) * p.bias_stride + col];
+                    bias_s[which * p.block_n + cc] = v;
+                }
+                if (p.bias_rows > 0 && valid) bias_sel = min(1, max(0, out_row / p.bias_rows - img0));
             }
-            const int bias_base = (p.bias_rows > 0 && valid) ? (out_row / p.bias_rows) * p.bias_stride : 0;
+            if (p.res_smem) {
+                const int vpr = p.block_n >> 3;  // 16-byte vectors per tile row
+                for (int i = tid_e; i < kBM * vpr; i += 128) {
+                    const int r = i / vpr, cv = i - r * vpr;
+                    int orow;
+                    if (tile_row(p, t, r, orow) && ncol0 + cv * 8 < p.N)
+                        cp_async16(res_s + r * ldr + cv * 8, p.residual + static_cast<size_t>(orow) * p.n_store + ncol0 + cv * 8);
+                }
+            }
+            const int bias_base = (p.bias_mode == 2 && p.bias_rows > 0 && valid) ? (out_row / p.bias_rows) * p.bias_stride : 0;
             mbar_wait(&tmem_full[as], aphase);
             tc_fence_after();
+            if (p.res_smem) cp_async_wait_all();
+            epi_bar_sync();  // staged bias / residual visible to all epilogue threads
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_group * 32) << 16) + as * 256;
-            const int ncol0 = t.n_tile * p.block_n;
+            auto process16 = [&](float (&acc)[16], int c) {  // c: column offset inside the tile
+                const float* bptr = nullptr;
+                if (p.bias_mode == 1) bptr = bias_s + bias_sel * p.block_n + c;
+                else if (kGeneric && p.bias_mode == 2) bptr = p.bias + bias_base + ncol0 + c;
+                const __half* rptr = nullptr;
+                if (p.res_smem) rptr = res_s + row * ldr + c;
+                else if (kGeneric && p.residual != nullptr)
+                    rptr = p.residual + static_cast<size_t>(out_row) * p.n_store + ((ncol0 + c) >> (p.geglu ? 1 : 0));
+                epilogue_store16<kGeneric, kGeglu, kOutF32, kPartial>(p, acc, out_row, ncol0 + c, t.split, bptr, rptr);
+            };
             auto process32 = [&](const uint32_t (&v)[32], int c) {
                 if (!valid) return;
 #pragma unroll
@@ -308,11 +371,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) umma_gemm_kernel(const __grid
                         float acc[16];
 #pragma unroll
                         for (int j = 0; j < 16; ++j) acc[j] = __uint_as_float(v[16 * hh + j]);
-                        epilogue_store16(p, acc, out_row, ncol0 + c + 16 * hh, t.split, bias_base);
+                        process16(acc, c + 16 * hh);
                     }
                 }
             };
-            if ((p.block_n & 31) == 0) {
+            if (!kGeneric || (p.block_n & 31) == 0) {
                 // software-pipelined: the TMEM load of the next 32 columns is in flight while these are stored
                 uint32_t va[32], vb[32];
                 tmem_ld32(taddr, va);
@@ -327,7 +390,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) umma_gemm_kernel(const __grid
                         process32(vb, c + 32);
                     }
                 }
-            } else {
+            } else if (kGeneric) {
                 for (int c = 0; c < p.block_n; c += 16) {
                     uint32_t v[16];
                     tmem_ld16(taddr + c, v);
@@ -336,7 +399,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) umma_gemm_kernel(const __grid
                         float acc[16];
 #pragma unroll
                         for (int j = 0; j < 16; ++j) acc[j] = __uint_as_float(v[j]);
-                        epilogue_store16(p, acc, out_row, ncol0 + c, t.split, bias_base);
+                        process16(acc, c);
                     }
                 }
             }
@@ -357,6 +420,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) umma_gemm_kernel(const __grid
 __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int splits, int M, int N,
                                      const float* __restrict__ bias, int bias_rows, int bias_stride,
                                      const __half* __restrict__ residual, void* __restrict__ out, int out_f32) {
+    pdl_wait();
     const size_t total4 = static_cast<size_t>(M) * N / 4;
     const size_t stride = static_cast<size_t>(M) * N;
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total4;
@@ -396,6 +460,7 @@ struct GemmPlan {
     int M, N, Kpt, taps, kc0, kc1, kb_total;
     int m_tiles, n_tiles, block_n, splits, kb_per_split, stages;
     int Hout, Wout, bw, bh, bn_img, tiles_w, tiles_h, tiles_n;
+    int bias_mode, res_smem, epi_smem;
 };
 
 static int ilog2(int v) {
@@ -447,33 +512,64 @@ static int plan_gemm(const b200sd_gemm_args& a, GemmPlan& pl) {
         pl.m_tiles = pl.tiles_w * pl.tiles_h * pl.tiles_n;
     }
     if (a.geglu) B200SD_REQUIRE(a.n % 16 == 0, "b200sd_gemm: GEGLU needs n %% 16 == 0");
-    // N tiling: fewest tiles, then least padding
-    if (a.block_n > 0) {
-        B200SD_REQUIRE(a.block_n % 16 == 0 && a.block_n <= 256, "b200sd_gemm: block_n %d", a.block_n);
-        pl.block_n = a.block_n;
-    } else {
-        const int nt = (a.n + 255) / 256;
-        pl.block_n = std::min(256, ((a.n + nt - 1) / nt + 15) / 16 * 16);
-    }
-    pl.n_tiles = (a.n + pl.block_n - 1) / pl.block_n;
-    // split-K: fill the machine when the output grid is small
-    const int tiles = pl.m_tiles * pl.n_tiles;
+    // ---- tile shape / split-K selection by a small cost model (cycles; constants fitted to B200 runs) ----
     const int sms = num_sms();
-    int splits = 1;
-    if (a.split_k > 0) {
-        splits = a.split_k;
-    } else if (!a.geglu && a.n % 4 == 0 && tiles * 10 < sms * 7) {
-        splits = std::max(1, std::min(sms / tiles, pl.kb_total / 4));
+    const bool can_split = !a.geglu && a.n % 4 == 0;
+    auto epi_cycles = [&](int bn) { return 400.0 + (bn / 32.0) * (a.geglu ? 520.0 : 230.0); };
+    auto kb_cycles = [&](int bn) { return std::max(2.0 * bn, (kAStage + 128.0 * bn) / 38.0); };
+    double best_t = 1e30;
+    int best_bn = 0, best_s = 1;
+    static const int kBns[] = {256, 224, 192, 160, 128, 96, 64, 32, 16};
+    static const int kSplits[] = {1, 2, 3, 4, 6, 8, 12, 16, 24, 32};
+    for (int bn : kBns) {
+        if (a.block_n > 0 && bn != a.block_n) continue;
+        const int nt = (a.n + bn - 1) / bn;
+        if (a.block_n == 0 && bn > 16 && nt * bn > a.n + a.n / 4 + 15) continue;  // > 25 % padding
+        for (int sp : kSplits) {
+            if (a.split_k > 0 && sp != a.split_k) continue;
+            if (sp > 1 && (!can_split || sp * 2 > pl.kb_total) && a.split_k == 0) continue;
+            const int kb = (pl.kb_total + sp - 1) / sp;
+            const int se = (pl.kb_total + kb - 1) / kb;
+            const long units = static_cast<long>(pl.m_tiles) * nt * se;
+            const double waves = std::ceil(static_cast<double>(units) / sms);
+            const double main = kb * kb_cycles(bn);
+            double t = 5000.0 + main + epi_cycles(bn) + (waves - 1.0) * std::max(main, epi_cycles(bn));
+            if (se > 1) t += 6000.0 + static_cast<double>(se) * pl.M * a.n * 8.0 / 3000.0;
+            if (t < best_t) {
+                best_t = t;
+                best_bn = bn;
+                best_s = sp;
+            }
+        }
     }
-    splits = std::max(1, std::min(splits, pl.kb_total));
+    if (best_bn == 0) {  // explicit overrides that the loops above did not enumerate
+        best_bn = a.block_n > 0 ? a.block_n : 128;
+        best_s = a.split_k > 0 ? a.split_k : 1;
+    }
+    B200SD_REQUIRE(best_bn % 16 == 0 && best_bn >= 16 && best_bn <= 256, "b200sd_gemm: block_n %d", best_bn);
+    pl.block_n = best_bn;
+    pl.n_tiles = (a.n + pl.block_n - 1) / pl.block_n;
+    int splits = std::max(1, std::min(best_s, pl.kb_total));
     pl.kb_per_split = (pl.kb_total + splits - 1) / splits;
     pl.splits = (pl.kb_total + pl.kb_per_split - 1) / pl.kb_per_split;
     if (pl.splits > 1) {
         B200SD_REQUIRE(!a.geglu, "b200sd_gemm: split-K with GEGLU is not supported");
         B200SD_REQUIRE(a.n % 4 == 0, "b200sd_gemm: split-K needs n %% 4 == 0");
     }
+    // ---- epilogue operand staging ----
+    pl.bias_mode = 0;
+    pl.res_smem = 0;
+    if (pl.splits == 1) {
+        if (a.bias != nullptr) {
+            const bool two_vec_ok = a.bias_rows == 0 || a.bias_rows >= kBM ||
+                                    (a.mode == 1 && a.bias_rows == pl.Hout * pl.Wout && pl.bn_img <= 2);
+            pl.bias_mode = two_vec_ok ? 1 : 2;
+        }
+        if (a.residual != nullptr && !a.geglu && a.n % 8 == 0) pl.res_smem = 1;
+    }
     const int per_stage = kAStage + pl.block_n * kBK * 2;
-    pl.stages = std::max(2, std::min(kMaxStages, kSmemBudget / per_stage));
+    pl.epi_smem = 2 * 256 * 4 + (pl.res_smem ? kBM * (pl.block_n + 8) * 2 : 0);
+    pl.stages = std::max(2, std::min(kMaxStages, (kSmemBudget - pl.epi_smem) / per_stage));
     return 0;
 }
 
@@ -564,29 +660,47 @@ static int launch_gemm(const b200sd_gemm_args& a, cudaStream_t stream) {
     p.bias_stride = a.bias_stride > 0 ? a.bias_stride : a.n;
     p.geglu = a.geglu;
     p.out_f32 = a.out_f32;
+    p.bias_mode = pl.bias_mode;
+    p.res_smem = pl.res_smem;
     p.out = a.out;
     p.bias = pl.splits > 1 ? nullptr : a.bias;
     p.residual = pl.splits > 1 ? nullptr : reinterpret_cast<const __half*>(a.residual);
     p.partial = pl.splits > 1 ? a.workspace : nullptr;
 
-    const int smem_bytes = pl.stages * (kAStage + pl.block_n * kBK * 2) + (2 * kMaxStages + 4) * 8 + 16 + 1024;
-    static bool attr_set = false;
-    if (!attr_set) {
-        B200SD_CHECK_CUDA(cudaFuncSetAttribute(umma_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               227 * 1024));
-        attr_set = true;
-    }
+    const int smem_bytes = pl.stages * (kAStage + pl.block_n * kBK * 2) + (2 * kMaxStages + 4) * 8 + 16 + pl.epi_smem + 1024;
     const int total = pl.m_tiles * pl.n_tiles * pl.splits;
     const int grid = std::min(total, num_sms());
-    umma_gemm_kernel<<<grid, kGemmThreads, smem_bytes, stream>>>(p);
+    // compile-time epilogue variants for the hot shapes; anything irregular takes the generic kernel
+    const bool regular = (a.n % 16 == 0) && (p.n_store % 8 == 0) && (pl.block_n % 32 == 0) && pl.bias_mode != 2 &&
+                         (a.residual == nullptr || pl.res_smem || pl.splits > 1);
+    using KernelFn = void (*)(GemmParams);
+    KernelFn fn;
+    int variant;
+    if (!regular) {
+        fn = umma_gemm_kernel<true, false, false, false>, variant = 0;
+    } else if (pl.splits > 1) {
+        fn = umma_gemm_kernel<false, false, false, true>, variant = 1;
+    } else if (a.geglu) {
+        fn = umma_gemm_kernel<false, true, false, false>, variant = 2;
+    } else if (a.out_f32) {
+        fn = umma_gemm_kernel<false, false, true, false>, variant = 3;
+    } else {
+        fn = umma_gemm_kernel<false, false, false, false>, variant = 4;
+    }
+    static bool attr_set[5] = {false, false, false, false, false};
+    if (!attr_set[variant]) {
+        B200SD_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set[variant] = true;
+    }
+    B200SD_CHECK_CUDA(launch_kernel(fn, dim3(grid), dim3(kGemmThreads), smem_bytes, stream, p));
     B200SD_CHECK_CUDA(cudaGetLastError());
     count_launch(1);
     if (pl.splits > 1) {
         const size_t total4 = static_cast<size_t>(pl.M) * a.n / 4;
         const int rgrid = static_cast<int>(std::min<size_t>((total4 + 255) / 256, static_cast<size_t>(num_sms()) * 8));
-        splitk_reduce_kernel<<<rgrid, 256, 0, stream>>>(a.workspace, pl.splits, pl.M, a.n, a.bias, a.bias_rows,
+        B200SD_CHECK_CUDA(launch_kernel(splitk_reduce_kernel, dim3(rgrid), dim3(256), 0, stream, a.workspace, pl.splits, pl.M, a.n, a.bias, a.bias_rows,
                                                         a.bias_stride > 0 ? a.bias_stride : a.n,
-                                                        reinterpret_cast<const __half*>(a.residual), a.out, a.out_f32);
+                                                        reinterpret_cast<const __half*>(a.residual), a.out, a.out_f32));
         B200SD_CHECK_CUDA(cudaGetLastError());
         count_launch(1);
     }

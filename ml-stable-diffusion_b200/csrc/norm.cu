@@ -35,11 +35,12 @@ __device__ __forceinline__ void load8(const __half* src, float (&f)[8]) {
 // tree folds rows -> channels -> groups (no atomics: bitwise reproducible).  The last block of each
 // image (ticket counter) merges the chunk partials in chunk order with Chan's formula and writes the
 // final (mean, rstd) per group.
-__global__ void __launch_bounds__(384) gn_stats_kernel(const __half* __restrict__ x0, const __half* __restrict__ x1,
+__global__ void __launch_bounds__(416) gn_stats_kernel(const __half* __restrict__ x0, const __half* __restrict__ x1,
                                                        int c0, int c1, int hw, int groups, int chunks, int rows,
                                                        float eps, float* __restrict__ partial /* [n][chunks][g][2] */,
                                                        float* __restrict__ final_stats /* [n][g][2] */,
                                                        unsigned int* __restrict__ tickets /* [n] */) {
+    pdl_wait();
     const int C = c0 + c1;
     const int cpg = C / groups;
     const int vecs = C / 8;
@@ -59,7 +60,8 @@ __global__ void __launch_bounds__(384) gn_stats_kernel(const __half* __restrict_
     const __half* base = from0 ? x0 + static_cast<size_t>(n) * hw * c0 + ch
                                : x1 + static_cast<size_t>(n) * hw * c1 + (ch - c0);
     const int cs = from0 ? c0 : c1;
-    for (int px = px0 + r; px < px1; px += rows) {
+    const bool active = r < rows;  // the block is padded to whole warps; padding threads only help reduce
+    for (int px = px0 + r; active && px < px1; px += rows) {
         float f[8];
         load8(base + static_cast<size_t>(px) * cs, f);
 #pragma unroll
@@ -68,11 +70,13 @@ __global__ void __launch_bounds__(384) gn_stats_kernel(const __half* __restrict_
             q[e] += f[e] * f[e];
         }
     }
-    float* row_buf = sm + (static_cast<size_t>(r) * C + ch) * 2;
+    if (active) {
+        float* row_buf = sm + (static_cast<size_t>(r) * C + ch) * 2;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-        row_buf[2 * e] = s[e];
-        row_buf[2 * e + 1] = q[e];
+        for (int e = 0; e < 8; ++e) {
+            row_buf[2 * e] = s[e];
+            row_buf[2 * e + 1] = q[e];
+        }
     }
     __syncthreads();
     // rows -> channel totals (thread c < C), fixed order
@@ -107,9 +111,12 @@ __global__ void __launch_bounds__(384) gn_stats_kernel(const __half* __restrict_
     __syncthreads();
     if (s_ticket != static_cast<unsigned int>(chunks - 1)) return;
     __threadfence();
-    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+    // one warp per group; lanes stride over the chunks (fixed assignment), then a fixed butterfly of Chan
+    // merges: deterministic and ~log-depth instead of a serial walk over all chunks
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+    for (int g = wrp; g < groups; g += nwarps) {
         float tot = 0.f, mean = 0.f, m2 = 0.f;
-        for (int k = 0; k < chunks; ++k) {
+        for (int k = lane; k < chunks; k += 32) {
             const int p0 = k * px_per_chunk;
             const int p1 = min(hw, p0 + px_per_chunk);
             const float cb = static_cast<float>(max(0, p1 - p0) * cpg);
@@ -122,9 +129,29 @@ __global__ void __launch_bounds__(384) gn_stats_kernel(const __half* __restrict_
             m2 += m2b + delta * delta * (tot * cb / nt);
             tot = nt;
         }
-        final_stats[(static_cast<size_t>(n) * groups + g) * 2] = mean;
-        final_stats[(static_cast<size_t>(n) * groups + g) * 2 + 1] = rsqrtf(m2 / tot + eps);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float tot_b = __shfl_xor_sync(0xffffffffu, tot, o);
+            const float mean_b = __shfl_xor_sync(0xffffffffu, mean, o);
+            const float m2_b = __shfl_xor_sync(0xffffffffu, m2, o);
+            // symmetric merge so both partners compute the identical result
+            const float nt = tot + tot_b;
+            if (nt > 0.f) {
+                const float lo_t = (lane & o) ? tot_b : tot, hi_t = (lane & o) ? tot : tot_b;
+                const float lo_m = (lane & o) ? mean_b : mean, hi_m = (lane & o) ? mean : mean_b;
+                const float lo_2 = (lane & o) ? m2_b : m2, hi_2 = (lane & o) ? m2 : m2_b;
+                const float delta = hi_m - lo_m;
+                mean = lo_m + delta * (hi_t / nt);
+                m2 = lo_2 + hi_2 + delta * delta * (lo_t * hi_t / nt);
+                tot = nt;
+            }
+        }
+        if (lane == 0) {
+            final_stats[(static_cast<size_t>(n) * groups + g) * 2] = mean;
+            final_stats[(static_cast<size_t>(n) * groups + g) * 2 + 1] = rsqrtf(m2 / tot + eps);
+        }
     }
+    __syncthreads();
     if (threadIdx.x == 0) tickets[n] = 0;  // self-reset for the next launch
 }
 
@@ -135,6 +162,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __half* __restrict_
                                                        const float* __restrict__ gamma,
                                                        const float* __restrict__ beta, int silu,
                                                        __half* __restrict__ out, int px_per_block) {
+    pdl_wait();
     const int C = c0 + c1;
     const int cpg = C / groups;
     const int vecs = C / 8;
@@ -176,9 +204,10 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __half* __restrict_
 }
 
 static int gn_chunks(int hw, int n_img) {
-    // ~2 blocks per SM overall, at least 16 pixels per chunk
-    int want = std::max(1, (2 * num_sms()) / std::max(1, n_img));
-    return std::max(1, std::min({kGnMaxChunks, want, std::max(1, hw / 16)}));
+    // <= 32 chunks per image: the finalising block's warps then read one partial per lane (no serial walk);
+    // the streaming phase is tiny (a few MB, L2 resident), so 32 blocks per image are plenty
+    (void)n_img;
+    return std::max(1, std::min(32, hw / 16));
 }
 
 static unsigned int* gn_tickets() {
@@ -195,6 +224,7 @@ template <int kVecsPerLane>
 __global__ void __launch_bounds__(256) layer_norm_kernel(const __half* __restrict__ x, const float* __restrict__ gamma,
                                                          const float* __restrict__ beta, __half* __restrict__ out,
                                                          int rows, int c, float eps) {
+    pdl_wait();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= rows) return;
@@ -266,6 +296,7 @@ __global__ void __launch_bounds__(256) layer_norm_kernel(const __half* __restric
 // ---- row softmax: fp32 scores [rows, cols] -> fp16 probabilities (VAE mid-block attention, d=512) ----
 __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ in, __half* __restrict__ out,
                                                            int cols, float scale_log2) {
+    pdl_wait();
     const size_t row = blockIdx.x;
     const float* src = in + row * cols;
     __half* dst = out + row * cols;
@@ -321,7 +352,7 @@ extern "C" int b200sd_group_norm(const void* x0, const void* x1, int32_t c0, int
     const int vecs = C / 8;
     B200SD_REQUIRE(vecs <= 384, "b200sd_group_norm: too many channels (%d)", C);
     const int rows = std::max(1, std::min(256 / vecs, (hw + chunks - 1) / chunks));
-    const int threads = vecs * rows;
+    const int threads = (vecs * rows + 31) / 32 * 32;
     float* partial = stats_ws;
     float* final_stats = stats_ws + static_cast<size_t>(n_img) * chunks * groups * 2;
     const size_t smem1 = (static_cast<size_t>(rows) * C * 2 + static_cast<size_t>(C) * 2) * sizeof(float);
@@ -331,17 +362,17 @@ extern "C" int b200sd_group_norm(const void* x0, const void* x1, int32_t c0, int
                                                static_cast<int>(smem1)));
         smem1_max = smem1;
     }
-    gn_stats_kernel<<<dim3(chunks, n_img), threads, smem1, stream>>>(
+    B200SD_CHECK_CUDA(launch_kernel(gn_stats_kernel, dim3(dim3(chunks, n_img)), dim3(threads), smem1, stream, 
         reinterpret_cast<const __half*>(x0), reinterpret_cast<const __half*>(x1), c0, c1, hw, groups, chunks, rows, eps,
-        partial, final_stats, tickets);
+        partial, final_stats, tickets));
     B200SD_CHECK_CUDA(cudaGetLastError());
     const int want_blocks = std::max(1, (num_sms() * 4) / std::max(1, n_img));
     const int px_per_block = std::max(1, (hw + want_blocks - 1) / want_blocks);
     const int blocks = (hw + px_per_block - 1) / px_per_block;
     const size_t smem2 = 2 * static_cast<size_t>(C) * sizeof(float);
-    gn_apply_kernel<<<dim3(blocks, n_img), 256, smem2, stream>>>(
+    B200SD_CHECK_CUDA(launch_kernel(gn_apply_kernel, dim3(dim3(blocks, n_img)), dim3(256), smem2, stream, 
         reinterpret_cast<const __half*>(x0), reinterpret_cast<const __half*>(x1), c0, c1, hw, groups, final_stats,
-        gamma, beta, silu, reinterpret_cast<__half*>(out), px_per_block);
+        gamma, beta, silu, reinterpret_cast<__half*>(out), px_per_block));
     B200SD_CHECK_CUDA(cudaGetLastError());
     count_launch(2);
     return 0;
@@ -358,11 +389,11 @@ extern "C" int b200sd_layer_norm(const void* x, const float* gamma, const float*
     const __half* xi = reinterpret_cast<const __half*>(x);
     __half* xo = reinterpret_cast<__half*>(out);
     if (per_lane <= 2)
-        layer_norm_kernel<2><<<blocks, 256, 0, stream>>>(xi, gamma, beta, xo, rows, c, eps);
+        B200SD_CHECK_CUDA(launch_kernel(layer_norm_kernel<2>, dim3(blocks), dim3(256), 0, stream, xi, gamma, beta, xo, rows, c, eps));
     else if (per_lane <= 5)
-        layer_norm_kernel<5><<<blocks, 256, 0, stream>>>(xi, gamma, beta, xo, rows, c, eps);
+        B200SD_CHECK_CUDA(launch_kernel(layer_norm_kernel<5>, dim3(blocks), dim3(256), 0, stream, xi, gamma, beta, xo, rows, c, eps));
     else
-        layer_norm_kernel<8><<<blocks, 256, 0, stream>>>(xi, gamma, beta, xo, rows, c, eps);
+        B200SD_CHECK_CUDA(launch_kernel(layer_norm_kernel<8>, dim3(blocks), dim3(256), 0, stream, xi, gamma, beta, xo, rows, c, eps));
     B200SD_CHECK_CUDA(cudaGetLastError());
     count_launch(1);
     return 0;
@@ -372,8 +403,8 @@ extern "C" int b200sd_softmax_rows(const float* in, void* out, int32_t rows, int
                                    void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     B200SD_REQUIRE(in && out && rows > 0 && cols > 0, "b200sd_softmax_rows: bad arguments");
-    softmax_rows_kernel<<<rows, 256, 0, stream>>>(in, reinterpret_cast<__half*>(out), cols,
-                                                  scale * 1.4426950408889634f);
+    B200SD_CHECK_CUDA(launch_kernel(softmax_rows_kernel, dim3(rows), dim3(256), 0, stream, in, reinterpret_cast<__half*>(out), cols,
+                                                  scale * 1.4426950408889634f));
     B200SD_CHECK_CUDA(cudaGetLastError());
     count_launch(1);
     return 0;

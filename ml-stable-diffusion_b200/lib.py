@@ -42,6 +42,7 @@ _SIGNATURES = {
     "b200sd_last_error": (C.c_char_p, []),
     "b200sd_version": (C.c_int, []),
     "b200sd_launch_count": (C.c_uint64, []),
+    "b200sd_set_pdl": (None, [C.c_int]),
     "b200sd_gemm": (C.c_int, [C.POINTER(GemmArgs), C.c_void_p]),
     "b200sd_gemm_workspace_bytes": (C.c_size_t, [C.POINTER(GemmArgs)]),
     "b200sd_linear_small": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
