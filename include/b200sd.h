@@ -81,6 +81,8 @@ typedef struct {
 } b200sd_gemm_args;
 
 int b200sd_gemm(const b200sd_gemm_args* args, void* stream);
+/* host-only: human-readable tiling plan (tile shape, split-K, pipeline depth) the launcher would use */
+int b200sd_gemm_describe_plan(const b200sd_gemm_args* args, char* buf, size_t buf_size);
 /* bytes of fp32 scratch b200sd_gemm would need for these args (0 if no split-K) */
 size_t b200sd_gemm_workspace_bytes(const b200sd_gemm_args* args);
 

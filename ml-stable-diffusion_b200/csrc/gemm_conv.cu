@@ -717,6 +717,18 @@ extern "C" int b200sd_gemm(const b200sd_gemm_args* args, void* stream) {
     return b200sd::launch_gemm(*args, static_cast<cudaStream_t>(stream));
 }
 
+extern "C" int b200sd_gemm_describe_plan(const b200sd_gemm_args* args, char* buf, size_t buf_size) {
+    if (!args || !buf || buf_size == 0) return 2;
+    b200sd::GemmPlan pl;
+    if (int rc = b200sd::plan_gemm(*args, pl)) return rc;
+    snprintf(buf, buf_size,
+             "M=%d N=%d kb_total=%d m_tiles=%d n_tiles=%d block_n=%d splits=%d kb_per_split=%d stages=%d "
+             "box=%dx%dx%d bias_mode=%d res_smem=%d epi_smem=%d",
+             pl.M, pl.N, pl.kb_total, pl.m_tiles, pl.n_tiles, pl.block_n, pl.splits, pl.kb_per_split, pl.stages,
+             pl.bn_img, pl.bh, pl.bw, pl.bias_mode, pl.res_smem, pl.epi_smem);
+    return 0;
+}
+
 extern "C" size_t b200sd_gemm_workspace_bytes(const b200sd_gemm_args* args) {
     if (!args) return 0;
     b200sd::GemmPlan pl;

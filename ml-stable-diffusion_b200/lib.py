@@ -45,6 +45,7 @@ _SIGNATURES = {
     "b200sd_set_pdl": (None, [C.c_int]),
     "b200sd_gemm": (C.c_int, [C.POINTER(GemmArgs), C.c_void_p]),
     "b200sd_gemm_workspace_bytes": (C.c_size_t, [C.POINTER(GemmArgs)]),
+    "b200sd_gemm_describe_plan": (C.c_int, [C.POINTER(GemmArgs), C.c_char_p, C.c_size_t]),
     "b200sd_linear_small": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                       C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "b200sd_timestep_embedding": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float,
@@ -162,6 +163,19 @@ def gemm_args(mode, a0, wgt, out, *, a1=None, bias=None, residual=None, m=0, n=0
     args.workspace = None if workspace is None else workspace.data_ptr()
     args.workspace_bytes = 0 if workspace is None else workspace.numel() * workspace.element_size()
     return args
+
+
+def describe_plan(mode, m=0, n=0, c0=0, c1=0, n_img=0, h=0, w=0, stride=1, geglu=False, has_bias=True,
+                  has_residual=False, bias_rows=0) -> str:
+    """Host-only: the tiling the launcher would choose (no GPU needed)."""
+    a = GemmArgs()
+    a.mode, a.m, a.n, a.c0, a.c1, a.n_img, a.h, a.w, a.stride = mode, m, n, c0, c1, n_img, h, w, stride
+    a.geglu, a.bias_rows = int(geglu), bias_rows
+    a.bias = 1 if has_bias else None       # only tested for null-ness by the planner
+    a.residual = 1 if has_residual else None
+    buf = C.create_string_buffer(512)
+    _check(load().b200sd_gemm_describe_plan(C.byref(a), buf, 512), "b200sd_gemm_describe_plan")
+    return buf.value.decode()
 
 
 def gemm_workspace_bytes(args) -> int:

@@ -155,9 +155,10 @@ class B200StableDiffusionPipeline:
 
     # ---------------------------------------------------------------- device loop
     def denoise(self, text_embeddings, latents, num_inference_steps, guidance_scale, callback=None,
-                callback_steps=1, time_ids=None, text_embeds=None, return_denoised=False):
+                callback_steps=1, time_ids=None, text_embeds=None, return_denoised=False, record=None):
         """Runs the N-step loop entirely on the device.  ``text_embeddings`` (2B, D, 1, S) and ``latents``
-        (B, C, h, w) may be numpy (copied once, before the loop) or CUDA tensors."""
+        (B, C, h, w) may be numpy (copied once, before the loop) or CUDA tensors.  ``record`` (a list) receives
+        (timestep, noise_pred, latents_after_step) clones per step -- a debugging / testing aid."""
         sched = S.make_scheduler(self.scheduler_name, num_inference_steps)
         n = self.images_per_call
         self._ctx.copy_(torch.as_tensor(text_embeddings), non_blocking=True)
@@ -175,7 +176,11 @@ class B200StableDiffusionPipeline:
                 k.x0_ch[j] = st.x0_ch[j]
             k.n_hist, k.push_eps_slot, k.push_x0_slot, k.push_x_slot = (st.n_hist, st.push_eps_slot,
                                                                         st.push_x0_slot, st.push_x_slot)
+            if record is not None:
+                eps_copy = noise_pred.clone()
             L.cfg_scheduler_step(noise_pred, self._latents, k, hist=self._hist, denoised=self._denoised)
+            if record is not None:
+                record.append((st.timestep, eps_copy, self._latents.clone()))
             if callback is not None and i % callback_steps == 0:
                 callback(i, st.timestep, self._latents)
         return self._denoised if return_denoised else self._latents

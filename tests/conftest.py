@@ -18,6 +18,11 @@ def cuda_lib():
 
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
+    # the PyTorch fp32 reference ops must not depend on cuDNN/TF32: loading cuDNN on a fresh box can take
+    # minutes (observed) and TF32 would blur the comparison
+    torch.backends.cudnn.enabled = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
     from b200sd import lib
 
     lib.load()  # raises loudly if libb200sd.so is missing -- never fall back

@@ -241,5 +241,7 @@ def test_cfg_scheduler_step(cuda_lib):
     _close(den, ref_x0, 1e-5, 1e-5, "step x0")
     _close(hist2[3], ref_x0, 1e-5, 1e-5, "history push")
     assert torch.equal(hist2[:2], hist[:2]) and torch.equal(hist2[2], x)
-    want = ref.permute(0, 2, 3, 1).half()
-    assert torch.equal(unet_in[:n, ..., :4], want) and torch.equal(unet_in[n:, ..., :4], want)
+    want = ref.permute(0, 2, 3, 1)  # fp16 rounding of an FMA-contracted fp32 value: compare to 1 half-ulp
+    _close(unet_in[:n, ..., :4], want, 2e-3, 1e-3, "next unet input (uncond half)")
+    _close(unet_in[n:, ..., :4], want, 2e-3, 1e-3, "next unet input (cond half)")
+    assert (unet_in[..., 4:] == 0).all()
