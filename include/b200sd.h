@@ -70,6 +70,7 @@ typedef struct {
     int32_t bias_stride;   /* elements between consecutive bias vectors (0 = n) */
     int32_t split_k;       /* 0 = auto */
     int32_t block_n;       /* 0 = auto; else multiple of 16 in [16, 256] */
+    int32_t act;           /* 0 none; 1 SiLU after the bias (ControlNet conditioning embedder, controlnet.py:36-44) */
     const void* a0;
     const void* a1;
     const void* wgt;

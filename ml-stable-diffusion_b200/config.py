@@ -44,6 +44,34 @@ TINY_UNET = dict(
     flip_sin_to_cos=True, freq_shift=0, transformer_layers_per_block=1,
 )
 
+# tiny SDXL-style config: DownBlock2D first, text_time conditioning, deeper transformer stacks
+TINY_XL_UNET = dict(
+    sample_size=16, in_channels=4, out_channels=4,
+    down_block_types=("DownBlock2D", "CrossAttnDownBlock2D"),
+    up_block_types=("CrossAttnUpBlock2D", "UpBlock2D"),
+    block_out_channels=(64, 128), layers_per_block=2,
+    attention_head_dim=(1, 2), cross_attention_dim=96, norm_num_groups=32, norm_eps=1e-5,
+    flip_sin_to_cos=True, freq_shift=0, transformer_layers_per_block=(1, 2),
+    addition_embed_type="text_time", addition_time_embed_dim=32,
+    projection_class_embeddings_input_dim=64 + 6 * 32,
+)
+
+SD21_CONTROLNET = dict(
+    in_channels=4, block_out_channels=(320, 640, 1280, 1280), layers_per_block=2,
+    down_block_types=("CrossAttnDownBlock2D", "CrossAttnDownBlock2D", "CrossAttnDownBlock2D", "DownBlock2D"),
+    attention_head_dim=(5, 10, 20, 20), cross_attention_dim=1024, norm_num_groups=32, norm_eps=1e-5,
+    flip_sin_to_cos=True, freq_shift=0, transformer_layers_per_block=1,
+    conditioning_embedding_out_channels=(16, 32, 96, 256),
+)
+
+TINY_CONTROLNET = dict(
+    in_channels=4, block_out_channels=(64, 128, 128), layers_per_block=1,
+    down_block_types=("CrossAttnDownBlock2D", "CrossAttnDownBlock2D", "DownBlock2D"),
+    attention_head_dim=(1, 2, 2), cross_attention_dim=96, norm_num_groups=32, norm_eps=1e-5,
+    flip_sin_to_cos=True, freq_shift=0, transformer_layers_per_block=1,
+    conditioning_embedding_out_channels=(16, 32, 96, 256),
+)
+
 SD_VAE = dict(latent_channels=4, out_channels=3, block_out_channels=(128, 256, 512, 512),
               layers_per_block=2, norm_num_groups=32, scaling_factor=0.18215)
 
@@ -137,6 +165,46 @@ def unet_param_shapes(cfg) -> "OrderedDict[str, tuple]":
             _conv(sh, f"up_blocks.{i}.upsamplers.0.conv", out, out, 3)
     _norm(sh, "conv_norm_out", boc[0])
     _conv(sh, "conv_out", cfg["out_channels"], boc[0], 3)
+    return sh
+
+
+def controlnet_param_shapes(cfg) -> "OrderedDict[str, tuple]":
+    """name -> shape for the reference ``ControlNetModel`` (controlnet.py:49-189)."""
+    sh = OrderedDict()
+    boc = list(cfg["block_out_channels"])
+    nb = len(boc)
+    lpb = cfg.get("layers_per_block", 2)
+    depth = _as_list(cfg.get("transformer_layers_per_block", 1), nb)
+    ctx = cfg["cross_attention_dim"]
+    temb = boc[0] * 4
+    _conv(sh, "conv_in", boc[0], cfg.get("in_channels", 4), 3)
+    _conv(sh, "time_embedding.linear_1", temb, boc[0], 1)
+    _conv(sh, "time_embedding.linear_2", temb, temb, 1)
+    ce = list(cfg.get("conditioning_embedding_out_channels", (16, 32, 96, 256)))
+    _conv(sh, "controlnet_cond_embedding.conv_in", ce[0], 3, 3)
+    for i in range(len(ce) - 1):
+        _conv(sh, f"controlnet_cond_embedding.blocks.{2 * i}", ce[i], ce[i], 3)
+        _conv(sh, f"controlnet_cond_embedding.blocks.{2 * i + 1}", ce[i + 1], ce[i], 3)
+    _conv(sh, "controlnet_cond_embedding.conv_out", boc[0], ce[-1], 3)
+    k = 0
+    _conv(sh, f"controlnet_down_blocks.{k}", boc[0], boc[0], 1)
+    out = boc[0]
+    for i, typ in enumerate(cfg["down_block_types"]):
+        inp, out = out, boc[i]
+        for j in range(lpb):
+            _resnet(sh, f"down_blocks.{i}.resnets.{j}", inp if j == 0 else out, out, temb)
+            if typ == "CrossAttnDownBlock2D":
+                _transformer(sh, f"down_blocks.{i}.attentions.{j}", out, ctx, depth[i])
+            k += 1
+            _conv(sh, f"controlnet_down_blocks.{k}", out, out, 1)
+        if i != nb - 1:
+            _conv(sh, f"down_blocks.{i}.downsamplers.0.conv", out, out, 3)
+            k += 1
+            _conv(sh, f"controlnet_down_blocks.{k}", out, out, 1)
+    _conv(sh, "controlnet_mid_block", boc[-1], boc[-1], 1)
+    _resnet(sh, "mid_block.resnets.0", boc[-1], boc[-1], temb)
+    _transformer(sh, "mid_block.attentions.0", boc[-1], ctx, 1)  # controlnet.py:168-180: default depth 1
+    _resnet(sh, "mid_block.resnets.1", boc[-1], boc[-1], temb)
     return sh
 
 

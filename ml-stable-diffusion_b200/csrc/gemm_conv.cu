@@ -33,6 +33,7 @@ struct __align__(64) GemmParams {
     int m_tiles, n_tiles, block_n, stages;
     int n_img, Hout, Wout, stride, bw_log2, bh_log2, tiles_w, tiles_h;
     int bias_rows, bias_stride, geglu, out_f32;
+    int act;         // 0 none, 1 SiLU after bias (generic variant only)
     int bias_mode;   // 0 none, 1 staged in smem (<= 2 vectors per tile), 2 read from global per chunk
     int res_smem;    // 1: residual tile prefetched into smem with cp.async
     void* out;
@@ -100,6 +101,10 @@ __device__ __forceinline__ void epilogue_store16(const GemmParams& p, float (&ac
             for (int j = 0; j < 16; ++j)
                 if (col0 + j < p.N) acc[j] += bias[j];
         }
+    }
+    if (kGeneric && p.act == 1) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j] = silu_f(acc[j]);
     }
     int ocol0 = col0;
     const int nvals = geglu ? 8 : 16;
@@ -514,7 +519,7 @@ static int plan_gemm(const b200sd_gemm_args& a, GemmPlan& pl) {
     if (a.geglu) B200SD_REQUIRE(a.n % 16 == 0, "b200sd_gemm: GEGLU needs n %% 16 == 0");
     // ---- tile shape / split-K selection by a small cost model (cycles; constants fitted to B200 runs) ----
     const int sms = num_sms();
-    const bool can_split = !a.geglu && a.n % 4 == 0;
+    const bool can_split = !a.geglu && a.n % 4 == 0 && a.act == 0;
     auto epi_cycles = [&](int bn) { return 400.0 + (bn / 32.0) * (a.geglu ? 520.0 : 230.0); };
     auto kb_cycles = [&](int bn) { return std::max(2.0 * bn, (kAStage + 128.0 * bn) / 38.0); };
     double best_t = 1e30;
@@ -660,6 +665,7 @@ static int launch_gemm(const b200sd_gemm_args& a, cudaStream_t stream) {
     p.bias_stride = a.bias_stride > 0 ? a.bias_stride : a.n;
     p.geglu = a.geglu;
     p.out_f32 = a.out_f32;
+    p.act = a.act;
     p.bias_mode = pl.bias_mode;
     p.res_smem = pl.res_smem;
     p.out = a.out;
@@ -671,7 +677,8 @@ static int launch_gemm(const b200sd_gemm_args& a, cudaStream_t stream) {
     const int total = pl.m_tiles * pl.n_tiles * pl.splits;
     const int grid = std::min(total, num_sms());
     // compile-time epilogue variants for the hot shapes; anything irregular takes the generic kernel
-    const bool regular = (a.n % 16 == 0) && (p.n_store % 8 == 0) && (pl.block_n % 32 == 0) && pl.bias_mode != 2 &&
+    B200SD_REQUIRE(a.act == 0 || (a.act == 1 && pl.splits == 1 && !a.geglu), "b200sd_gemm: act=%d unsupported here", a.act);
+    const bool regular = (a.act == 0) && (a.n % 16 == 0) && (p.n_store % 8 == 0) && (pl.block_n % 32 == 0) && pl.bias_mode != 2 &&
                          (a.residual == nullptr || pl.res_smem || pl.splits > 1);
     using KernelFn = void (*)(GemmParams);
     KernelFn fn;

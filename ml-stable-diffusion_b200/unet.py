@@ -87,6 +87,7 @@ class UNetEngine:
         self.lpb = cfg.get("layers_per_block", 2)
         self.heads = _as_list(cfg.get("attention_head_dim", 8), nb)
         self.depth = _as_list(cfg.get("transformer_layers_per_block", 1), nb)
+        self.mid_depth = cfg.get("mid_block_transformer_layers", self.depth[-1])
         self.groups = cfg.get("norm_num_groups", 32)
         self.eps = cfg.get("norm_eps", 1e-5)
         self.down_types = list(cfg["down_block_types"])
@@ -171,7 +172,7 @@ class UNetEngine:
                 p = f"down_blocks.{i}.downsamplers.0.conv"
                 w[p] = {"w": P.conv3(p), "b": P.bias(p)}
         resnet("mid_block.resnets.0")
-        transformer("mid_block.attentions.0", boc[-1], self.depth[-1])
+        transformer("mid_block.attentions.0", boc[-1], self.mid_depth)
         resnet("mid_block.resnets.1")
         rboc, rdepth = boc[::-1], self.depth[::-1]
         for i, typ in enumerate(self.up_types):

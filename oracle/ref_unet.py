@@ -154,3 +154,12 @@ def build_unet(cfg: dict, state_dict: dict | None = None, xl: bool = False, impl
 def set_attention_impl(impl: str):
     ref = load()
     ref.unet.ATTENTION_IMPLEMENTATION_IN_EFFECT = ref.unet.AttentionImplementations[impl]
+
+
+def build_controlnet(cfg: dict, state_dict: dict | None = None):
+    """Instantiate the reference ControlNetModel (controlnet.py:49-189) on CPU/fp32."""
+    ref = load()
+    model = ref.controlnet.ControlNetModel(**cfg).eval()
+    if state_dict is not None:
+        model.load_state_dict({k: v.clone().float() for k, v in state_dict.items()})
+    return model

@@ -196,6 +196,44 @@ def unet_forward(sd, cfg, sample, timestep, encoder_hidden_states, time_ids=None
     return _conv(sd, "conv_out", x, padding=1)
 
 
+def controlnet_forward(sd, cfg, sample, timestep, encoder_hidden_states, controlnet_cond):
+    """Restates ``ControlNetModel.forward`` (controlnet.py:199-250) and the conditioning embedder
+    (:15-47).  Returns the list of down residuals followed by the mid residual."""
+    boc = list(cfg["block_out_channels"])
+    nb = len(boc)
+    lpb = cfg.get("layers_per_block", 2)
+    heads = _as_list(cfg.get("attention_head_dim", 8), nb)
+    depth = _as_list(cfg.get("transformer_layers_per_block", 1), nb)
+    groups = cfg.get("norm_num_groups", 32)
+    eps = cfg.get("norm_eps", 1e-5)
+    ctx = encoder_hidden_states.float()
+    temb = _time_mlp(sd, "time_embedding",
+                     timestep_embedding(timestep, boc[0], cfg.get("flip_sin_to_cos", True), cfg.get("freq_shift", 0)))
+    ce = list(cfg.get("conditioning_embedding_out_channels", (16, 32, 96, 256)))
+    e = F.silu(_conv(sd, "controlnet_cond_embedding.conv_in", controlnet_cond.float(), padding=1))
+    for i in range(len(ce) - 1):
+        e = F.silu(_conv(sd, f"controlnet_cond_embedding.blocks.{2 * i}", e, padding=1))
+        e = F.silu(_conv(sd, f"controlnet_cond_embedding.blocks.{2 * i + 1}", e, stride=2, padding=1))
+    e = _conv(sd, "controlnet_cond_embedding.conv_out", e, padding=1)
+    x = _conv(sd, "conv_in", sample.float(), padding=1) + e
+    skips = [x]
+    for i, typ in enumerate(cfg["down_block_types"]):
+        for j in range(lpb):
+            x = _resnet(sd, f"down_blocks.{i}.resnets.{j}", x, temb, groups, eps)
+            if typ == "CrossAttnDownBlock2D":
+                x = _spatial_transformer(sd, f"down_blocks.{i}.attentions.{j}", x, ctx, heads[i], depth[i])
+            skips.append(x)
+        if i != nb - 1:
+            x = _conv(sd, f"down_blocks.{i}.downsamplers.0.conv", x, stride=2, padding=1)
+            skips.append(x)
+    x = _resnet(sd, "mid_block.resnets.0", x, temb, groups, eps)
+    x = _spatial_transformer(sd, "mid_block.attentions.0", x, ctx, heads[-1], 1)
+    x = _resnet(sd, "mid_block.resnets.1", x, temb, groups, eps)
+    outs = [_conv(sd, f"controlnet_down_blocks.{k}", s) for k, s in enumerate(skips)]
+    outs.append(_conv(sd, "controlnet_mid_block", x))
+    return outs
+
+
 # --------------------------------------------------------------------------------------
 # VAE decoder (diffusers AutoencoderKL.decoder o post_quant_conv) -- parity unpinned
 # --------------------------------------------------------------------------------------

@@ -58,6 +58,30 @@ def main():
                             **{f"noise_pred_{k}": v.astype(np.float32) for k, v in outs.items()})
         print(name, {k: float(np.abs(v).max()) for k, v in outs.items()})
 
+    # ---- SDXL-style UNet (UNet2DConditionModelXL) and ControlNetModel, tiny configs ------------------------
+    cfg = config.TINY_XL_UNET
+    sd = config.random_state_dict(config.unet_param_shapes(cfg), seed=3)
+    x, c = unet_inputs(cfg, 9)
+    gg = torch.Generator().manual_seed(10)
+    tid = torch.tensor([[64.0, 64.0, 0.0, 0.0, 64.0, 64.0]] * 2)
+    te = torch.randn(2, 64, generator=gg)
+    m = ref_unet.build_unet(cfg, sd, xl=True, impl="SPLIT_EINSUM")
+    with torch.no_grad():
+        y = m(x, torch.tensor([981.0, 981.0]), c, tid, te)[0].numpy()
+    np.savez_compressed(os.path.join(OUT, "unet_tiny_xl.npz"), weight_seed=3, input_seed=9, fingerprint=fingerprint(sd),
+                        text_embeds=te.numpy(), time_ids=tid.numpy(), noise_pred=y.astype(np.float32))
+    ccfg = config.TINY_CONTROLNET
+    csd = config.random_state_dict(config.controlnet_param_shapes(ccfg), seed=4)
+    x, c = unet_inputs(config.TINY_UNET, 6)
+    cond = torch.rand(2, 3, 128, 128, generator=torch.Generator().manual_seed(7))
+    cn = ref_unet.build_controlnet(ccfg, csd)
+    with torch.no_grad():
+        down, mid = cn(x.clone(), torch.tensor([501.0, 501.0]), c, cond)
+    np.savez_compressed(os.path.join(OUT, "controlnet_tiny.npz"), weight_seed=4, input_seed=6, cond_seed=7,
+                        fingerprint=fingerprint(csd),
+                        **{f"residual_{i}": r.numpy().astype(np.float32) for i, r in enumerate(list(down) + [mid])})
+    print("xl + controlnet done")
+
     # ---- attention variants + LayerNormANE on their own ---------------------------------------
     g = torch.Generator().manual_seed(5)
     q = torch.randn(2, 128, 1, 200, generator=g)

@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header():
     from b200sd import lib
 
-    # b200sd_gemm_args: 15 int32 (60 B, padded to 64) + 7 pointers + size_t
+    # b200sd_gemm_args: 16 int32 (64 B) + 7 pointers + size_t
     assert ctypes.sizeof(lib.GemmArgs) == 64 + 7 * 8 + 8
     assert lib.GemmArgs.a0.offset == 64
     # b200sd_step_coeffs: 13 floats + 4 int32

@@ -46,6 +46,38 @@ def test_restated_unet_matches_reference_golden(name, cfg):
             assert R.compute_psnr(torch.from_numpy(y), torch.from_numpy(gold[key])) > 100
 
 
+def test_restated_xl_and_controlnet_match_reference_golden():
+    gold = _load("unet_tiny_xl.npz")
+    cfg = config.TINY_XL_UNET
+    sd = config.random_state_dict(config.unet_param_shapes(cfg), seed=int(gold["weight_seed"]))
+    assert np.allclose(_fingerprint(sd), gold["fingerprint"], rtol=1e-6)
+    x, c = _inputs(cfg, int(gold["input_seed"]))
+    with torch.no_grad():
+        y = R.unet_forward(sd, cfg, x, torch.tensor([981.0, 981.0]), c, time_ids=torch.from_numpy(gold["time_ids"]),
+                           text_embeds=torch.from_numpy(gold["text_embeds"])).numpy()
+    assert np.abs(y - gold["noise_pred"]).max() < 2e-5
+    gold = _load("controlnet_tiny.npz")
+    ccfg = config.TINY_CONTROLNET
+    csd = config.random_state_dict(config.controlnet_param_shapes(ccfg), seed=int(gold["weight_seed"]))
+    assert np.allclose(_fingerprint(csd), gold["fingerprint"], rtol=1e-6)
+    x, c = _inputs(config.TINY_UNET, int(gold["input_seed"]))
+    cond = torch.rand(2, 3, 128, 128, generator=torch.Generator().manual_seed(int(gold["cond_seed"])))
+    with torch.no_grad():
+        outs = R.controlnet_forward(csd, ccfg, x, torch.tensor([501.0, 501.0]), c, cond)
+    assert len(outs) == 7
+    for i, o in enumerate(outs):
+        assert np.abs(o.numpy() - gold[f"residual_{i}"]).max() < 2e-5, i
+
+
+@pytest.mark.skipif(not ref_unet.available(), reason="reference tree not present on this box")
+def test_controlnet_schema_matches_reference_modules():
+    for cfg in (config.TINY_CONTROLNET, config.SD21_CONTROLNET):
+        with torch.device("meta"):
+            m = ref_unet.build_controlnet(cfg)
+        ref_shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+        assert ref_shapes == {k: tuple(v) for k, v in config.controlnet_param_shapes(cfg).items()}
+
+
 def test_restated_blocks_match_reference_golden():
     g = _load("blocks.npz")
     q, k, v = (torch.from_numpy(g[n]) for n in "qkv")

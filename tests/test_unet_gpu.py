@@ -216,3 +216,54 @@ def test_pipeline_tiny_batched_and_schedulers(cuda_lib):
         rel = float((final - x).abs().max() / x.abs().max())
         print(f"{name}: end-to-end latent rel err after {steps} steps = {rel:.3e}")
         assert rel < 5e-2, name
+
+
+def test_unet_tiny_xl_text_time_conditioning(cuda_lib):
+    """SDXL-style forward (UNet2DConditionModelXL.forward, unet.py:1051-1152): text_time added conditioning,
+    DownBlock2D first level, transformer depth > 1."""
+    from b200sd.model import UNetModel
+
+    cfg = config.TINY_XL_UNET
+    sd = config.random_state_dict(config.unet_param_shapes(cfg), seed=3)
+    x, c = _inputs(cfg, 9)
+    g = torch.Generator().manual_seed(10)
+    tid = torch.tensor([[64.0, 64.0, 0.0, 0.0, 64.0, 64.0]] * 2)
+    te = torch.randn(2, 64, generator=g)
+    t = np.array([981.0, 981.0], np.float16)
+    m = UNetModel(cfg, sd, batch=2, height=16, width=16, use_cuda_graph=False)
+    out = m(sample=x.half().numpy(), timestep=t, encoder_hidden_states=c.half().numpy(),
+            time_ids=tid.half().numpy(), text_embeds=te.half().numpy())["noise_pred"]
+    with torch.no_grad():
+        ref = R.unet_forward(sd, cfg, x, torch.tensor([981.0, 981.0]), c, time_ids=tid,
+                             text_embeds=te.half().float()).numpy()
+    _check(out, ref, "tiny SDXL-style unet")
+
+
+def test_controlnet_tiny_vs_oracle_and_chain_into_unet(cuda_lib):
+    """ControlNetModel.forward (controlnet.py:199-250) residuals, then fed to the control-UNet exactly like the
+    reference loop does (pipeline.py:516-536)."""
+    from b200sd.controlnet import ControlNetModel
+    from b200sd.model import UNetModel
+
+    ccfg = config.TINY_CONTROLNET
+    csd = config.random_state_dict(config.controlnet_param_shapes(ccfg), seed=4)
+    ucfg = dict(config.TINY_UNET, support_controlnet=True)
+    usd = config.random_state_dict(config.unet_param_shapes(ucfg), seed=5)
+    x, c = _inputs(config.TINY_UNET, 6)
+    cond = torch.rand(2, 3, 128, 128, generator=torch.Generator().manual_seed(7))
+    t = np.array([501.0, 501.0], np.float16)
+    cn = ControlNetModel(ccfg, csd, batch=2, height=16, width=16)
+    res = cn(sample=x.half().numpy(), timestep=t, encoder_hidden_states=c.half().numpy(),
+             controlnet_cond=cond.half().numpy())
+    with torch.no_grad():
+        ref = R.controlnet_forward(csd, ccfg, x, torch.tensor([501.0, 501.0]), c, cond.half().float())
+    assert len(res) == len(ref) == 7
+    for i, r in enumerate(ref):
+        _check(res[f"additional_residual_{i}"], r.numpy(), f"controlnet residual {i}",
+               max_abs=1e-2 * max(1.0, float(r.abs().max())))
+    unet = UNetModel(ucfg, usd, batch=2, height=16, width=16, use_cuda_graph=False)
+    kw = {k: v.astype(np.float16) for k, v in res.items()}
+    out = unet(sample=x.half().numpy(), timestep=t, encoder_hidden_states=c.half().numpy(), **kw)["noise_pred"]
+    with torch.no_grad():
+        uref = R.unet_forward(usd, ucfg, x, torch.tensor([501.0, 501.0]), c, additional_residuals=ref).numpy()
+    _check(out, uref, "controlnet -> control-unet chain")
