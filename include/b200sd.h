@@ -71,6 +71,8 @@ typedef struct {
     int32_t split_k;       /* 0 = auto */
     int32_t block_n;       /* 0 = auto; else multiple of 16 in [16, 256] */
     int32_t act;           /* 0 none; 1 SiLU after the bias (ControlNet conditioning embedder, controlnet.py:36-44) */
+    int32_t wgt_tiled;     /* 1: `wgt` is pre-tiled [n_tiles][k_blocks][block_n][64] (block_n must be given): every
+                              weight tile is one contiguous block_n*128-byte burst instead of block_n strided rows */
     const void* a0;
     const void* a1;
     const void* wgt;
@@ -82,6 +84,9 @@ typedef struct {
 } b200sd_gemm_args;
 
 int b200sd_gemm(const b200sd_gemm_args* args, void* stream);
+/* host-only: block_n / split count / k-block count the launcher would choose: out[0..3] = block_n, splits,
+ * kb_total, n_tiles */
+int b200sd_gemm_plan(const b200sd_gemm_args* args, int32_t* out4);
 /* host-only: human-readable tiling plan (tile shape, split-K, pipeline depth) the launcher would use */
 int b200sd_gemm_describe_plan(const b200sd_gemm_args* args, char* buf, size_t buf_size);
 /* bytes of fp32 scratch b200sd_gemm would need for these args (0 if no split-K) */

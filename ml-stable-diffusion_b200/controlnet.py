@@ -63,7 +63,7 @@ class ControlNetEngine(UNetEngine):
         """Returns the list of NHWC fp16 residuals: 12 (or fewer) down residuals + the mid residual."""
         batch = sample.shape[0]
         temb_all = self.time_embedding(timesteps)
-        kv_all = L.linear(ctx_tokens, self.kv_w) if self.kv_w is not None else None
+        kv_all = L.linear(ctx_tokens, self.kv_w, static_w=True) if self.kv_w is not None else None
         e = self.embed_condition(cond_nhwc)
         x = L.conv3x3(sample, self.w["conv_in"]["w"], self.w["conv_in"]["b"], e)   # conv_in(sample) + embedding
         skips = [x]
@@ -83,9 +83,9 @@ class ControlNetEngine(UNetEngine):
         outs = []
         for s, (w, b) in zip(skips, self.zero_convs):
             n, h, wd, c = s.shape
-            outs.append(L.linear(s.reshape(n * h * wd, c), w, b).reshape(n, h, wd, c))
+            outs.append(L.linear(s.reshape(n * h * wd, c), w, b, static_w=True).reshape(n, h, wd, c))
         n, h, wd, c = x.shape
-        outs.append(L.linear(x.reshape(n * h * wd, c), self.zero_mid[0], self.zero_mid[1]).reshape(n, h, wd, c))
+        outs.append(L.linear(x.reshape(n * h * wd, c), self.zero_mid[0], self.zero_mid[1], static_w=True).reshape(n, h, wd, c))
         return outs
 
 

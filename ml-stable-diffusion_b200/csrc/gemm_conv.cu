@@ -34,6 +34,7 @@ struct __align__(64) GemmParams {
     int n_img, Hout, Wout, stride, bw_log2, bh_log2, tiles_w, tiles_h;
     int bias_rows, bias_stride, geglu, out_f32;
     int act;         // 0 none, 1 SiLU after bias (generic variant only)
+    int wgt_tiled;   // B operand pre-tiled: tile (n_tile, kb) starts at row (n_tile * kb_total + kb) * block_n
     int bias_mode;   // 0 none, 1 staged in smem (<= 2 vectors per tile), 2 read from global per chunk
     int res_smem;    // 1: residual tile prefetched into smem with cp.async
     void* out;
@@ -266,8 +267,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) umma_gemm_kernel(const __grid
                         tma_load_4d(dst_a, tmA, &full_bar[stage], c, t.w0 * p.stride + s - 1,
                                     t.h0 * p.stride + r - 1, t.n0, kEvictNormal);
                     }
-                    tma_load_2d(smem_b + stage * b_stage, &p.tmB, &full_bar[stage], wk, t.n_tile * p.block_n,
-                                kEvictLast);
+                    if (p.wgt_tiled)
+                        tma_load_2d(smem_b + stage * b_stage, &p.tmB, &full_bar[stage], 0,
+                                    (t.n_tile * p.kb_total + kb) * p.block_n, kEvictFirst);
+                    else
+                        tma_load_2d(smem_b + stage * b_stage, &p.tmB, &full_bar[stage], wk, t.n_tile * p.block_n,
+                                    kEvictLast);
                     if (++stage == p.stages) {
                         stage = 0;
                         phase ^= 1;
@@ -630,7 +635,14 @@ static int launch_gemm(const b200sd_gemm_args& a, cudaStream_t stream) {
                 return rc;
         }
     }
-    {
+    if (a.wgt_tiled) {
+        B200SD_REQUIRE(a.block_n == pl.block_n, "b200sd_gemm: tiled weights need an explicit block_n");
+        const uint64_t rows = static_cast<uint64_t>(pl.n_tiles) * pl.kb_total * pl.block_n;
+        const uint64_t dims[2] = {kBK, rows};
+        const uint64_t str[1] = {kBK * 2};
+        const uint32_t box[2] = {kBK, static_cast<uint32_t>(pl.block_n)};
+        if (int rc = encode_tmap_f16(&p.tmB, a.wgt, 2, dims, str, box, es1)) return rc;
+    } else {
         const uint64_t ktot = static_cast<uint64_t>(pl.taps) * pl.Kpt;
         const uint64_t dims[2] = {ktot, static_cast<uint64_t>(a.n)};
         const uint64_t str[1] = {ktot * 2};
@@ -666,6 +678,7 @@ static int launch_gemm(const b200sd_gemm_args& a, cudaStream_t stream) {
     p.geglu = a.geglu;
     p.out_f32 = a.out_f32;
     p.act = a.act;
+    p.wgt_tiled = a.wgt_tiled;
     p.bias_mode = pl.bias_mode;
     p.res_smem = pl.res_smem;
     p.out = a.out;
@@ -722,6 +735,14 @@ extern "C" int b200sd_gemm(const b200sd_gemm_args* args, void* stream) {
         return 2;
     }
     return b200sd::launch_gemm(*args, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int b200sd_gemm_plan(const b200sd_gemm_args* args, int32_t* out4) {
+    if (!args || !out4) return 2;
+    b200sd::GemmPlan pl;
+    if (int rc = b200sd::plan_gemm(*args, pl)) return rc;
+    out4[0] = pl.block_n, out4[1] = pl.splits, out4[2] = pl.kb_total, out4[3] = pl.n_tiles;
+    return 0;
 }
 
 extern "C" int b200sd_gemm_describe_plan(const b200sd_gemm_args* args, char* buf, size_t buf_size) {

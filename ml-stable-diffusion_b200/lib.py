@@ -5,6 +5,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import weakref
 
 import torch
 
@@ -23,7 +24,7 @@ class GemmArgs(C.Structure):
         ("n_img", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("stride", C.c_int32),
         ("geglu", C.c_int32), ("out_f32", C.c_int32), ("bias_rows", C.c_int32), ("bias_stride", C.c_int32),
         ("split_k", C.c_int32),
-        ("block_n", C.c_int32), ("act", C.c_int32),
+        ("block_n", C.c_int32), ("act", C.c_int32), ("wgt_tiled", C.c_int32),
         ("a0", C.c_void_p), ("a1", C.c_void_p), ("wgt", C.c_void_p), ("bias", C.c_void_p),
         ("residual", C.c_void_p), ("out", C.c_void_p), ("workspace", C.c_void_p),
         ("workspace_bytes", C.c_size_t),
@@ -45,6 +46,7 @@ _SIGNATURES = {
     "b200sd_set_pdl": (None, [C.c_int]),
     "b200sd_gemm": (C.c_int, [C.POINTER(GemmArgs), C.c_void_p]),
     "b200sd_gemm_workspace_bytes": (C.c_size_t, [C.POINTER(GemmArgs)]),
+    "b200sd_gemm_plan": (C.c_int, [C.POINTER(GemmArgs), C.POINTER(C.c_int32)]),
     "b200sd_gemm_describe_plan": (C.c_int, [C.POINTER(GemmArgs), C.c_char_p, C.c_size_t]),
     "b200sd_linear_small": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                       C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
@@ -179,6 +181,51 @@ def describe_plan(mode, m=0, n=0, c0=0, c1=0, n_img=0, h=0, w=0, stride=1, geglu
     return buf.value.decode()
 
 
+TILED_WEIGHTS = os.environ.get("B200SD_TILED_W", "1") != "0"
+_tiled_cache = {}
+
+
+def pack_tiled(w2d, c0, c1, taps, bn):
+    """[N, taps*(c0+c1)] -> [n_tiles, k_blocks, bn, 64] fp16 in the exact k-block order of the kernel's main
+    loop (tap-major; per tap the 64-channel chunks of source 0, then of source 1; ragged chunks zero padded), so
+    that each weight tile is one contiguous bn*128-byte burst in HBM."""
+    n, kpt = w2d.shape[0], c0 + c1
+    kc0, kc1 = (c0 + 63) // 64, (c1 + 63) // 64
+    kc = kc0 + kc1
+    nt = (n + bn - 1) // bn
+    wp = torch.zeros(nt * bn, taps, kpt, dtype=w2d.dtype, device=w2d.device)
+    wp[:n] = w2d.reshape(n, taps, kpt)
+    out = torch.zeros(nt, taps, kc, bn, 64, dtype=w2d.dtype, device=w2d.device)
+    for j in range(kc):
+        lo = j * 64 if j < kc0 else c0 + (j - kc0) * 64
+        hi = min(lo + 64, c0 if j < kc0 else kpt)
+        out[:, :, j, :, : hi - lo] = wp[:, :, lo:hi].reshape(nt, bn, taps, hi - lo).permute(0, 2, 1, 3)
+    return out.reshape(nt, taps * kc, bn, 64).contiguous()
+
+
+def _maybe_tile_weights(args, wgt, taps):
+    """Static weight operands are re-laid out once per (weight, block_n) and cached."""
+    plan = (C.c_int32 * 4)()
+    _check(load().b200sd_gemm_plan(C.byref(args), plan), "b200sd_gemm_plan")
+    bn = int(plan[0])
+    key = (wgt.data_ptr(), bn, args.c0, args.c1, taps)
+    hit = _tiled_cache.get(key)
+    packed = None
+    if hit is not None and hit[0]() is wgt and hit[1] == wgt._version:
+        packed = hit[2]
+    if packed is None:
+        if torch.cuda.is_current_stream_capturing():
+            return  # never pack during capture; the warm-up pass has populated the cache for these shapes
+        packed = pack_tiled(wgt, args.c0, args.c1, taps, bn)
+        if len(_tiled_cache) > 4096:  # drop entries whose source tensor is gone
+            for k in [k for k, v in _tiled_cache.items() if v[0]() is None]:
+                del _tiled_cache[k]
+        _tiled_cache[key] = (weakref.ref(wgt), wgt._version, packed)
+    args.wgt = packed.data_ptr()
+    args.block_n = bn
+    args.wgt_tiled = 1
+
+
 def gemm_workspace_bytes(args) -> int:
     return int(load().b200sd_gemm_workspace_bytes(C.byref(args)))
 
@@ -206,8 +253,9 @@ def _workspace(nbytes, device):
 
 
 def linear(x, wgt, bias=None, residual=None, *, x1=None, geglu=False, out_dtype=torch.float16, split_k=0,
-           block_n=0, bias_rows=0, bias_stride=0, out=None):
-    """out[M, N] = epilogue([x | x1] @ wgt^T).  x [M, C0] fp16, wgt [N, C0(+C1)] fp16, bias fp32 [N]."""
+           block_n=0, bias_rows=0, bias_stride=0, out=None, static_w=False):
+    """out[M, N] = epilogue([x | x1] @ wgt^T).  x [M, C0] fp16, wgt [N, C0(+C1)] fp16, bias fp32 [N].
+    static_w: `wgt` is a model weight (constant address/content) and may be re-tiled + cached."""
     _req(x, torch.float16, "linear x")
     _req(wgt, torch.float16, "linear wgt")
     m, n = x.shape[0], wgt.shape[0]
@@ -216,6 +264,8 @@ def linear(x, wgt, bias=None, residual=None, *, x1=None, geglu=False, out_dtype=
         out = torch.empty(m, n_out, dtype=out_dtype, device=x.device)
     args = gemm_args(0, x, wgt, out, a1=x1, bias=bias, residual=residual, m=m, n=n, geglu=geglu,
                      bias_rows=bias_rows, bias_stride=bias_stride, split_k=split_k, block_n=block_n)
+    if static_w and TILED_WEIGHTS:
+        _maybe_tile_weights(args, wgt, 1)
     need = gemm_workspace_bytes(args)
     if need:
         ws = _workspace(need, x.device)
@@ -226,7 +276,7 @@ def linear(x, wgt, bias=None, residual=None, *, x1=None, geglu=False, out_dtype=
 
 
 def conv3x3(x, wgt, bias=None, residual=None, *, x1=None, stride=1, out_dtype=torch.float16, split_k=0,
-            block_n=0, bias_rows=0, bias_stride=0, out=None, act=0):
+            block_n=0, bias_rows=0, bias_stride=0, out=None, act=0, static_w=True):
     """3x3 pad-1 convolution.  x NHWC fp16 [N, H, W, C0]; wgt [Cout, 9*(C0+C1)] fp16 (OHWI);
     bias fp32 [Cout] or [N_img, Cout] with bias_rows = Hout*Wout."""
     _req(x, torch.float16, "conv3x3 x")
@@ -238,6 +288,8 @@ def conv3x3(x, wgt, bias=None, residual=None, *, x1=None, stride=1, out_dtype=to
         out = torch.empty(nimg, ho, wo, cout, dtype=out_dtype, device=x.device)
     args = gemm_args(1, x, wgt, out, a1=x1, bias=bias, residual=residual, n=cout, n_img=nimg, h=h, w=w,
                      stride=stride, bias_rows=bias_rows, bias_stride=bias_stride, split_k=split_k, block_n=block_n, act=act)
+    if static_w and TILED_WEIGHTS:
+        _maybe_tile_weights(args, wgt, 9)
     need = gemm_workspace_bytes(args)
     if need:
         ws = _workspace(need, x.device)

@@ -219,7 +219,7 @@ class UNetEngine:
         hh = L.group_norm(hh, r["n2g"], r["n2b"], self.groups, self.eps, silu=True)
         if "sc" in r:
             res = L.linear(x.reshape(n * h * wd, -1), r["sc"], r["scb"],
-                           x1=None if x1 is None else x1.reshape(n * h * wd, -1))
+                           x1=None if x1 is None else x1.reshape(n * h * wd, -1), static_w=True)
         else:
             res = x
         return L.conv3x3(hh, r["c2"], r["c2b"], res)
@@ -230,21 +230,21 @@ class UNetEngine:
         m, s = n * h * wd, h * wd
         impl = _IMPL_CODE[ATTENTION_IMPLEMENTATION_IN_EFFECT]
         hn = L.group_norm(x, t["ng"], t["nb"], 32, 1e-6, silu=False)
-        tok = L.linear(hn.reshape(m, c), t["pi"], t["pib"])
+        tok = L.linear(hn.reshape(m, c), t["pi"], t["pib"], static_w=True)
         for blk in t["blocks"]:
             n1 = L.layer_norm(tok, blk["ln1g"], blk["ln1b"])
-            qkv = L.linear(n1, blk["qkv"])
+            qkv = L.linear(n1, blk["qkv"], static_w=True)
             a = L.attention(qkv[:, :c], qkv[:, c:2 * c], qkv[:, 2 * c:], batch, heads, s, s, impl=impl)
-            tok = L.linear(a, blk["o1"], blk["o1b"], tok)
+            tok = L.linear(a, blk["o1"], blk["o1b"], tok, static_w=True)
             n2 = L.layer_norm(tok, blk["ln2g"], blk["ln2b"])
-            q = L.linear(n2, blk["q2"])
+            q = L.linear(n2, blk["q2"], static_w=True)
             ko = blk["kv_off"]
             a = L.attention(q, kv_all[:, ko:ko + c], kv_all[:, ko + c:ko + 2 * c], batch, heads, s, s_ctx, impl=impl)
-            tok = L.linear(a, blk["o2"], blk["o2b"], tok)
+            tok = L.linear(a, blk["o2"], blk["o2b"], tok, static_w=True)
             n3 = L.layer_norm(tok, blk["ln3g"], blk["ln3b"])
-            g = L.linear(n3, blk["gg"], blk["ggb"], geglu=True)
-            tok = L.linear(g, blk["f2"], blk["f2b"], tok)
-        out = L.linear(tok, t["po"], t["pob"], x.reshape(m, c))
+            g = L.linear(n3, blk["gg"], blk["ggb"], geglu=True, static_w=True)
+            tok = L.linear(g, blk["f2"], blk["f2b"], tok, static_w=True)
+        out = L.linear(tok, t["po"], t["pob"], x.reshape(m, c), static_w=True)
         return out.reshape(n, h, wd, c)
 
     # ------------------------------------------------------------------ forward
@@ -271,7 +271,7 @@ class UNetEngine:
         Returns noise_pred NHWC fp32 [B, H, W, out_ch]."""
         batch = sample.shape[0]
         temb_all = self.time_embedding(timesteps, time_ids, text_embeds)
-        kv_all = L.linear(ctx_tokens, self.kv_w) if self.kv_w is not None else None
+        kv_all = L.linear(ctx_tokens, self.kv_w, static_w=True) if self.kv_w is not None else None
         x = L.conv3x3(sample, self.w["conv_in"]["w"], self.w["conv_in"]["b"])
         skips = [x]
         for i, typ in enumerate(self.down_types):

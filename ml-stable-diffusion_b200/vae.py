@@ -69,7 +69,7 @@ class VAEDecoderEngine:
         hh = L.group_norm(x, r["n1g"], r["n1b"], self.groups, 1e-6, silu=True)
         hh = L.conv3x3(hh, r["c1"], r["c1b"])
         hh = L.group_norm(hh, r["n2g"], r["n2b"], self.groups, 1e-6, silu=True)
-        res = L.linear(x.reshape(n * h * wd, -1), r["sc"], r["scb"]) if "sc" in r else x
+        res = L.linear(x.reshape(n * h * wd, -1), r["sc"], r["scb"], static_w=True) if "sc" in r else x
         return L.conv3x3(hh, r["c2"], r["c2b"], res)
 
     def _attention(self, p, x):
@@ -77,8 +77,8 @@ class VAEDecoderEngine:
         n, h, wd, c = x.shape
         s = h * wd
         hn = L.group_norm(x, a["ng"], a["nb"], self.groups, 1e-6, silu=False).reshape(n * s, c)
-        q = L.linear(hn, a["q"], a["qb"])
-        k = L.linear(hn, a["k"], a["kb"])
+        q = L.linear(hn, a["q"], a["qb"], static_w=True)
+        k = L.linear(hn, a["k"], a["kb"], static_w=True)
         xr = x.reshape(n * s, c)
         out = torch.empty_like(xr)
         for i in range(n):
@@ -89,7 +89,7 @@ class VAEDecoderEngine:
             scores = L.linear(q[rows], k[rows], out_dtype=torch.float32)
             prob = L.softmax_rows(scores, c ** -0.5)
             att = L.linear(prob, vt, a["vb"])
-            L.linear(att, a["o"], a["ob"], xr[rows], out=out[rows])
+            L.linear(att, a["o"], a["ob"], xr[rows], out=out[rows], static_w=True)
         return out.reshape(n, h, wd, c)
 
     def forward(self, z):
