@@ -15,6 +15,8 @@
 #include "../../include/b200sd.h"
 
 #include <algorithm>
+#include <cmath>
+#include <stdlib.h>
 
 namespace b200sd {
 
@@ -34,6 +36,8 @@ struct __align__(64) GemmParams {
     int n_img, Hout, Wout, stride, bw_log2, bh_log2, tiles_w, tiles_h;
     int bias_rows, bias_stride, geglu, out_f32;
     int act;         // 0 none, 1 SiLU after bias (generic variant only)
+    int fused_reduce;  // split-K: the split CTAs of a tile meet at a counter and reduce-scatter it in-kernel
+    unsigned int* tile_ctr;
     int wgt_tiled;   // B operand pre-tiled: tile (n_tile, kb) starts at row (n_tile * kb_total + kb) * block_n
     int bias_mode;   // 0 none, 1 staged in smem (<= 2 vectors per tile), 2 read from global per chunk
     int res_smem;    // 1: residual tile prefetched into smem with cp.async
@@ -415,6 +419,65 @@ __global__ void __launch_bounds__(kGemmThreads, 1) umma_gemm_kernel(const __grid
             }
             tc_fence_before();
             mbar_arrive(&tmem_empty[as]);
+            if (kPartial && p.fused_reduce) {
+                // ---- in-kernel split-K reduction: all `splits` CTAs of this output tile are co-resident (the
+                // launcher guarantees units <= #SMs); they meet at a counter, then each reduces 1/splits of the
+                // tile in fixed split order (deterministic) and applies bias / residual / conversion ----
+                __threadfence();
+                epi_bar_sync();
+                unsigned int* ctr = p.tile_ctr + 2 * (t.n_tile * p.m_tiles + t.m_tile);
+                if (tid_e == 0) {
+                    atomicAdd(ctr, 1u);
+                    while (*reinterpret_cast<volatile unsigned int*>(ctr) < static_cast<unsigned int>(p.splits)) {
+                    }
+                    __threadfence();
+                }
+                epi_bar_sync();
+                const int q4 = p.block_n >> 2;
+                const int total4 = kBM * q4;
+                const int lo = static_cast<int>(static_cast<long long>(total4) * t.split / p.splits);
+                const int hi = static_cast<int>(static_cast<long long>(total4) * (t.split + 1) / p.splits);
+                const size_t sstride = static_cast<size_t>(p.M) * p.N;
+                for (int idx = lo + tid_e; idx < hi; idx += 128) {
+                    const int r = idx / q4, c4 = idx - r * q4;
+                    const int col = ncol0 + c4 * 4;
+                    int orow;
+                    if (!tile_row(p, t, r, orow) || col >= p.N) continue;
+                    const float* src = p.partial + static_cast<size_t>(orow) * p.N + col;
+                    float4 acc = __ldcg(reinterpret_cast<const float4*>(src));
+                    for (int sp = 1; sp < p.splits; ++sp) {
+                        const float4 v = __ldcg(reinterpret_cast<const float4*>(src + sp * sstride));
+                        acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+                    }
+                    if (p.bias != nullptr) {
+                        const float* b = p.bias + (p.bias_rows > 0 ? (orow / p.bias_rows) * p.bias_stride : 0) + col;
+                        acc.x += b[0], acc.y += b[1], acc.z += b[2], acc.w += b[3];
+                    }
+                    const size_t off = static_cast<size_t>(orow) * p.N + col;
+                    if (p.residual != nullptr) {
+                        const __half2* rr = reinterpret_cast<const __half2*>(p.residual + off);
+                        const float2 r0 = __half22float2(rr[0]), r1 = __half22float2(rr[1]);
+                        acc.x += r0.x, acc.y += r0.y, acc.z += r1.x, acc.w += r1.y;
+                    }
+                    if (p.out_f32) {
+                        *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off) = acc;
+                    } else {
+                        uint2 pk;
+                        pk.x = pack_half2(acc.x, acc.y);
+                        pk.y = pack_half2(acc.z, acc.w);
+                        *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.out) + off) = pk;
+                    }
+                }
+                epi_bar_sync();
+                if (tid_e == 0) {
+                    const unsigned int old = atomicAdd(ctr + 1, 1u);
+                    if (old == static_cast<unsigned int>(p.splits - 1)) {
+                        ctr[0] = 0;
+                        ctr[1] = 0;
+                        __threadfence();
+                    }
+                }
+            }
         }
     }
 
@@ -538,6 +601,7 @@ static int plan_gemm(const b200sd_gemm_args& a, GemmPlan& pl) {
         for (int sp : kSplits) {
             if (a.split_k > 0 && sp != a.split_k) continue;
             if (sp > 1 && (!can_split || sp * 2 > pl.kb_total) && a.split_k == 0) continue;
+            if (sp > 1 && a.split_k == 0 && static_cast<long>(pl.m_tiles) * nt * sp > sms) continue;  // keep split CTAs co-resident
             const int kb = (pl.kb_total + sp - 1) / sp;
             const int se = (pl.kb_total + kb - 1) / kb;
             const long units = static_cast<long>(pl.m_tiles) * nt * se;
@@ -588,6 +652,25 @@ static size_t plan_workspace(const GemmPlan& pl) {
 }
 
 extern void count_launch(int n);
+
+static constexpr int kMaxTileCounters = 8192;
+static bool fused_splitk_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("B200SD_FUSED_SPLITK");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
+}
+
+static unsigned int* tile_counters() {
+    static unsigned int* c = nullptr;
+    if (!c) {
+        if (cudaMalloc(&c, 2 * kMaxTileCounters * sizeof(unsigned int)) != cudaSuccess) return nullptr;
+        cudaMemset(c, 0, 2 * kMaxTileCounters * sizeof(unsigned int));
+    }
+    return c;
+}
 
 static int launch_gemm(const b200sd_gemm_args& a, cudaStream_t stream) {
     GemmPlan pl;
@@ -682,8 +765,8 @@ static int launch_gemm(const b200sd_gemm_args& a, cudaStream_t stream) {
     p.bias_mode = pl.bias_mode;
     p.res_smem = pl.res_smem;
     p.out = a.out;
-    p.bias = pl.splits > 1 ? nullptr : a.bias;
-    p.residual = pl.splits > 1 ? nullptr : reinterpret_cast<const __half*>(a.residual);
+    p.bias = a.bias;
+    p.residual = reinterpret_cast<const __half*>(a.residual);
     p.partial = pl.splits > 1 ? a.workspace : nullptr;
 
     const int smem_bytes = pl.stages * (kAStage + pl.block_n * kBK * 2) + (2 * kMaxStages + 4) * 8 + 16 + pl.epi_smem + 1024;
@@ -707,6 +790,18 @@ static int launch_gemm(const b200sd_gemm_args& a, cudaStream_t stream) {
     } else {
         fn = umma_gemm_kernel<false, false, false, false>, variant = 4;
     }
+    const int total_units = pl.m_tiles * pl.n_tiles * pl.splits;
+    p.fused_reduce = 0;
+    if (variant == 1 && total_units <= num_sms() && pl.m_tiles * pl.n_tiles <= kMaxTileCounters && fused_splitk_enabled()) {
+        p.tile_ctr = tile_counters();
+        B200SD_REQUIRE(p.tile_ctr != nullptr, "b200sd_gemm: could not allocate the split-K tile counters");
+        p.fused_reduce = 1;
+    }
+    if (pl.splits > 1 && !p.fused_reduce) {
+        // the separate reduce kernel applies bias / residual; the partial writer must not
+        p.bias = nullptr;
+        p.residual = nullptr;
+    }
     static bool attr_set[5] = {false, false, false, false, false};
     if (!attr_set[variant]) {
         B200SD_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -715,7 +810,7 @@ static int launch_gemm(const b200sd_gemm_args& a, cudaStream_t stream) {
     B200SD_CHECK_CUDA(launch_kernel(fn, dim3(grid), dim3(kGemmThreads), smem_bytes, stream, p));
     B200SD_CHECK_CUDA(cudaGetLastError());
     count_launch(1);
-    if (pl.splits > 1) {
+    if (pl.splits > 1 && !p.fused_reduce) {
         const size_t total4 = static_cast<size_t>(pl.M) * a.n / 4;
         const int rgrid = static_cast<int>(std::min<size_t>((total4 + 255) / 256, static_cast<size_t>(num_sms()) * 8));
         B200SD_CHECK_CUDA(launch_kernel(splitk_reduce_kernel, dim3(rgrid), dim3(256), 0, stream, a.workspace, pl.splits, pl.M, a.n, a.bias, a.bias_rows,
