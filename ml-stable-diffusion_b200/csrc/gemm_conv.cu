@@ -4,7 +4,7 @@
 //   warp 0      TMA producer  (cp.async.bulk.tensor 2D/4D boxes, SWIZZLE_128B, mbarrier tx)
 //   warp 1      MMA issuer    (one elected lane; tcgen05.mma kind::f16 M=128, N=block_n, K=16;
 //                              accumulators double-buffered in TMEM; tcgen05.commit -> mbarriers)
-//   warps 2..5  epilogue      (tcgen05.ld 32x32b; bias / time-embedding / GEGLU / residual; fp16|fp32
+//   warps 2..9  epilogue      (tcgen05.ld 32x32b; two warps per TMEM lane quarter split the columns; bias / time-embedding / GEGLU / residual; fp16|fp32
 //                              stores or fp32 split-K partials)
 //
 // Replaces every nn.Conv2d of the reference UNet / VAE decoder (reference
@@ -23,7 +23,8 @@ namespace b200sd {
 static constexpr int kBM = 128;
 static constexpr int kBK = 64;
 static constexpr int kAStage = kBM * kBK * 2;  // 16 KiB
-static constexpr int kGemmThreads = 192;
+static constexpr int kGemmThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
+static constexpr int kEpiThreads = 256;
 static constexpr int kMaxStages = 8;
 static constexpr int kSmemBudget = 220 * 1024;
 
@@ -191,7 +192,7 @@ __device__ __forceinline__ bool tile_row(const GemmParams& p, const TileCoord& t
     return (on < p.n_img) && (oy < p.Hout) && (ox < p.Wout);
 }
 
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
@@ -226,7 +227,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) umma_gemm_kernel(const __grid
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tmem_full[s], 1);
-            mbar_init(&tmem_empty[s], 128);
+            mbar_init(&tmem_empty[s], kEpiThreads);
         }
         fence_barrier_init();
     }
@@ -323,8 +324,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) umma_gemm_kernel(const __grid
     } else {
         // ------------------------------- epilogue -----------------------------------
         const int lane_group = warp & 3;  // TMEM lanes [32*lane_group, +32) are accessible to this warp
+        const int half = (warp - 2) >> 2;  // which of the two warps of this lane quarter: it takes every other chunk
         const int row = lane_group * 32 + lane;
-        const int tid_e = threadIdx.x - 64;  // 0..127 among the epilogue warps
+        const int tid_e = threadIdx.x - 64;  // 0..255 among the epilogue warps
         int iter = 0;
         for (int work = blockIdx.x; work < total_work; work += gridDim.x, ++iter) {
             const TileCoord t = decode_work(p, work);
@@ -341,7 +343,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) umma_gemm_kernel(const __grid
                 tile_row(p, t, 0, row0);
                 const int img0 = p.bias_rows > 0 ? row0 / p.bias_rows : 0;
                 const int nvec = p.bias_rows > 0 ? (p.M + p.bias_rows - 1) / p.bias_rows : 1;
-                for (int c = tid_e; c < 2 * p.block_n; c += 128) {
+                for (int c = tid_e; c < 2 * p.block_n; c += kEpiThreads) {
                     const int which = c >= p.block_n ? 1 : 0;
                     const int cc = c - which * p.block_n;
                     const int col = ncol0 + cc;
@@ -354,7 +356,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) umma_gemm_kernel(const __grid
             }
             if (p.res_smem) {
                 const int vpr = p.block_n >> 3;  // 16-byte vectors per tile row
-                for (int i = tid_e; i < kBM * vpr; i += 128) {
+                for (int i = tid_e; i < kBM * vpr; i += kEpiThreads) {
                     const int r = i / vpr, cv = i - r * vpr;
                     int orow;
                     if (tile_row(p, t, r, orow) && ncol0 + cv * 8 < p.N)
@@ -390,22 +392,25 @@ __global__ void __launch_bounds__(kGemmThreads, 1) umma_gemm_kernel(const __grid
                 }
             };
             if (!kGeneric || (p.block_n & 31) == 0) {
-                // software-pipelined: the TMEM load of the next 32 columns is in flight while these are stored
+                // this warp's 32-column chunks: half, half+2, ...; software-pipelined (the TMEM load of the next
+                // chunk is in flight while the current one is converted and stored)
                 uint32_t va[32], vb[32];
-                tmem_ld32(taddr, va);
-                for (int c = 0; c < p.block_n; c += 64) {
+                int c = 32 * half;
+                if (c < p.block_n) tmem_ld32(taddr + c, va);
+                while (c < p.block_n) {
                     tmem_ld_wait();
-                    const bool has_b = c + 32 < p.block_n;
-                    if (has_b) tmem_ld32(taddr + c + 32, vb);
+                    const int c2 = c + 64;
+                    if (c2 < p.block_n) tmem_ld32(taddr + c2, vb);
                     process32(va, c);
-                    if (has_b) {
-                        tmem_ld_wait();
-                        if (c + 64 < p.block_n) tmem_ld32(taddr + c + 64, va);
-                        process32(vb, c + 32);
-                    }
+                    if (c2 >= p.block_n) break;
+                    tmem_ld_wait();
+                    const int c3 = c2 + 64;
+                    if (c3 < p.block_n) tmem_ld32(taddr + c3, va);
+                    process32(vb, c2);
+                    c = c3;
                 }
             } else if (kGeneric) {
-                for (int c = 0; c < p.block_n; c += 16) {
+                for (int c = 16 * half; c < p.block_n; c += 32) {
                     uint32_t v[16];
                     tmem_ld16(taddr + c, v);
                     tmem_ld_wait();
@@ -438,7 +443,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) umma_gemm_kernel(const __grid
                 const int lo = static_cast<int>(static_cast<long long>(total4) * t.split / p.splits);
                 const int hi = static_cast<int>(static_cast<long long>(total4) * (t.split + 1) / p.splits);
                 const size_t sstride = static_cast<size_t>(p.M) * p.N;
-                for (int idx = lo + tid_e; idx < hi; idx += 128) {
+                for (int idx = lo + tid_e; idx < hi; idx += kEpiThreads) {
                     const int r = idx / q4, c4 = idx - r * q4;
                     const int col = ncol0 + c4 * 4;
                     int orow;
@@ -536,6 +541,17 @@ struct GemmPlan {
     int bias_mode, res_smem, epi_smem;
 };
 
+static bool fused_splitk_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        // opt-in: measured slower (163.6 vs 178.3 iter/s) than the separate, fully parallel reduce kernel --
+        // the co-residency constraint costs split parallelism and the per-tile barrier serialises the tail
+        const char* e = getenv("B200SD_FUSED_SPLITK");
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    return v == 1;
+}
+
 static int ilog2(int v) {
     int l = 0;
     while ((1 << l) < v) ++l;
@@ -601,7 +617,8 @@ static int plan_gemm(const b200sd_gemm_args& a, GemmPlan& pl) {
         for (int sp : kSplits) {
             if (a.split_k > 0 && sp != a.split_k) continue;
             if (sp > 1 && (!can_split || sp * 2 > pl.kb_total) && a.split_k == 0) continue;
-            if (sp > 1 && a.split_k == 0 && static_cast<long>(pl.m_tiles) * nt * sp > sms) continue;  // keep split CTAs co-resident
+            if (sp > 1 && a.split_k == 0 && fused_splitk_enabled() && static_cast<long>(pl.m_tiles) * nt * sp > sms)
+                continue;  // fused reduction needs the split CTAs co-resident
             const int kb = (pl.kb_total + sp - 1) / sp;
             const int se = (pl.kb_total + kb - 1) / kb;
             const long units = static_cast<long>(pl.m_tiles) * nt * se;
@@ -654,15 +671,6 @@ static size_t plan_workspace(const GemmPlan& pl) {
 extern void count_launch(int n);
 
 static constexpr int kMaxTileCounters = 8192;
-static bool fused_splitk_enabled() {
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("B200SD_FUSED_SPLITK");
-        v = (e && e[0] == '0') ? 0 : 1;
-    }
-    return v == 1;
-}
-
 static unsigned int* tile_counters() {
     static unsigned int* c = nullptr;
     if (!c) {
