@@ -14,6 +14,7 @@ from b200sd.model import UNetModel  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--forwards", type=int, default=2)
 ap.add_argument("--shapes", action="store_true")
+ap.add_argument("--capture-last", action="store_true")
 ap.add_argument("--kernels", action="store_true", help="per-op-type CUDA-event timing of one forward")
 args = ap.parse_args()
 
@@ -29,6 +30,12 @@ m._t.fill_(981.0)
 for _ in range(args.forwards):
     m._run()
 torch.cuda.synchronize()
+if args.capture_last:
+    # ncu --profile-from-start off: only this forward is profiled (the first one also packs weights)
+    torch.cuda.profiler.start()
+    m._run()
+    torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
 
 if args.kernels:
     import collections
