@@ -105,6 +105,8 @@ def cpu_unet_runner():
     c = torch.randn(2, 1024, 1, 77, generator=g)
     t = torch.tensor([981.0, 981.0])
     torch.set_grad_enabled(False)
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm should use the host's cores (physical ~ logical / 2)
+    torch.set_num_threads(max(1, (os.cpu_count() or 2) // 2))
     if ref_unet.available():
         m = ref_unet.build_unet(cfg, sd, impl="ORIGINAL")
         return "reference", (lambda: m(x, t, c)[0])
