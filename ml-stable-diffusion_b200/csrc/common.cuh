@@ -287,7 +287,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
     return y;
 }
 
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 // exact-erf GELU (unet.py:617 F.gelu default).  erf via Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far below
 // the fp16 output rounding): 1 MUFU.RCP + 1 MUFU.EX2 + ~10 FMA instead of libdevice erff's ~40 instructions --
 // the GEGLU epilogue evaluates 128 of these per thread per tile and was the bottleneck of those GEMMs.

@@ -9,6 +9,7 @@
 #include "../../include/b200sd.h"
 
 #include <algorithm>
+#include <cooperative_groups.h>
 #include <stdlib.h>
 
 namespace b200sd {
@@ -365,7 +366,14 @@ __global__ void __launch_bounds__(512) gn_fused_kernel(const __half* __restrict_
         ch_buf[2 * c + 1] = beta[c] - g_buf[2 * g] * sc;
     }
     __syncthreads();
-    // ---- normalise the slab from shared memory ----
+    // ---- normalise the slab from shared memory (this thread's 8 channels: affine held in registers) ----
+    float sc8[8], sh8[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        sc8[e] = ch_buf[2 * (ch + e)];
+        sh8[e] = ch_buf[2 * (ch + e) + 1];
+    }
+#pragma unroll 2
     for (int px = px0 + r; active && px < px1; px += rows) {
         const uint4 raw = tile[static_cast<size_t>(px - px0) * vecs + v];
         const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
@@ -377,8 +385,8 @@ __global__ void __launch_bounds__(512) gn_fused_kernel(const __half* __restrict_
         }
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-            const float y = f[e] * ch_buf[2 * (ch + e)] + ch_buf[2 * (ch + e) + 1];
-            f[e] = silu ? silu_f(y) : y;
+            const float y = fmaf(f[e], sc8[e], sh8[e]);
+            f[e] = silu ? __fdividef(y, 1.0f + __expf(-y)) : y;
         }
         uint4 pk;
         pk.x = pack_half2(f[0], f[1]);
@@ -397,6 +405,155 @@ __global__ void __launch_bounds__(512) gn_fused_kernel(const __half* __restrict_
             __threadfence();
         }
     }
+}
+
+// ---- GroupNorm on thread-block clusters (the default path) ---------------------------------------
+// grid = (cs, C / chunk, n_img) with cluster dims (cs, 1, 1): one cluster per (image, channel chunk), where a
+// chunk is a whole number of groups and of 16-byte vectors.  The cs CTAs of a cluster split the image's
+// pixels; each keeps its [pixels x chunk] slab in shared memory, so the tensor is read from L2/HBM exactly
+// once.  Statistics are exact two-pass (mean, then sum of squared deviations from the slab) and are exchanged
+// between the CTAs through distributed shared memory in rank order -- no global barrier, no partial buffers,
+// no atomics (bitwise reproducible).  Thread t owns vector column t % vpr for all its pixels, so per-channel
+// partial sums live in registers and fold rows -> channels -> groups in a fixed order.
+__global__ void gn_cluster_kernel(const __half* __restrict__ x0, const __half* __restrict__ x1, int c0, int c1, int hw,
+                                  int groups, int chunk_ch, int rows_per_cta, float eps,
+                                  const float* __restrict__ gamma, const float* __restrict__ beta, int silu,
+                                  __half* __restrict__ out) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int cs = gridDim.x, rank = blockIdx.x;
+    const int C = c0 + c1, cpg = C / groups;
+    const int vpr = chunk_ch >> 3;
+    const int ng = chunk_ch / cpg;
+    const int ch0 = blockIdx.y * chunk_ch;
+    const int n = blockIdx.z;
+    const int TY = blockDim.x / vpr;
+    const int cv = threadIdx.x % vpr, ty = threadIdx.x / vpr;
+    const bool active = ty < TY;
+    const int px0 = rank * rows_per_cta, px1 = min(hw, px0 + rows_per_cta);
+    const int ch = ch0 + cv * 8;
+    const bool from0 = ch < c0;
+    const int ld = from0 ? c0 : c1;
+    const __half* src = from0 ? x0 + static_cast<size_t>(n) * hw * c0 + ch : x1 + static_cast<size_t>(n) * hw * c1 + (ch - c0);
+
+    extern __shared__ __align__(16) uint8_t csm[];
+    uint4* slab = reinterpret_cast<uint4*>(csm);                                   // [rows_per_cta][vpr]
+    float* red = reinterpret_cast<float*>(slab + static_cast<size_t>(rows_per_cta) * vpr);  // [TY][chunk_ch]
+    float* chsum = red + TY * chunk_ch;                                            // [chunk_ch]
+    float* xchg = chsum + chunk_ch;                                                // [2][ng]  (read by the peers)
+    float* stat = xchg + 2 * ng;                                                   // [2][ng]  mean, rstd
+    pdl_wait();
+
+    // fold the threads' per-channel registers: rows -> channels -> groups, then across the cluster
+    auto cluster_total = [&](float (&v)[8], int slot) {
+        if (active) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) red[ty * chunk_ch + cv * 8 + e] = v[e];
+        }
+        __syncthreads();
+        if (threadIdx.x < chunk_ch) {
+            float a = 0.f;
+            for (int r = 0; r < TY; ++r) a += red[r * chunk_ch + threadIdx.x];
+            chsum[threadIdx.x] = a;
+        }
+        __syncthreads();
+        if (threadIdx.x < ng) {
+            float a = 0.f;
+            for (int c = 0; c < cpg; ++c) a += chsum[threadIdx.x * cpg + c];
+            xchg[slot * ng + threadIdx.x] = a;
+        }
+        cluster.sync();
+        float tot = 0.f;
+        if (threadIdx.x < ng)
+            for (int r = 0; r < cs; ++r) tot += *cluster.map_shared_rank(&xchg[slot * ng + threadIdx.x], r);
+        return tot;
+    };
+
+    // ---- pass 1: global -> shared slab, per-channel sums ----
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    if (active) {
+#pragma unroll 4
+        for (int px = px0 + ty; px < px1; px += TY) {
+            const uint4 raw = *reinterpret_cast<const uint4*>(src + static_cast<size_t>(px) * ld);
+            slab[(px - px0) * vpr + cv] = raw;
+            const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float2 t = __half22float2(h2[q]);
+                acc[2 * q] += t.x;
+                acc[2 * q + 1] += t.y;
+            }
+        }
+    }
+    const float inv_cnt = 1.0f / (static_cast<float>(hw) * static_cast<float>(cpg));
+    {
+        const float tot = cluster_total(acc, 0);
+        if (threadIdx.x < ng) stat[threadIdx.x] = tot * inv_cnt;
+    }
+    __syncthreads();
+    // ---- pass 2: sum of squared deviations, from the slab ----
+    float mean8[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        mean8[e] = active ? stat[(cv * 8 + e) / cpg] : 0.f;
+        acc[e] = 0.f;
+    }
+    if (active) {
+        for (int px = px0 + ty; px < px1; px += TY) {
+            const uint4 raw = slab[(px - px0) * vpr + cv];
+            const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float2 t = __half22float2(h2[q]);
+                const float d0 = t.x - mean8[2 * q], d1 = t.y - mean8[2 * q + 1];
+                acc[2 * q] = fmaf(d0, d0, acc[2 * q]);
+                acc[2 * q + 1] = fmaf(d1, d1, acc[2 * q + 1]);
+            }
+        }
+    }
+    {
+        const float tot = cluster_total(acc, 1);
+        if (threadIdx.x < ng) stat[ng + threadIdx.x] = rsqrtf(tot * inv_cnt + eps);
+    }
+    cluster.barrier_arrive();  // done reading the peers' shared memory; matched by the wait before exit
+    __syncthreads();
+    // ---- apply: y = (x - mean) * rstd * gamma + beta (+ SiLU), slab -> global ----
+    if (active) {
+        float sc8[8], sh8[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int g = (cv * 8 + e) / cpg;
+            sc8[e] = stat[ng + g] * gamma[ch + e];
+            sh8[e] = fmaf(-mean8[e], sc8[e], beta[ch + e]);
+        }
+        __half* dst = out + static_cast<size_t>(n) * hw * C + ch;
+#pragma unroll 2
+        for (int px = px0 + ty; px < px1; px += TY) {
+            const uint4 raw = slab[(px - px0) * vpr + cv];
+            const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+            float f[8];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float2 t = __half22float2(h2[q]);
+                f[2 * q] = t.x;
+                f[2 * q + 1] = t.y;
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float y = fmaf(f[e], sc8[e], sh8[e]);
+                f[e] = silu ? __fdividef(y, 1.0f + __expf(-y)) : y;
+            }
+            uint4 pk;
+            pk.x = pack_half2(f[0], f[1]);
+            pk.y = pack_half2(f[2], f[3]);
+            pk.z = pack_half2(f[4], f[5]);
+            pk.w = pack_half2(f[6], f[7]);
+            *reinterpret_cast<uint4*>(dst + static_cast<size_t>(px) * C) = pk;
+        }
+    }
+    cluster.barrier_wait();
 }
 
 static int gn_chunks(int hw, int n_img) {
@@ -558,6 +715,61 @@ extern "C" int b200sd_group_norm(const void* x0, const void* x1, int32_t c0, int
     }
     const int vecs = C / 8;
     B200SD_REQUIRE(vecs <= 384, "b200sd_group_norm: too many channels (%d)", C);
+    // ---- cluster path: one cluster of <= 8 CTAs per (image, channel chunk), slab in shared memory ----
+    {
+        static int mode = -1;  // B200SD_GN_CLUSTER=0 disables
+        if (mode < 0) {
+            const char* e = getenv("B200SD_GN_CLUSTER");
+            mode = (e && e[0] == '0') ? 0 : 1;
+        }
+        const int cpg = C / groups;
+        int chunk = cpg;
+        while (chunk % 8 != 0) chunk += cpg;                       // lcm(cpg, 8)
+        while (chunk < 32 && C % (2 * chunk) == 0) chunk *= 2;     // at least 64-byte pieces per pixel
+        const int vpr = chunk / 8;
+        const long clusters = static_cast<long>(C / chunk) * n_img;
+        int cs = 8;
+        while (cs > 1 && (hw / cs < 32 || clusters * cs > 4L * num_sms())) cs >>= 1;
+        const int rows_per_cta = (hw + cs - 1) / cs;
+        const int threads = static_cast<long>(rows_per_cta) * vpr >= 2048 ? 512 : 256;
+        const int TY = threads / std::max(1, vpr);
+        const size_t csmem = static_cast<size_t>(rows_per_cta) * vpr * 16 +
+                             (static_cast<size_t>(TY) * chunk + chunk + 4 * (chunk / cpg)) * sizeof(float);
+        if (mode == 1 && vpr <= 64 && C % chunk == 0 && csmem <= 200 * 1024 && n_img <= 65535 && C / chunk <= 65535) {
+            static bool attr = false;
+            if (!attr) {
+                B200SD_CHECK_CUDA(cudaFuncSetAttribute(gn_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                       200 * 1024));
+                attr = true;
+            }
+            cudaLaunchConfig_t cfg;
+            memset(&cfg, 0, sizeof(cfg));
+            cfg.gridDim = dim3(cs, C / chunk, n_img);
+            cfg.blockDim = dim3(threads);
+            cfg.dynamicSmemBytes = csmem;
+            cfg.stream = stream;
+            cudaLaunchAttribute at[2];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = cs;
+            at[0].val.clusterDim.y = 1;
+            at[0].val.clusterDim.z = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            if (pdl_enabled()) {
+                at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                at[1].val.programmaticStreamSerializationAllowed = 1;
+                cfg.numAttrs = 2;
+            }
+            B200SD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gn_cluster_kernel, reinterpret_cast<const __half*>(x0),
+                                                 reinterpret_cast<const __half*>(x1), static_cast<int>(c0),
+                                                 static_cast<int>(c1), static_cast<int>(hw), static_cast<int>(groups), chunk,
+                                                 rows_per_cta, eps, gamma, beta, static_cast<int>(silu),
+                                                 reinterpret_cast<__half*>(out)));
+            B200SD_CHECK_CUDA(cudaGetLastError());
+            count_launch(1);
+            return 0;
+        }
+    }
     // ---- single-launch path: all CTAs co-resident (<= one per SM), pixel slab kept in shared memory ----
     {
         const int sms = num_sms();
