@@ -37,8 +37,7 @@ struct __align__(64) GemmParams {
     int n_img, Hout, Wout, stride, bw_log2, bh_log2, tiles_w, tiles_h;
     int bias_rows, bias_stride, geglu, out_f32;
     int act;         // 0 none, 1 SiLU after bias (generic variant only)
-    int fused_reduce;  // split-K: the split CTAs of a tile meet at a counter and reduce-scatter it in-kernel
-    unsigned int* tile_ctr;
+    int cluster;     // split-K on a thread-block cluster: the `splits` CTAs of a tile reduce it through DSMEM
     int wgt_tiled;   // B operand pre-tiled: tile (n_tile, kb) starts at row (n_tile * kb_total + kb) * block_n
     int bias_mode;   // 0 none, 1 staged in smem (<= 2 vectors per tile), 2 read from global per chunk
     int res_smem;    // 1: residual tile prefetched into smem with cp.async
@@ -55,10 +54,17 @@ struct TileCoord {
 
 __device__ __forceinline__ TileCoord decode_work(const GemmParams& p, int work) {
     TileCoord t;
-    t.m_tile = work % p.m_tiles;
-    int r = work / p.m_tiles;
-    t.n_tile = r % p.n_tiles;
-    t.split = r / p.n_tiles;
+    if (p.cluster) {  // the CTAs of a cluster (consecutive blockIdx.x) are the k-splits of one tile
+        t.split = work % p.splits;
+        const int r = work / p.splits;
+        t.m_tile = r % p.m_tiles;
+        t.n_tile = r / p.m_tiles;
+    } else {
+        t.m_tile = work % p.m_tiles;
+        const int r = work / p.m_tiles;
+        t.n_tile = r % p.n_tiles;
+        t.split = r / p.n_tiles;
+    }
     t.n0 = t.h0 = t.w0 = 0;
     if (p.mode == 1) {
         int tw = t.m_tile % p.tiles_w;
@@ -70,6 +76,17 @@ __device__ __forceinline__ TileCoord decode_work(const GemmParams& p, int work) 
         t.n0 = tn << (7 - p.bw_log2 - p.bh_log2);
     }
     return t;
+}
+
+// k-block range of one split: even floor/ceil distribution on clusters (every split non-empty), fixed stride otherwise
+__device__ __forceinline__ void split_range(const GemmParams& p, int split, int& kb0, int& kb1) {
+    if (p.cluster) {
+        kb0 = split * p.kb_total / p.splits;
+        kb1 = (split + 1) * p.kb_total / p.splits;
+    } else {
+        kb0 = split * p.kb_per_split;
+        kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+    }
 }
 
 // Applies the epilogue to 16 consecutive accumulator columns of one output row and stores them.
@@ -198,6 +215,21 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+// ---- thread-block cluster primitives (distributed shared memory) ----
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float4 ld_dsmem_f4(uint32_t local_addr, uint32_t cta_rank) {
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_addr), "r"(cta_rank));
+    float4 v;
+    asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "r"(ra)
+                 : "memory");
+    return v;
+}
+
 template <bool kGeneric, bool kGeglu, bool kOutF32, bool kPartial>
 __global__ void __launch_bounds__(kGemmThreads, 1) umma_gemm_kernel(const __grid_constant__ GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -253,8 +285,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) umma_gemm_kernel(const __grid
             const uint32_t tx_bytes = kAStage + b_stage;
             for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
                 const TileCoord t = decode_work(p, work);
-                const int kb0 = t.split * p.kb_per_split;
-                const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+                int kb0, kb1;
+                split_range(p, t.split, kb0, kb1);
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     mbar_expect_tx(&full_bar[stage], tx_bytes);
@@ -293,8 +325,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) umma_gemm_kernel(const __grid
         int iter = 0;
         for (int work = blockIdx.x; work < total_work; work += gridDim.x, ++iter) {
             const TileCoord t = decode_work(p, work);
-            const int kb0 = t.split * p.kb_per_split;
-            const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+            int kb0, kb1;
+            split_range(p, t.split, kb0, kb1);
             const int as = iter & 1;
             const uint32_t aphase = (iter >> 1) & 1;
             mbar_wait(&tmem_empty[as], aphase ^ 1);
@@ -380,6 +412,16 @@ __global__ void __launch_bounds__(kGemmThreads, 1) umma_gemm_kernel(const __grid
                 epilogue_store16<kGeneric, kGeglu, kOutF32, kPartial>(p, acc, out_row, ncol0 + c, t.split, bptr, rptr);
             };
             auto process32 = [&](const uint32_t (&v)[32], int c) {
+                if (kPartial && p.cluster) {
+                    // fp32 accumulators -> this CTA's shared memory (over the drained pipeline stages); row stride
+                    // block_n + 4 floats keeps the 32 rows of a warp on distinct banks
+                    float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(smem) + row * (p.block_n + 4) + c);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                             __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                    return;
+                }
                 if (!valid) return;
 #pragma unroll
                 for (int hh = 0; hh < 2; ++hh) {
@@ -424,66 +466,56 @@ __global__ void __launch_bounds__(kGemmThreads, 1) umma_gemm_kernel(const __grid
             }
             tc_fence_before();
             mbar_arrive(&tmem_empty[as]);
-            if (kPartial && p.fused_reduce) {
-                // ---- in-kernel split-K reduction: all `splits` CTAs of this output tile are co-resident (the
-                // launcher guarantees units <= #SMs); they meet at a counter, then each reduces 1/splits of the
-                // tile in fixed split order (deterministic) and applies bias / residual / conversion ----
-                __threadfence();
-                epi_bar_sync();
-                unsigned int* ctr = p.tile_ctr + 2 * (t.n_tile * p.m_tiles + t.m_tile);
-                if (tid_e == 0) {
-                    atomicAdd(ctr, 1u);
-                    while (*reinterpret_cast<volatile unsigned int*>(ctr) < static_cast<unsigned int>(p.splits)) {
-                    }
-                    __threadfence();
-                }
-                epi_bar_sync();
-                const int q4 = p.block_n >> 2;
-                const int total4 = kBM * q4;
-                const int lo = static_cast<int>(static_cast<long long>(total4) * t.split / p.splits);
-                const int hi = static_cast<int>(static_cast<long long>(total4) * (t.split + 1) / p.splits);
-                const size_t sstride = static_cast<size_t>(p.M) * p.N;
-                for (int idx = lo + tid_e; idx < hi; idx += kEpiThreads) {
-                    const int r = idx / q4, c4 = idx - r * q4;
-                    const int col = ncol0 + c4 * 4;
-                    int orow;
-                    if (!tile_row(p, t, r, orow) || col >= p.N) continue;
-                    const float* src = p.partial + static_cast<size_t>(orow) * p.N + col;
-                    float4 acc = __ldcg(reinterpret_cast<const float4*>(src));
-                    for (int sp = 1; sp < p.splits; ++sp) {
-                        const float4 v = __ldcg(reinterpret_cast<const float4*>(src + sp * sstride));
-                        acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
-                    }
-                    if (p.bias != nullptr) {
-                        const float* b = p.bias + (p.bias_rows > 0 ? (orow / p.bias_rows) * p.bias_stride : 0) + col;
-                        acc.x += b[0], acc.y += b[1], acc.z += b[2], acc.w += b[3];
-                    }
-                    const size_t off = static_cast<size_t>(orow) * p.N + col;
-                    if (p.residual != nullptr) {
-                        const __half2* rr = reinterpret_cast<const __half2*>(p.residual + off);
-                        const float2 r0 = __half22float2(rr[0]), r1 = __half22float2(rr[1]);
-                        acc.x += r0.x, acc.y += r0.y, acc.z += r1.x, acc.w += r1.y;
-                    }
-                    if (p.out_f32) {
-                        *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off) = acc;
-                    } else {
-                        uint2 pk;
-                        pk.x = pack_half2(acc.x, acc.y);
-                        pk.y = pack_half2(acc.z, acc.w);
-                        *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.out) + off) = pk;
-                    }
-                }
-                epi_bar_sync();
-                if (tid_e == 0) {
-                    const unsigned int old = atomicAdd(ctr + 1, 1u);
-                    if (old == static_cast<unsigned int>(p.splits - 1)) {
-                        ctr[0] = 0;
-                        ctr[1] = 0;
-                        __threadfence();
-                    }
-                }
+        }
+    }
+
+    if (kPartial && p.cluster) {
+        // ---- split-K reduction inside the cluster: every CTA has parked its fp32 tile in shared memory; CTA `rank`
+        // sums its 1/splits slice of the tile over all peers through DSMEM in rank order (deterministic), applies
+        // bias / residual / conversion and stores it.  No workspace round trip, no second launch. ----
+        __syncwarp();
+        cluster_sync_all();
+        const TileCoord t = decode_work(p, blockIdx.x);
+        const int ncol0 = t.n_tile * p.block_n;
+        const int ldred = p.block_n + 4;
+        const int q4 = p.block_n >> 2;
+        const int total4 = kBM * q4;
+        const int lo = static_cast<int>(static_cast<long long>(total4) * t.split / p.splits);
+        const int hi = static_cast<int>(static_cast<long long>(total4) * (t.split + 1) / p.splits);
+        const uint32_t red_base = smem_u32(smem);
+        for (int idx = lo + static_cast<int>(threadIdx.x); idx < hi; idx += kGemmThreads) {
+            const int r = idx / q4, c4 = idx - r * q4;
+            const int col = ncol0 + c4 * 4;
+            int orow;
+            if (!tile_row(p, t, r, orow) || col >= p.N) continue;
+            const uint32_t la = red_base + static_cast<uint32_t>(r * ldred + c4 * 4) * 4u;
+            float4 acc = ld_dsmem_f4(la, 0);
+            for (int sp = 1; sp < p.splits; ++sp) {
+                const float4 v = ld_dsmem_f4(la, sp);
+                acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+            }
+            if (p.bias != nullptr) {
+                const float4 b = *reinterpret_cast<const float4*>(
+                    p.bias + (p.bias_rows > 0 ? (orow / p.bias_rows) * p.bias_stride : 0) + col);
+                acc.x += b.x, acc.y += b.y, acc.z += b.z, acc.w += b.w;
+            }
+            const size_t off = static_cast<size_t>(orow) * p.N + col;
+            if (p.residual != nullptr) {
+                const uint2 rr = *reinterpret_cast<const uint2*>(p.residual + off);
+                const float2 r0 = __half22float2(*reinterpret_cast<const __half2*>(&rr.x));
+                const float2 r1 = __half22float2(*reinterpret_cast<const __half2*>(&rr.y));
+                acc.x += r0.x, acc.y += r0.y, acc.z += r1.x, acc.w += r1.y;
+            }
+            if (p.out_f32) {
+                *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off) = acc;
+            } else {
+                uint2 pk;
+                pk.x = pack_half2(acc.x, acc.y);
+                pk.y = pack_half2(acc.z, acc.w);
+                *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.out) + off) = pk;
             }
         }
+        cluster_sync_all();  // nobody leaves (or frees its shared memory) while a peer may still read it
     }
 
     tc_fence_before();
@@ -539,17 +571,13 @@ struct GemmPlan {
     int m_tiles, n_tiles, block_n, splits, kb_per_split, stages;
     int Hout, Wout, bw, bh, bn_img, tiles_w, tiles_h, tiles_n;
     int bias_mode, res_smem, epi_smem;
+    int cluster;  // split-K reduced inside a thread-block cluster of `splits` CTAs (DSMEM) instead of a second kernel
 };
 
-static bool fused_splitk_enabled() {
-    static int v = -1;
-    if (v < 0) {
-        // opt-in: measured slower (163.6 vs 178.3 iter/s) than the separate, fully parallel reduce kernel --
-        // the co-residency constraint costs split parallelism and the per-tile barrier serialises the tail
-        const char* e = getenv("B200SD_FUSED_SPLITK");
-        v = (e && e[0] == '1') ? 1 : 0;
-    }
-    return v == 1;
+static bool cluster_splitk_enabled() {
+    // B200SD_CLUSTER_SPLITK=0: always take the workspace + reduce-kernel path (read per call: tuning scripts flip it)
+    const char* e = getenv("B200SD_CLUSTER_SPLITK");
+    return !(e && e[0] == '0');
 }
 
 static int ilog2(int v) {
@@ -607,29 +635,44 @@ static int plan_gemm(const b200sd_gemm_args& a, GemmPlan& pl) {
     auto epi_cycles = [&](int bn) { return 400.0 + (bn / 32.0) * (a.geglu ? 520.0 : 230.0); };
     auto kb_cycles = [&](int bn) { return std::max(2.0 * bn, (kAStage + 128.0 * bn) / 38.0); };
     double best_t = 1e30;
-    int best_bn = 0, best_s = 1;
+    int best_bn = 0, best_s = 1, best_cluster = 0;
     static const int kBns[] = {256, 224, 192, 160, 128, 96, 64, 32, 16};
     static const int kSplits[] = {1, 2, 3, 4, 6, 8, 12, 16, 24, 32};
+    const bool can_cluster = can_split && cluster_splitk_enabled() && a.n % 16 == 0;
     for (int bn : kBns) {
         if (a.block_n > 0 && bn != a.block_n) continue;
         const int nt = (a.n + bn - 1) / bn;
         if (a.block_n == 0 && bn > 16 && nt * bn > a.n + a.n / 4 + 15) continue;  // > 25 % padding
+        const int stages_bn = std::min(kMaxStages, (kSmemBudget - 2 * 256 * 4) / (kAStage + bn * kBK * 2));
         for (int sp : kSplits) {
             if (a.split_k > 0 && sp != a.split_k) continue;
             if (sp > 1 && (!can_split || sp * 2 > pl.kb_total) && a.split_k == 0) continue;
-            if (sp > 1 && a.split_k == 0 && fused_splitk_enabled() && static_cast<long>(pl.m_tiles) * nt * sp > sms)
-                continue;  // fused reduction needs the split CTAs co-resident
             const int kb = (pl.kb_total + sp - 1) / sp;
             const int se = (pl.kb_total + kb - 1) / kb;
-            const long units = static_cast<long>(pl.m_tiles) * nt * se;
-            const double waves = std::ceil(static_cast<double>(units) / sms);
             const double main = kb * kb_cycles(bn);
-            double t = 5000.0 + main + epi_cycles(bn) + (waves - 1.0) * std::max(main, epi_cycles(bn));
-            if (se > 1) t += 6000.0 + static_cast<double>(se) * pl.M * a.n * 8.0 / 3000.0;
-            if (t < best_t) {
-                best_t = t;
-                best_bn = bn;
-                best_s = sp;
+            for (int cl = 0; cl < 2; ++cl) {
+                double t;
+                if (cl == 1) {
+                    // cluster of sp CTAs per tile: portable sizes only, fp32 tile must fit over the pipeline stages
+                    if (!can_cluster || (sp != 2 && sp != 4 && sp != 8) || bn % 32 != 0 || sp > pl.kb_total) continue;
+                    if (512L * (bn + 4) > static_cast<long>(stages_bn) * (kAStage + bn * kBK * 2)) continue;
+                    const long units = static_cast<long>(pl.m_tiles) * nt * sp;
+                    // clusters need sp free SMs of one GPC: count ~10 % of the SMs as stranded
+                    const double waves = std::ceil(static_cast<double>(units) / (sms - sms / 10));
+                    const double epi = 1500.0 + (bn / 32.0) * 120.0 + 128.0 * bn * 4.0 / 17.0;  // TMEM->smem, 2 syncs, DSMEM
+                    t = 5000.0 + waves * (main + epi);
+                } else {
+                    const long units = static_cast<long>(pl.m_tiles) * nt * se;
+                    const double waves = std::ceil(static_cast<double>(units) / sms);
+                    t = 5000.0 + main + epi_cycles(bn) + (waves - 1.0) * std::max(main, epi_cycles(bn));
+                    if (se > 1) t += 6000.0 + static_cast<double>(se) * pl.M * a.n * 8.0 / 3000.0;
+                }
+                if (t < best_t) {
+                    best_t = t;
+                    best_bn = bn;
+                    best_s = sp;
+                    best_cluster = cl;
+                }
             }
         }
     }
@@ -643,6 +686,11 @@ static int plan_gemm(const b200sd_gemm_args& a, GemmPlan& pl) {
     int splits = std::max(1, std::min(best_s, pl.kb_total));
     pl.kb_per_split = (pl.kb_total + splits - 1) / splits;
     pl.splits = (pl.kb_total + pl.kb_per_split - 1) / pl.kb_per_split;
+    pl.cluster = 0;
+    if (best_cluster && splits > 1) {  // even distribution, exactly `splits` non-empty ranges (split_range())
+        pl.cluster = 1;
+        pl.splits = splits;
+    }
     if (pl.splits > 1) {
         B200SD_REQUIRE(!a.geglu, "b200sd_gemm: split-K with GEGLU is not supported");
         B200SD_REQUIRE(a.n % 4 == 0, "b200sd_gemm: split-K needs n %% 4 == 0");
@@ -665,20 +713,10 @@ static int plan_gemm(const b200sd_gemm_args& a, GemmPlan& pl) {
 }
 
 static size_t plan_workspace(const GemmPlan& pl) {
-    return pl.splits > 1 ? static_cast<size_t>(pl.splits) * pl.M * pl.N * sizeof(float) : 0;
+    return (pl.splits > 1 && !pl.cluster) ? static_cast<size_t>(pl.splits) * pl.M * pl.N * sizeof(float) : 0;
 }
 
 extern void count_launch(int n);
-
-static constexpr int kMaxTileCounters = 8192;
-static unsigned int* tile_counters() {
-    static unsigned int* c = nullptr;
-    if (!c) {
-        if (cudaMalloc(&c, 2 * kMaxTileCounters * sizeof(unsigned int)) != cudaSuccess) return nullptr;
-        cudaMemset(c, 0, 2 * kMaxTileCounters * sizeof(unsigned int));
-    }
-    return c;
-}
 
 static int launch_gemm(const b200sd_gemm_args& a, cudaStream_t stream) {
     GemmPlan pl;
@@ -775,7 +813,8 @@ static int launch_gemm(const b200sd_gemm_args& a, cudaStream_t stream) {
     p.out = a.out;
     p.bias = a.bias;
     p.residual = reinterpret_cast<const __half*>(a.residual);
-    p.partial = pl.splits > 1 ? a.workspace : nullptr;
+    p.partial = (pl.splits > 1 && !pl.cluster) ? a.workspace : nullptr;
+    p.cluster = pl.cluster;
 
     const int smem_bytes = pl.stages * (kAStage + pl.block_n * kBK * 2) + (2 * kMaxStages + 4) * 8 + 16 + pl.epi_smem + 1024;
     const int total = pl.m_tiles * pl.n_tiles * pl.splits;
@@ -798,14 +837,7 @@ static int launch_gemm(const b200sd_gemm_args& a, cudaStream_t stream) {
     } else {
         fn = umma_gemm_kernel<false, false, false, false>, variant = 4;
     }
-    const int total_units = pl.m_tiles * pl.n_tiles * pl.splits;
-    p.fused_reduce = 0;
-    if (variant == 1 && total_units <= num_sms() && pl.m_tiles * pl.n_tiles <= kMaxTileCounters && fused_splitk_enabled()) {
-        p.tile_ctr = tile_counters();
-        B200SD_REQUIRE(p.tile_ctr != nullptr, "b200sd_gemm: could not allocate the split-K tile counters");
-        p.fused_reduce = 1;
-    }
-    if (pl.splits > 1 && !p.fused_reduce) {
+    if (pl.splits > 1 && !pl.cluster) {
         // the separate reduce kernel applies bias / residual; the partial writer must not
         p.bias = nullptr;
         p.residual = nullptr;
@@ -815,10 +847,35 @@ static int launch_gemm(const b200sd_gemm_args& a, cudaStream_t stream) {
         B200SD_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set[variant] = true;
     }
+    if (pl.cluster) {
+        B200SD_REQUIRE(variant == 1, "b200sd_gemm: cluster split-K needs the regular epilogue variant");
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(total);  // one (tile, split) per CTA; the splits of a tile are one cluster
+        cfg.blockDim = dim3(kGemmThreads);
+        cfg.dynamicSmemBytes = smem_bytes;
+        cfg.stream = stream;
+        cudaLaunchAttribute at[2];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = pl.splits;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        if (pdl_enabled()) {
+            at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at[1].val.programmaticStreamSerializationAllowed = 1;
+            cfg.numAttrs = 2;
+        }
+        B200SD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, fn, p));
+        B200SD_CHECK_CUDA(cudaGetLastError());
+        count_launch(1);
+        return 0;
+    }
     B200SD_CHECK_CUDA(launch_kernel(fn, dim3(grid), dim3(kGemmThreads), smem_bytes, stream, p));
     B200SD_CHECK_CUDA(cudaGetLastError());
     count_launch(1);
-    if (pl.splits > 1 && !p.fused_reduce) {
+    if (pl.splits > 1) {
         const size_t total4 = static_cast<size_t>(pl.M) * a.n / 4;
         const int rgrid = static_cast<int>(std::min<size_t>((total4 + 255) / 256, static_cast<size_t>(num_sms()) * 8));
         B200SD_CHECK_CUDA(launch_kernel(splitk_reduce_kernel, dim3(rgrid), dim3(256), 0, stream, a.workspace, pl.splits, pl.M, a.n, a.bias, a.bias_rows,
@@ -854,9 +911,9 @@ extern "C" int b200sd_gemm_describe_plan(const b200sd_gemm_args* args, char* buf
     if (int rc = b200sd::plan_gemm(*args, pl)) return rc;
     snprintf(buf, buf_size,
              "M=%d N=%d kb_total=%d m_tiles=%d n_tiles=%d block_n=%d splits=%d kb_per_split=%d stages=%d "
-             "box=%dx%dx%d bias_mode=%d res_smem=%d epi_smem=%d",
+             "box=%dx%dx%d bias_mode=%d res_smem=%d epi_smem=%d cluster=%d",
              pl.M, pl.N, pl.kb_total, pl.m_tiles, pl.n_tiles, pl.block_n, pl.splits, pl.kb_per_split, pl.stages,
-             pl.bn_img, pl.bh, pl.bw, pl.bias_mode, pl.res_smem, pl.epi_smem);
+             pl.bn_img, pl.bh, pl.bw, pl.bias_mode, pl.res_smem, pl.epi_smem, pl.cluster);
     return 0;
 }
 

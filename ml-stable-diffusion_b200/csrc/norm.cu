@@ -16,7 +16,6 @@ namespace b200sd {
 
 extern void count_launch(int n);
 
-static constexpr int kGnMaxChunks = 256;
 static constexpr int kGnMaxImages = 1024;
 
 __device__ __forceinline__ void load8(const __half* src, float (&f)[8]) {
@@ -218,195 +217,6 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __half* __restrict_
     }
 }
 
-// ---- GroupNorm, single launch: statistics + grid barrier + apply from shared memory -----------------
-// grid = (B, n_img) with B * n_img <= #SMs (one CTA per SM, all co-resident).  Each CTA loads its pixel
-// slab ONCE into shared memory while accumulating per-channel sums, publishes its (mean, M2) partial per
-// group, meets the other CTAs of the same image at a global-memory barrier (arrive counter + spin), merges
-// all partials in fixed order (deterministic, every CTA redundantly) and normalises its slab straight from
-// shared memory.  Replaces the stats + apply pair (one launch, one global read instead of two).
-__global__ void __launch_bounds__(512) gn_fused_kernel(const __half* __restrict__ x0, const __half* __restrict__ x1,
-                                                       int c0, int c1, int hw, int groups, int rows, int px_per_block,
-                                                       float eps, const float* __restrict__ gamma,
-                                                       const float* __restrict__ beta, int silu,
-                                                       __half* __restrict__ out, float* __restrict__ partial,
-                                                       unsigned int* __restrict__ barrier) {
-    pdl_wait();
-    const int C = c0 + c1;
-    const int cpg = C / groups;
-    const int vecs = C / 8;
-    const int B = gridDim.x;
-    const int n = blockIdx.y, blk = blockIdx.x;
-    const int px0 = blk * px_per_block;
-    const int px1 = min(hw, px0 + px_per_block);
-    const int v = threadIdx.x % vecs;
-    const int r = threadIdx.x / vecs;
-    const int ch = v * 8;
-    const bool active = r < rows;
-
-    extern __shared__ __align__(16) uint8_t gsm[];
-    uint4* tile = reinterpret_cast<uint4*>(gsm);                                   // [px_per_block][vecs]
-    float* red = reinterpret_cast<float*>(gsm + static_cast<size_t>(px_per_block) * vecs * 16);  // [rows][C][2]
-    float* ch_buf = red + static_cast<size_t>(rows) * C * 2;                        // [C][2] -> later scale/shift
-    float* g_buf = ch_buf + static_cast<size_t>(C) * 2;                             // [groups][2] mean, rstd
-
-    float s[8], q[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) s[e] = q[e] = 0.f;
-    const bool from0 = ch < c0;
-    const __half* base = from0 ? x0 + static_cast<size_t>(n) * hw * c0 + ch
-                               : x1 + static_cast<size_t>(n) * hw * c1 + (ch - c0);
-    const int cs = from0 ? c0 : c1;
-#pragma unroll 4
-    for (int px = px0 + r; active && px < px1; px += rows) {
-        const uint4 raw = *reinterpret_cast<const uint4*>(base + static_cast<size_t>(px) * cs);
-        tile[static_cast<size_t>(px - px0) * vecs + v] = raw;
-        const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const float2 t = __half22float2(h2[k]);
-            s[2 * k] += t.x, s[2 * k + 1] += t.y;
-            q[2 * k] += t.x * t.x, q[2 * k + 1] += t.y * t.y;
-        }
-    }
-    if (active) {
-        float* row_buf = red + (static_cast<size_t>(r) * C + ch) * 2;
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            row_buf[2 * e] = s[e];
-            row_buf[2 * e + 1] = q[e];
-        }
-    }
-    __syncthreads();
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        float a = 0.f, b = 0.f;
-        for (int rr = 0; rr < rows; ++rr) {
-            a += red[(static_cast<size_t>(rr) * C + c) * 2];
-            b += red[(static_cast<size_t>(rr) * C + c) * 2 + 1];
-        }
-        ch_buf[2 * c] = a;
-        ch_buf[2 * c + 1] = b;
-    }
-    __syncthreads();
-    const float cnt = static_cast<float>(max(0, px1 - px0) * cpg);
-    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
-        float a = 0.f, b = 0.f;
-        for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
-            a += ch_buf[2 * c];
-            b += ch_buf[2 * c + 1];
-        }
-        const float mean = cnt > 0.f ? a / cnt : 0.f;
-        float* o = partial + ((static_cast<size_t>(n) * B + blk) * groups + g) * 2;
-        o[0] = mean;
-        o[1] = cnt > 0.f ? fmaxf(b - a * mean, 0.f) : 0.f;
-    }
-    // ---- barrier among the B CTAs of image n ----
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        atomicAdd(&barrier[2 * n], 1u);
-        while (*reinterpret_cast<volatile unsigned int*>(&barrier[2 * n]) < static_cast<unsigned int>(B)) {
-        }
-        __threadfence();
-    }
-    __syncthreads();
-    // ---- merge all partials (fixed order), one warp per group ----
-    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    for (int g = wrp; g < groups; g += nwarps) {
-        float tot = 0.f, mean = 0.f, m2 = 0.f;
-        float cbv[5], mbv[5], m2v[5];
-#pragma unroll
-        for (int t = 0; t < 5; ++t) {
-            const int k = lane + 32 * t;
-            cbv[t] = 0.f, mbv[t] = 0.f, m2v[t] = 0.f;
-            if (k < B) {
-                const int p0 = k * px_per_block;
-                const int p1 = min(hw, p0 + px_per_block);
-                cbv[t] = static_cast<float>(max(0, p1 - p0) * cpg);
-                const float* pp = partial + ((static_cast<size_t>(n) * B + k) * groups + g) * 2;
-                mbv[t] = __ldcg(pp);
-                m2v[t] = __ldcg(pp + 1);
-            }
-        }
-#pragma unroll
-        for (int t = 0; t < 5; ++t) {
-            if (cbv[t] > 0.f) {
-                const float nt = tot + cbv[t];
-                const float delta = mbv[t] - mean;
-                mean += delta * (cbv[t] / nt);
-                m2 += m2v[t] + delta * delta * (tot * cbv[t] / nt);
-                tot = nt;
-            }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const float tot_b = __shfl_xor_sync(0xffffffffu, tot, o);
-            const float mean_b = __shfl_xor_sync(0xffffffffu, mean, o);
-            const float m2_b = __shfl_xor_sync(0xffffffffu, m2, o);
-            const float nt = tot + tot_b;
-            if (nt > 0.f) {
-                const float lo_t = (lane & o) ? tot_b : tot, hi_t = (lane & o) ? tot : tot_b;
-                const float lo_m = (lane & o) ? mean_b : mean, hi_m = (lane & o) ? mean : mean_b;
-                const float lo_2 = (lane & o) ? m2_b : m2, hi_2 = (lane & o) ? m2 : m2_b;
-                const float delta = hi_m - lo_m;
-                mean = lo_m + delta * (hi_t / nt);
-                m2 = lo_2 + hi_2 + delta * delta * (lo_t * hi_t / nt);
-                tot = nt;
-            }
-        }
-        if (lane == 0) {
-            g_buf[2 * g] = mean;
-            g_buf[2 * g + 1] = rsqrtf(m2 / tot + eps);
-        }
-    }
-    __syncthreads();
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        const int g = c / cpg;
-        const float sc = gamma[c] * g_buf[2 * g + 1];
-        ch_buf[2 * c] = sc;
-        ch_buf[2 * c + 1] = beta[c] - g_buf[2 * g] * sc;
-    }
-    __syncthreads();
-    // ---- normalise the slab from shared memory (this thread's 8 channels: affine held in registers) ----
-    float sc8[8], sh8[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-        sc8[e] = ch_buf[2 * (ch + e)];
-        sh8[e] = ch_buf[2 * (ch + e) + 1];
-    }
-#pragma unroll 2
-    for (int px = px0 + r; active && px < px1; px += rows) {
-        const uint4 raw = tile[static_cast<size_t>(px - px0) * vecs + v];
-        const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
-        float f[8];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const float2 t = __half22float2(h2[k]);
-            f[2 * k] = t.x, f[2 * k + 1] = t.y;
-        }
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const float y = fmaf(f[e], sc8[e], sh8[e]);
-            f[e] = silu ? __fdividef(y, 1.0f + __expf(-y)) : y;
-        }
-        uint4 pk;
-        pk.x = pack_half2(f[0], f[1]);
-        pk.y = pack_half2(f[2], f[3]);
-        pk.z = pack_half2(f[4], f[5]);
-        pk.w = pack_half2(f[6], f[7]);
-        *reinterpret_cast<uint4*>(out + (static_cast<size_t>(n) * hw + px) * C + ch) = pk;
-    }
-    // ---- depart; the last CTA of the image re-arms the barrier for the next launch ----
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned int old = atomicAdd(&barrier[2 * n + 1], 1u);
-        if (old == static_cast<unsigned int>(B - 1)) {
-            barrier[2 * n] = 0;
-            barrier[2 * n + 1] = 0;
-            __threadfence();
-        }
-    }
-}
-
 // ---- GroupNorm on thread-block clusters (the default path) ---------------------------------------
 // grid = (cs, C / chunk, n_img) with cluster dims (cs, 1, 1): one cluster per (image, channel chunk), where a
 // chunk is a whole number of groups and of 16-byte vectors.  The cs CTAs of a cluster split the image's
@@ -563,13 +373,11 @@ static int gn_chunks(int hw, int n_img) {
     return std::max(1, std::min(128, hw / 16));
 }
 
-static bool g_gn_fused = true;  // B200SD_GN_FUSED=0 selects the two-kernel path
-
 static unsigned int* gn_tickets() {
     static unsigned int* t = nullptr;
     if (!t) {
-        if (cudaMalloc(&t, 3 * kGnMaxImages * sizeof(unsigned int)) != cudaSuccess) return nullptr;
-        cudaMemset(t, 0, 3 * kGnMaxImages * sizeof(unsigned int));  // [tickets | fused-barrier arrive/depart pairs]
+        if (cudaMalloc(&t, kGnMaxImages * sizeof(unsigned int)) != cudaSuccess) return nullptr;
+        cudaMemset(t, 0, kGnMaxImages * sizeof(unsigned int));
     }
     return t;
 }
@@ -686,8 +494,7 @@ extern "C" size_t b200sd_group_norm_workspace_bytes(int32_t n_img, int32_t hw, i
     // chunk partials + final (mean, rstd)
     const size_t two_kernel = static_cast<size_t>(n_img) * gn_chunks(hw, n_img) * groups * 2 +
                               static_cast<size_t>(n_img) * groups * 2;
-    const size_t fused = static_cast<size_t>(n_img) * 160 * groups * 2;
-    return std::max(two_kernel, fused) * sizeof(float);
+    return two_kernel * sizeof(float);
 }
 
 extern "C" int b200sd_group_norm(const void* x0, const void* x1, int32_t c0, int32_t c1, int32_t n_img, int32_t hw,
@@ -705,14 +512,6 @@ extern "C" int b200sd_group_norm(const void* x0, const void* x1, int32_t c0, int
                    "b200sd_group_norm: workspace too small");
     unsigned int* tickets = gn_tickets();
     B200SD_REQUIRE(tickets != nullptr, "b200sd_group_norm: could not allocate ticket counters");
-    {
-        static bool env_read = false;
-        if (!env_read) {
-            const char* e = getenv("B200SD_GN_FUSED");
-            if (e && e[0] == '0') g_gn_fused = false;
-            env_read = true;
-        }
-    }
     const int vecs = C / 8;
     B200SD_REQUIRE(vecs <= 384, "b200sd_group_norm: too many channels (%d)", C);
     // ---- cluster path: one cluster of <= 8 CTAs per (image, channel chunk), slab in shared memory ----
@@ -770,35 +569,7 @@ extern "C" int b200sd_group_norm(const void* x0, const void* x1, int32_t c0, int
             return 0;
         }
     }
-    // ---- single-launch path: all CTAs co-resident (<= one per SM), pixel slab kept in shared memory ----
-    {
-        const int sms = num_sms();
-        int B = std::min({sms / std::max(1, n_img), 160, std::max(1, hw / 4)});
-        if (B >= 1 && n_img <= sms) {
-            const int ppb = (hw + B - 1) / B;
-            B = (hw + ppb - 1) / ppb;
-            const int frows = std::max(1, std::min(512 / vecs, ppb));
-            const int fthreads = (vecs * frows + 31) / 32 * 32;
-            const size_t fsmem = static_cast<size_t>(ppb) * vecs * 16 +
-                                 (static_cast<size_t>(frows) * C * 2 + static_cast<size_t>(C) * 2 + groups * 2) * sizeof(float);
-            const size_t need_ws = static_cast<size_t>(n_img) * B * groups * 2 * sizeof(float);
-            if (fsmem <= 200 * 1024 && fthreads <= 512 && need_ws <= stats_ws_bytes && g_gn_fused) {
-                static bool attr = false;
-                if (!attr) {
-                    B200SD_CHECK_CUDA(cudaFuncSetAttribute(gn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                           200 * 1024));
-                    attr = true;
-                }
-                B200SD_CHECK_CUDA(launch_kernel(gn_fused_kernel, dim3(B, n_img), dim3(fthreads), fsmem, stream,
-                                                reinterpret_cast<const __half*>(x0), reinterpret_cast<const __half*>(x1),
-                                                c0, c1, hw, groups, frows, ppb, eps, gamma, beta, silu,
-                                                reinterpret_cast<__half*>(out), stats_ws, tickets + kGnMaxImages));
-                B200SD_CHECK_CUDA(cudaGetLastError());
-                count_launch(1);
-                return 0;
-            }
-        }
-    }
+    // ---- fallback (slab larger than shared memory, e.g. the VAE decoder's 512x512 maps): statistics + apply ----
     const int chunks = gn_chunks(hw, n_img);
     const int rows = std::max(1, std::min(256 / vecs, (hw + chunks - 1) / chunks));
     const int threads = (vecs * rows + 31) / 32 * 32;

@@ -169,11 +169,11 @@ def gemm_args(mode, a0, wgt, out, *, a1=None, bias=None, residual=None, m=0, n=0
 
 
 def describe_plan(mode, m=0, n=0, c0=0, c1=0, n_img=0, h=0, w=0, stride=1, geglu=False, has_bias=True,
-                  has_residual=False, bias_rows=0) -> str:
+                  has_residual=False, bias_rows=0, split_k=0, block_n=0) -> str:
     """Host-only: the tiling the launcher would choose (no GPU needed)."""
     a = GemmArgs()
     a.mode, a.m, a.n, a.c0, a.c1, a.n_img, a.h, a.w, a.stride = mode, m, n, c0, c1, n_img, h, w, stride
-    a.geglu, a.bias_rows = int(geglu), bias_rows
+    a.geglu, a.bias_rows, a.split_k, a.block_n = int(geglu), bias_rows, split_k, block_n
     a.bias = 1 if has_bias else None       # only tested for null-ness by the planner
     a.residual = 1 if has_residual else None
     buf = C.create_string_buffer(512)

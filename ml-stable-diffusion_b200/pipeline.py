@@ -69,8 +69,11 @@ class B200StableDiffusionPipeline:
     """Drop-in for ``CoreMLStableDiffusionPipeline`` on one B200."""
 
     def __init__(self, unet: UNetModel, vae_decoder: VAEDecoderModel, scheduler="DDIM", text_encoder=None,
-                 tokenizer=None, force_zeros_for_empty_prompt=True, xl=False):
+                 tokenizer=None, force_zeros_for_empty_prompt=True, xl=False, controlnet=None):
         self.unet = unet
+        self.controlnet = list(controlnet) if controlnet else None  # pipeline.py:66,106: Optional[List[model]]
+        if self.controlnet and not unet.engine.support_controlnet:
+            raise ValueError("the UNet was not built with support_controlnet=True (no additional_residual inputs)")
         self.vae_decoder = vae_decoder
         self.scheduler_name = scheduler
         self.device = unet.device
@@ -94,11 +97,14 @@ class B200StableDiffusionPipeline:
     # ---------------------------------------------------------------- factory
     @classmethod
     def from_random_init(cls, model_version="sd21-base", images_per_call=1, device="cuda", seed=0,
-                         scheduler="DDIM", height=512, width=512, unet_cfg=None, vae_cfg=None):
-        """Random-init weights of the named architecture (no checkpoints exist offline)."""
+                         scheduler="DDIM", height=512, width=512, unet_cfg=None, vae_cfg=None, controlnet_cfgs=None):
+        """Random-init weights of the named architecture (no checkpoints exist offline).  ``controlnet_cfgs``:
+        list of ControlNet configs (seeded seed+2, seed+3, ...); switches the UNet to its control variant."""
         unet_cfg = unet_cfg or {"sd21-base": C.SD21_BASE_UNET, "sdxl-base": C.SDXL_BASE_UNET,
                                 "tiny": C.TINY_UNET}[model_version]
         vae_cfg = vae_cfg or (C.TINY_VAE if model_version == "tiny" else C.SD_VAE)
+        if controlnet_cfgs:
+            unet_cfg = dict(unet_cfg, support_controlnet=True)
         f = 2 ** (len(vae_cfg["block_out_channels"]) - 1)
         usd = C.random_state_dict(C.unet_param_shapes(unet_cfg), seed=seed, dtype=torch.float16)
         vsd = C.random_state_dict(C.vae_decoder_param_shapes(vae_cfg), seed=seed + 1, dtype=torch.float16)
@@ -106,7 +112,14 @@ class B200StableDiffusionPipeline:
                          device=device)
         vae = VAEDecoderModel(vae_cfg, vsd, batch=images_per_call, height=height // f, width=width // f,
                               device=device)
-        return cls(unet, vae, scheduler=scheduler, xl=unet.engine.xl)
+        nets = None
+        if controlnet_cfgs:
+            from .controlnet import ControlNetModel
+            nets = [ControlNetModel(c, C.random_state_dict(C.controlnet_param_shapes(c), seed=seed + 2 + i,
+                                                           dtype=torch.float16),
+                                    batch=2 * images_per_call, height=height // f, width=width // f, device=device)
+                    for i, c in enumerate(controlnet_cfgs)]
+        return cls(unet, vae, scheduler=scheduler, xl=unet.engine.xl, controlnet=nets)
 
     # ---------------------------------------------------------------- reference-named helpers
     def check_inputs(self, prompt, height, width, callback_steps):
@@ -147,6 +160,35 @@ class B200StableDiffusionPipeline:
             raise ValueError(f"Unexpected latents shape, got {latents.shape}, expected {shape}")
         return latents.astype(np.float32) * 1.0
 
+    def prepare_control_cond(self, controlnet_cond, do_classifier_free_guidance, batch_size, num_images_per_prompt):
+        """pipeline.py:345-356: each (3, H, W) condition image is repeated per image and doubled for CFG."""
+        out = []
+        for cond in controlnet_cond:
+            cond = np.stack([np.asarray(cond)] * batch_size * num_images_per_prompt)
+            if do_classifier_free_guidance:
+                cond = np.concatenate([cond] * 2)
+            out.append(cond)
+        return out
+
+    def run_controlnet(self, sample, timestep, encoder_hidden_states, controlnet_cond):
+        """pipeline.py:259-284 on the device: every ControlNet sees the same UNet inputs; their residuals are
+        summed (fp16, like the reference's in-place numpy add).  Returns NCHW views of NHWC fp16 tensors."""
+        if not self.controlnet:
+            raise ValueError("Conditions for controlnet are given but the pipeline has no controlnet modules")
+        total = None
+        for module, cond in zip(self.controlnet, controlnet_cond):
+            module._sample.copy_(sample)
+            module._t.copy_(timestep)
+            module._ctx.copy_(encoder_hidden_states)
+            module._cond.copy_(cond)
+            outs = module.forward_device()
+            if total is None:
+                total = list(outs)
+            else:
+                for acc, o in zip(total, outs):
+                    L.add(acc, o, out=acc)
+        return [r.permute(0, 3, 1, 2) for r in total]
+
     @staticmethod
     def numpy_to_pil(images):
         from PIL import Image
@@ -155,7 +197,8 @@ class B200StableDiffusionPipeline:
 
     # ---------------------------------------------------------------- device loop
     def denoise(self, text_embeddings, latents, num_inference_steps, guidance_scale, callback=None,
-                callback_steps=1, time_ids=None, text_embeds=None, return_denoised=False, record=None):
+                callback_steps=1, time_ids=None, text_embeds=None, return_denoised=False, record=None,
+                controlnet_cond=None):
         """Runs the N-step loop entirely on the device.  ``text_embeddings`` (2B, D, 1, S) and ``latents``
         (B, C, h, w) may be numpy (copied once, before the loop) or CUDA tensors.  ``record`` (a list) receives
         (timestep, noise_pred, latents_after_step) clones per step -- a debugging / testing aid."""
@@ -164,11 +207,16 @@ class B200StableDiffusionPipeline:
         self._ctx.copy_(torch.as_tensor(text_embeddings), non_blocking=True)
         self._latents.copy_(torch.as_tensor(latents), non_blocking=True)
         self._hist.zero_()
+        if controlnet_cond:
+            controlnet_cond = [torch.as_tensor(c).to(self.device, torch.float16) for c in controlnet_cond]
         k = L.StepCoeffs()
         for i, st in enumerate(sched.plan()):
             self._t.fill_(float(st.timestep))
             sample = torch.cat([self._latents, self._latents], 0)  # pipeline.py:502
-            noise_pred = self.unet.forward_device(sample, self._t, self._ctx, time_ids, text_embeds)
+            residuals = None
+            if controlnet_cond:  # pipeline.py:515-529
+                residuals = self.run_controlnet(sample, self._t, self._ctx, controlnet_cond)
+            noise_pred = self.unet.forward_device(sample, self._t, self._ctx, time_ids, text_embeds, residuals)
             k.guidance = float(guidance_scale)
             k.cx, k.ce, k.x0_cx, k.x0_ce = st.cx, st.ce, st.x0_cx, st.x0_ce
             for j in range(4):
@@ -206,8 +254,8 @@ class B200StableDiffusionPipeline:
             raise ValueError(f"this pipeline instance was built for {self.height}x{self.width} images")
         if eta != 0.0:
             raise ValueError("only eta = 0 (deterministic DDIM) is implemented")
-        if controlnet_cond is not None:
-            raise NotImplementedError("ControlNet conditioning is not wired into this pipeline yet")
+        if controlnet_cond and not self.controlnet:
+            raise ValueError("Conditions for controlnet are given but the pipeline has no controlnet modules")
         prompts = [prompt] if isinstance(prompt, str) else list(prompt)
         prompts = [p for p in prompts for _ in range(num_images_per_prompt)]
         if len(prompts) != self.images_per_call:
@@ -228,8 +276,10 @@ class B200StableDiffusionPipeline:
             if text_embeds is None:
                 text_embeds = torch.zeros(2 * self.images_per_call, 1280, device=self.device)
         lat = self.prepare_latents(len(prompts), self.unet.in_channels, height, width, latents)
+        if controlnet_cond:  # pipeline.py:488-494
+            controlnet_cond = self.prepare_control_cond(controlnet_cond, do_cfg, len(prompts), 1)
         final = self.denoise(text_embeddings, lat, num_inference_steps, guidance_scale, callback, callback_steps,
-                             time_ids, text_embeds)
+                             time_ids, text_embeds, controlnet_cond=controlnet_cond or None)
         image = self.decode_latents(final).cpu().numpy()  # single device->host copy of the result
         has_nsfw = None  # the safety checker is out of scope
         if output_type == "pil":

@@ -97,6 +97,33 @@ def test_conv3x3(cuda_lib, n, h, w, ci, co):
     _close(out, _conv_ref(x, wt, b), 3e-3, 3e-3, f"conv3x3 {n}x{h}x{w} {ci}->{co}")
 
 
+@pytest.mark.parametrize("m,split,out_dtype", [(128, 8, torch.float16), (200, 4, torch.float16), (512, 2, torch.float32)])
+def test_linear_split_k_cluster(cuda_lib, m, split, out_dtype):
+    """split-K reduced inside a thread-block cluster through DSMEM (2 / 4 / 8 CTAs per tile), ragged last tile."""
+    n, k = 640, 2560
+    x, w, r = _rand(m, k, seed=1), _rand(n, k, scale=k ** -0.5, seed=2), _rand(m, n, seed=3)
+    b = torch.randn(n, device="cuda")
+    ref = x.float() @ w.float().t() + b + r.float()
+    plan = cuda_lib.describe_plan(0, m=m, n=n, c0=k, has_residual=True, split_k=split)
+    assert "cluster=1" in plan and f"splits={split} " in plan, plan
+    out = cuda_lib.linear(x, w, b, r, split_k=split, out_dtype=out_dtype)
+    _close(out, ref, 3e-3, 2e-3, f"cluster split-K {split}")
+    # bitwise reproducible: fixed rank order of the DSMEM reduction
+    assert torch.equal(out, cuda_lib.linear(x, w, b, r, split_k=split, out_dtype=out_dtype))
+
+
+def test_conv3x3_split_k_cluster_temb_residual(cuda_lib):
+    n, h, w, c0, c1, co = 2, 16, 16, 640, 320, 640
+    x0, x1 = _rand(n, h, w, c0, seed=1), _rand(n, h, w, c1, seed=2)
+    wt = _rand(co, c0 + c1, 3, 3, scale=(9 * (c0 + c1)) ** -0.5, seed=3)
+    bias_img = torch.randn(n, co, device="cuda")
+    res = _rand(n, h, w, co, seed=4)
+    ref = _conv_ref(torch.cat([x0, x1], -1), wt) + bias_img[:, None, None, :] + res.float()
+    for split in (4, 8):
+        out = cuda_lib.conv3x3(x0, _pack(wt), bias_img, res, x1=x1, bias_rows=h * w, split_k=split)
+        _close(out, ref, 4e-3, 3e-3, f"conv cluster split-K {split}")
+
+
 def test_conv3x3_small_channels(cuda_lib):
     # conv_in: 4 channels padded to 8; conv_out: 4 output channels, fp32 out
     x = _rand(2, 64, 64, 8, seed=1)

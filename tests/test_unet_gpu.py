@@ -267,3 +267,44 @@ def test_controlnet_tiny_vs_oracle_and_chain_into_unet(cuda_lib):
     with torch.no_grad():
         uref = R.unet_forward(usd, ucfg, x, torch.tensor([501.0, 501.0]), c, additional_residuals=ref).numpy()
     _check(out, uref, "controlnet -> control-unet chain")
+
+
+def test_pipeline_tiny_with_controlnet_vs_oracle(cuda_lib):
+    """BASELINE configs[4] shape class: ControlNet residuals computed every step inside the pipeline loop
+    (pipeline.py:488-494, 515-536), checked against the same loop run with the oracle."""
+    from b200sd.pipeline import B200StableDiffusionPipeline
+    from b200sd import scheduler as S
+
+    pipe = B200StableDiffusionPipeline.from_random_init("tiny", images_per_call=1, height=64, width=64, seed=21,
+                                                        controlnet_cfgs=[config.TINY_CONTROLNET])
+    np.random.seed(5)
+    lat0 = np.random.randn(1, 4, 16, 16).astype(np.float16)
+    cond = np.random.rand(3, 128, 128).astype(np.float16)
+    steps, g = 3, 5.0
+    rec = []
+    emb_np = pipe._encode_prompt(["a cat"], True, None)
+    cc = pipe.prepare_control_cond([cond], True, 1, 1)
+    assert cc[0].shape == (2, 3, 128, 128)
+    final = pipe.denoise(emb_np, lat0.astype(np.float32), steps, g, record=rec, controlnet_cond=cc).cpu().numpy()
+    # oracle loop
+    ucfg = dict(config.TINY_UNET, support_controlnet=True)
+    usd = config.random_state_dict(config.unet_param_shapes(ucfg), seed=21, dtype=torch.float16)
+    csd = config.random_state_dict(config.controlnet_param_shapes(config.TINY_CONTROLNET), seed=23, dtype=torch.float16)
+    emb = torch.from_numpy(emb_np).float()
+    x = torch.from_numpy(lat0.astype(np.float32))
+    abar = R.alphas_cumprod()
+    cond2 = torch.from_numpy(cc[0]).float()
+    with torch.no_grad():
+        for t in S.DDIMScheduler(steps).timesteps:
+            tt = torch.tensor([float(t)] * 2)
+            xin = torch.cat([x, x]).half().float()
+            res = R.controlnet_forward(csd, config.TINY_CONTROLNET, xin, tt, emb, cond2)
+            eps = R.unet_forward(usd, ucfg, xin, tt, emb, additional_residuals=res)
+            x = R.ddim_step(R.cfg_combine(eps[:1], eps[1:], g), t, x, abar, steps)
+    _check(final, x.numpy(), "pipeline + controlnet latents", max_abs=2e-2 * max(1.0, float(x.abs().max())))
+    # the public call accepts the reference's argument and rejects it without modules
+    out = pipe("a cat", height=64, width=64, num_inference_steps=2, controlnet_cond=[cond], output_type="np")
+    assert out.images.shape == (1, 64, 64, 3)
+    plain = B200StableDiffusionPipeline.from_random_init("tiny", images_per_call=1, height=64, width=64, seed=21)
+    with pytest.raises(ValueError, match="no controlnet modules"):
+        plain("a cat", height=64, width=64, num_inference_steps=1, controlnet_cond=[cond])
