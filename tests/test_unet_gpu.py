@@ -308,3 +308,46 @@ def test_pipeline_tiny_with_controlnet_vs_oracle(cuda_lib):
     plain = B200StableDiffusionPipeline.from_random_init("tiny", images_per_call=1, height=64, width=64, seed=21)
     with pytest.raises(ValueError, match="no controlnet modules"):
         plain("a cat", height=64, width=64, num_inference_steps=1, controlnet_cond=[cond])
+
+
+def test_unet_sdxl_base_768_vs_reference_golden(cuda_lib):
+    """BASELINE configs[3] parity case: SDXL-base (2.57 B parameters, text_time conditioning, 1/2/10 transformer
+    layers per block) at 768x768, against the unmodified reference run on the CPU (make_golden_sdxl.py)."""
+    from b200sd.model import UNetModel
+
+    path = os.path.join(GOLD, "unet_sdxl_768.npz")
+    if not os.path.exists(path):
+        pytest.skip("SDXL golden fixture not generated")
+    gold = np.load(path)
+    cfg = config.SDXL_BASE_UNET
+    sd = config.random_state_dict(config.unet_param_shapes(cfg), seed=int(gold["weight_seed"]), dtype=torch.float16)
+    keys = sorted(sd.keys())
+    fp = np.array([float(sd[k].double().sum()) for k in (keys[0], keys[len(keys) // 2], keys[-1])] + [float(len(keys))])
+    assert np.allclose(fp, gold["fingerprint"], rtol=1e-6), "weight generator differs from the one that made the golden"
+    g = torch.Generator().manual_seed(int(gold["input_seed"]))
+    x = torch.randn(2, 4, 96, 96, generator=g)
+    c = torch.randn(2, 2048, 1, 77, generator=g)
+    te = torch.randn(2, 1280, generator=torch.Generator().manual_seed(int(gold["embed_seed"])))
+    m = UNetModel(cfg, sd, batch=2, height=96, width=96, use_cuda_graph=True)
+    del sd
+    out = m(sample=x.half().numpy(), timestep=np.array([981.0, 981.0], np.float16),
+            encoder_hidden_states=c.half().numpy(), time_ids=gold["time_ids"].astype(np.float16),
+            text_embeds=te.half().numpy())["noise_pred"]
+    ref = gold["noise_pred"]
+    _check(out, ref, "SDXL-base 768 unet vs reference golden", max_abs=MAX_ABS * max(1.0, float(np.abs(ref).max())))
+
+
+def test_vae_decoder_sd_full_size_vs_oracle(cuda_lib):
+    """The SD VAE decoder at its real size (64x64 latents -> 512x512 image, 128..512 channels, mid-block attention
+    over 4096 tokens at d=512) against the oracle run live on the host."""
+    from b200sd.vae import VAEDecoderModel
+
+    cfg = config.SD_VAE
+    sd = config.random_state_dict(config.vae_decoder_param_shapes(cfg), seed=41, dtype=torch.float16)
+    z = torch.randn(1, 4, 64, 64, generator=torch.Generator().manual_seed(42)) * 3.0
+    m = VAEDecoderModel(cfg, sd, batch=1, height=64, width=64)
+    img = m(z=z.half().numpy())["image"]
+    assert img.shape == (1, 3, 512, 512)
+    with torch.no_grad():
+        ref = R.vae_decode(sd, cfg, z.half().float()).numpy()
+    _check(img, ref, "SD vae decoder 512x512", max_abs=2e-2 * max(1.0, float(np.abs(ref).max())))
