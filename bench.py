@@ -197,9 +197,16 @@ def gemm_roofline(pipe, peaks):
     ms = sum(r[1].elapsed_time(r[2]) for r in recs)
     achieved = flops / (ms * 1e-3) / 1e12
     burst, sustained, _, how = peaks
+    traffic = None  # DRAM bytes per launch of the same kernel from the committed ncu pass (profiles/traffic_r1.json)
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic_r1.json")) as f:
+            traffic = round(json.load(f)["dram_bytes_per_launch"])
+    except (OSError, KeyError, ValueError):
+        pass
     return {"bound": "tensor", "kernel": "umma_gemm_kernel (all conv3x3 / 1x1 / linear launches of one UNet forward)",
             "achieved": round(achieved, 1), "peak": sustained, "unit": "TFLOP/s", "frac": round(achieved / sustained, 4),
-            "peak_kind": f"{how} sustained bf16 dense (kernel timed inside a long step)", "traffic": None,
+            "peak_kind": f"{how} sustained bf16 dense (kernel timed inside a long step)", "traffic": traffic,
+            "traffic_unit": "DRAM bytes per launch (ncu, L2 flushed per kernel; algorithmic = weights 1.73e9 B / forward)",
             "launches": len(recs), "algorithmic_tflop": round(flops / 1e12, 4), "kernel_ms_sum": round(ms, 3)}
 
 

@@ -8,8 +8,9 @@
 // (B, heads, Sq, Sk) score tensor the reference materialises (671 MB at S=4096) never leaves the SM.
 //
 // CTA = 128 queries x 1 head; warp 0 TMA producer, warp 1 MMA issuer, warps 2..5 softmax (one query
-// row per thread).  256 TMEM columns (S 128 + O_step 64) so two CTAs share an SM and overlap one
-// CTA's softmax with the other's MMAs.
+// row per thread).  The pipeline runs on 64-key halves: S is double-buffered in TMEM (2 x 64 columns) and P
+// in shared memory (2 x 16 KiB), so S_{h+1} = Q K^T and O += P_{h-1} V execute on the tensor core while the
+// softmax warps exponentiate half h.  256 TMEM columns (S 128 + O 64) so two CTAs share an SM.
 #include "common.cuh"
 #include "../../include/b200sd.h"
 
@@ -18,7 +19,8 @@ namespace b200sd {
 extern void count_launch(int n);
 
 static constexpr int kQ = 128;   // queries per CTA
-static constexpr int kKV = 128;  // keys per step
+static constexpr int kKV = 128;  // keys per K/V tile (one TMA load)
+static constexpr int kHalf = 64;  // keys per pipeline step: S is double-buffered by halves of a tile
 static constexpr int kD = 64;    // head dim
 static constexpr int kAttnThreads = 192;
 static constexpr int kTileBytes = 128 * 64 * 2;  // 16 KiB: one [128 x 64] fp16 tile
@@ -47,11 +49,11 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
     uint64_t* q_full = bars + 0;
     uint64_t* kv_full = bars + 1;   // [2]
     uint64_t* kv_empty = bars + 3;  // [2]
-    uint64_t* s_full = bars + 5;
-    uint64_t* s_empty = bars + 6;
-    uint64_t* p_full = bars + 7;
-    uint64_t* o_full = bars + 8;
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 9);
+    uint64_t* s_full = bars + 5;    // [2]  per 64-key half of S
+    uint64_t* s_empty = bars + 7;   // [2]
+    uint64_t* p_full = bars + 9;    // [2]  per 64-key chunk of P
+    uint64_t* o_full = bars + 11;   // [2]  P V of the chunk retired (P chunk reusable; O quiescent up to here)
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 13);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -59,6 +61,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
     const int head = blockIdx.y;
     const int batch = blockIdx.z;
     const int n_kv = (p.sk + kKV - 1) / kKV;
+    const int n_half = (p.sk + kHalf - 1) / kHalf;  // the pipeline runs on 64-key halves of the 128-key tiles
 
     if (threadIdx.x == 0) {
         if ((smem_u32(smem) & 1023u) != 0) atomicExch(p.error_flag, 1);  // swizzle needs 1024 B alignment
@@ -70,10 +73,12 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
             mbar_init(&kv_full[s], 1);
             mbar_init(&kv_empty[s], 1);
         }
-        mbar_init(s_full, 1);
-        mbar_init(s_empty, 128);
-        mbar_init(p_full, 128);
-        mbar_init(o_full, 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&s_full[b], 1);
+            mbar_init(&s_empty[b], 128);
+            mbar_init(&p_full[b], 128);
+            mbar_init(&o_full[b], 1);
+        }
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -85,7 +90,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
     pdl_wait();  // PDL: the prologue above overlapped the previous kernel's tail
-    const uint32_t tmem_s = tmem_base;        // 128 columns
+    const uint32_t tmem_s = tmem_base;        // 2 x 64 columns (double-buffered S halves)
     const uint32_t tmem_o = tmem_base + 128;  // 64 columns
 
     if (warp == 0) {
@@ -104,62 +109,65 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
             }
         }
     } else if (warp == 1) {
-        // S = Q K^T : A = Q (K-major), B = K tile (K-major), M=128 N=128 K=64
-        const uint32_t idesc_s = make_idesc_f16(128, kKV, 0, 0);
-        // O_step = P V : A = P (K-major, two 64-key chunks), B = V tile [keys][d] = MN-major, N=64 K=128
+        // S_h = Q K_h^T : A = Q (K-major), B = 64 rows of the K tile (K-major), M=128 N=64 K=64
+        const uint32_t idesc_s = make_idesc_f16(128, kHalf, 0, 0);
+        // O += P_h V_h : A = P chunk (K-major, 64 keys), B = 64 rows of the V tile [keys][d] = MN-major, N=64 K=64
         const uint32_t idesc_o = make_idesc_f16(128, kD, 0, 1);
         const uint32_t q_addr = smem_u32(smem + kSmemQ);
         const uint32_t p_addr = smem_u32(smem + kSmemP);
-        auto issue_s = [&](int j) {
+        auto issue_s = [&](int h) {
+            const int j = h >> 1, b = h & 1;
             const int st = j % kKvStages;
             mbar_wait(&kv_full[st], (j / kKvStages) & 1);
-            if (j > 0) mbar_wait(s_empty, (j - 1) & 1);
+            if (h >= 2) mbar_wait(&s_empty[b], ((h - 2) >> 1) & 1);
             tc_fence_after();
             if (lane == 0) {
                 const uint64_t adesc = make_smem_desc_sw128(q_addr, 1024, 0);
-                const uint64_t bdesc = make_smem_desc_sw128(smem_u32(smem + kSmemK + st * kTileBytes), 1024, 0);
+                const uint64_t bdesc =
+                    make_smem_desc_sw128(smem_u32(smem + kSmemK + st * kTileBytes) + b * (kHalf * 128), 1024, 0);
 #pragma unroll
                 for (int k = 0; k < kD / 16; ++k)
-                    umma_f16_ss(tmem_s, adesc + 2 * k, bdesc + 2 * k, idesc_s, k > 0 ? 1u : 0u);
-                umma_commit(s_full);
+                    umma_f16_ss(tmem_s + b * kHalf, adesc + 2 * k, bdesc + 2 * k, idesc_s, k > 0 ? 1u : 0u);
+                umma_commit(&s_full[b]);
             }
             __syncwarp();
         };
         mbar_wait(q_full, 0);
         issue_s(0);
-        for (int j = 0; j < n_kv; ++j) {
-            if (j + 1 < n_kv) issue_s(j + 1);
+        if (n_half > 1) issue_s(1);
+        for (int h = 0; h < n_half; ++h) {
+            const int j = h >> 1, b = h & 1;
             const int st = j % kKvStages;
-            mbar_wait(p_full, j & 1);
+            mbar_wait(&p_full[b], (h >> 1) & 1);
             tc_fence_after();
             if (lane == 0) {
-                const uint32_t v_addr = smem_u32(smem + kSmemV + st * kTileBytes);
+                const uint32_t v_addr = smem_u32(smem + kSmemV + st * kTileBytes) + b * (kHalf * 128);
 #pragma unroll
-                for (int k = 0; k < kKV / 16; ++k) {
-                    // A: chunk (k / 4) of P, +32 B per 16 keys inside the chunk's 128 B rows
-                    const uint64_t adesc =
-                        make_smem_desc_sw128(p_addr + (k >> 2) * kTileBytes, 1024, 0) + 2 * (k & 3);
-                    // B: 16 keys = 16 rows of 128 B = 2048 B further down the MN-major tile
+                for (int k = 0; k < kHalf / 16; ++k) {
+                    // A: +32 B per 16 keys inside the chunk's 128 B rows;  B: 16 keys = 16 rows of 128 B = 2048 B
+                    const uint64_t adesc = make_smem_desc_sw128(p_addr + b * kTileBytes, 1024, 0) + 2 * k;
                     const uint64_t bdesc = make_smem_desc_sw128(v_addr + k * 2048, 1024, kKV * 128);
-                    umma_f16_ss(tmem_o, adesc, bdesc, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+                    umma_f16_ss(tmem_o, adesc, bdesc, idesc_o, (h > 0 || k > 0) ? 1u : 0u);
                 }
-                umma_commit(o_full);
-                umma_commit(&kv_empty[st]);
+                umma_commit(&o_full[b]);
+                if (b == 1 || h == n_half - 1) umma_commit(&kv_empty[st]);  // last half of this K/V tile
             }
             __syncwarp();
+            if (h + 2 < n_half) issue_s(h + 2);
         }
     } else {
         // ---------------- softmax warps: one query row per thread ----------------
         // O accumulates in TMEM across all KV steps (PV MMAs with accumulate=1).  The exp2 reference m_ref
-        // is refreshed lazily: a full, unmasked tile is exponentiated optimistically against the current
+        // is refreshed lazily: a full, unmasked half tile is exponentiated optimistically against the current
         // m_ref in ONE pass over S (row maximum tracked on the side); only if some row's maximum exceeds
-        // m_ref by more than kTau (log2 domain; P <= 2^kTau stays inside fp16) does the warp rescale its 32
-        // rows of O in TMEM and redo the tile -- rare after the first tiles.
+        // m_ref by more than kTau (log2 domain; P <= 2^kTau stays inside fp16) does the warp wait for the
+        // outstanding P V MMAs, rescale its 32 rows of O in TMEM and redo the half -- rare after the first tiles.
+        // S is double-buffered by halves, so the tensor core computes S_{h+1} / S_{h+2} and P_{h-1} V while
+        // this half is in the exponentials.
         constexpr float kTau = 8.0f;
         const int lane_group = warp & 3;
         const int row = lane_group * 32 + lane;
         const uint32_t lane_addr = static_cast<uint32_t>(lane_group * 32) << 16;
-        const uint32_t s_addr = tmem_s + lane_addr;
         const uint32_t o_addr = tmem_o + lane_addr;
         const float sl2 = p.scale_log2;
         float m_ref = -INFINITY, l_run = 0.f;
@@ -167,57 +175,49 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
         uint8_t* p_row = smem + kSmemP + row * 128;
         const int sw = row & 7;
 
-        // lean row maximum of a full unmasked tile (raw scores)
-        auto row_max_lean = [&]() {
+        // lean row maximum of a full unmasked half (raw scores)
+        auto row_max_lean = [&](uint32_t s_addr) {
             float m0 = -INFINITY, m1 = -INFINITY;
-#pragma unroll 1
-            for (int c = 0; c < kKV; c += 64) {
-                uint32_t va[32], vb[32];
-                tmem_ld32(s_addr + c, va);
-                tmem_ld32(s_addr + c + 32, vb);
-                tmem_ld_wait();
+            uint32_t va[32], vb[32];
+            tmem_ld32(s_addr, va);
+            tmem_ld32(s_addr + 32, vb);
+            tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                    m0 = fmaxf(m0, fmaxf(__uint_as_float(va[i]), __uint_as_float(vb[i])));
-                    m1 = fmaxf(m1, fmaxf(__uint_as_float(va[i + 1]), __uint_as_float(vb[i + 1])));
-                }
+            for (int i = 0; i < 32; i += 2) {
+                m0 = fmaxf(m0, fmaxf(__uint_as_float(va[i]), __uint_as_float(vb[i])));
+                m1 = fmaxf(m1, fmaxf(__uint_as_float(va[i + 1]), __uint_as_float(vb[i + 1])));
             }
             return fmaxf(m0, m1);
         };
-        // lean probabilities of a full unmasked tile against reference `ref`: writes the fp16 P tile,
-        // returns the row sum and (through tmax) the raw row maximum
-        auto probs_lean = [&](float ref, float& tmax) {
+        // lean probabilities of a full unmasked half against reference `ref`: writes the fp16 P chunk (one
+        // 128-byte swizzled row per query: eight 16-byte pieces), returns the row sum and (tmax) the raw maximum
+        auto probs_lean = [&](uint32_t s_addr, uint8_t* dst, float ref, float& tmax) {
             const float neg_m = -ref;
             float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
             float m0 = -INFINITY, m1 = -INFINITY;
-#pragma unroll 1
-            for (int c = 0; c < kKV; c += 64) {
-                uint32_t va[32], vb[32];
-                tmem_ld32(s_addr + c, va);
-                tmem_ld32(s_addr + c + 32, vb);
-                tmem_ld_wait();
-                uint32_t pk[32];
+            uint32_t va[32], vb[32];
+            tmem_ld32(s_addr, va);
+            tmem_ld32(s_addr + 32, vb);
+            tmem_ld_wait();
+            uint32_t pk[32];
 #pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                    const float a0 = __uint_as_float(va[i]), a1 = __uint_as_float(va[i + 1]);
-                    const float b0 = __uint_as_float(vb[i]), b1 = __uint_as_float(vb[i + 1]);
-                    m0 = fmaxf(m0, fmaxf(a0, b0));
-                    m1 = fmaxf(m1, fmaxf(a1, b1));
-                    const float p0 = ex2_approx(fmaf(a0, sl2, neg_m));
-                    const float p1 = ex2_approx(fmaf(a1, sl2, neg_m));
-                    const float p2 = ex2_approx(fmaf(b0, sl2, neg_m));
-                    const float p3 = ex2_approx(fmaf(b1, sl2, neg_m));
-                    s0 += p0, s1 += p1, s2 += p2, s3 += p3;
-                    pk[i >> 1] = pack_half2(p0, p1);
-                    pk[16 + (i >> 1)] = pack_half2(p2, p3);
-                }
-                // 64 keys = one 128-byte swizzled row of K-chunk (c / 64): eight 16-byte pieces
-                uint8_t* dst = p_row + (c >> 6) * kTileBytes;
+            for (int i = 0; i < 32; i += 2) {
+                const float a0 = __uint_as_float(va[i]), a1 = __uint_as_float(va[i + 1]);
+                const float b0 = __uint_as_float(vb[i]), b1 = __uint_as_float(vb[i + 1]);
+                m0 = fmaxf(m0, fmaxf(a0, b0));
+                m1 = fmaxf(m1, fmaxf(a1, b1));
+                const float p0 = ex2_approx(fmaf(a0, sl2, neg_m));
+                const float p1 = ex2_approx(fmaf(a1, sl2, neg_m));
+                const float p2 = ex2_approx(fmaf(b0, sl2, neg_m));
+                const float p3 = ex2_approx(fmaf(b1, sl2, neg_m));
+                s0 += p0, s1 += p1, s2 += p2, s3 += p3;
+                pk[i >> 1] = pack_half2(p0, p1);
+                pk[16 + (i >> 1)] = pack_half2(p2, p3);
+            }
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    uint4 val = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-                    *reinterpret_cast<uint4*>(dst + ((q ^ sw) << 4)) = val;
-                }
+            for (int q = 0; q < 8; ++q) {
+                uint4 val = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                *reinterpret_cast<uint4*>(dst + ((q ^ sw) << 4)) = val;
             }
             tmax = fmaxf(m0, m1);
             return (s0 + s1) + (s2 + s3);
@@ -238,51 +238,65 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
             l_run *= factor;
         };
 
-        for (int j = 0; j < n_kv; ++j) {
-            const int kvalid = min(kKV, p.sk - j * kKV);  // >= 1
-            mbar_wait(s_full, j & 1);
-            if (j > 0) mbar_wait(o_full, (j - 1) & 1);  // P V of the previous step done: P buffer and O are quiescent
+        for (int h = 0; h < n_half; ++h) {
+            const int b = h & 1;
+            const int kvalid = min(kHalf, p.sk - h * kHalf);  // >= 1
+            const uint32_t s_addr = tmem_s + lane_addr + b * kHalf;
+            uint8_t* dst = p_row + b * kTileBytes;
+            mbar_wait(&s_full[b], (h >> 1) & 1);
+            if (h >= 2) mbar_wait(&o_full[b], ((h - 2) >> 1) & 1);  // P V_{h-2} retired: P chunk b is free
             tc_fence_after();
-            float l_tile;
-            if (mask_row == nullptr && kvalid == kKV) {
-                if (j == 0) {
-                    m_ref = row_max_lean() * sl2;
+            // every P V issued so far (up to half h-1) has retired: O may be rescaled in place
+            auto wait_o_quiescent = [&]() {
+                if (h >= 1) {
+                    mbar_wait(&o_full[(h - 1) & 1], ((h - 1) >> 1) & 1);
+                    tc_fence_after();
+                }
+            };
+            float l_half;
+            if (mask_row == nullptr && kvalid == kHalf) {
+                if (h == 0) {
+                    m_ref = row_max_lean(s_addr) * sl2;
                     float unused;
-                    l_tile = probs_lean(m_ref, unused);
+                    l_half = probs_lean(s_addr, dst, m_ref, unused);
                 } else {
                     float tmax;
-                    l_tile = probs_lean(m_ref, tmax);
-                    const float m_tile = tmax * sl2;
-                    if (__any_sync(0xffffffffu, m_tile > m_ref + kTau)) {
-                        const float m_new = fmaxf(m_ref, m_tile);
+                    l_half = probs_lean(s_addr, dst, m_ref, tmax);
+                    const float m_half = tmax * sl2;
+                    if (__any_sync(0xffffffffu, m_half > m_ref + kTau)) {
+                        const float m_new = fmaxf(m_ref, m_half);
+                        wait_o_quiescent();
                         rescale_o(m_new);
                         m_ref = m_new;
-                        l_tile = probs_lean(m_ref, tmax);
+                        l_half = probs_lean(s_addr, dst, m_ref, tmax);
                     }
                 }
             } else {
-                // ---- general tile (additive mask and/or ragged tail): two passes with per-key predicates ----
-                float m_tile = -INFINITY;
+                // ---- general half (additive mask and/or ragged tail): two passes with per-key predicates ----
+                float m_half = -INFINITY;
 #pragma unroll 1
-                for (int c = 0; c < kKV; c += 32) {
+                for (int c = 0; c < kHalf; c += 32) {
                     uint32_t v[32];
                     tmem_ld32(s_addr + c, v);
                     tmem_ld_wait();
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
                         float sc = __uint_as_float(v[i]) * sl2;
-                        if (mask_row && c + i < kvalid) sc += mask_row[j * kKV + c + i] * 1.4426950408889634f;
-                        if (c + i < kvalid) m_tile = fmaxf(m_tile, sc);
+                        if (mask_row && c + i < kvalid) sc += mask_row[h * kHalf + c + i] * 1.4426950408889634f;
+                        if (c + i < kvalid) m_half = fmaxf(m_half, sc);
                     }
                 }
-                if (__any_sync(0xffffffffu, m_tile > m_ref + kTau)) {
-                    const float m_new = fmaxf(m_ref, m_tile);
-                    if (j > 0) rescale_o(m_new);
+                if (__any_sync(0xffffffffu, m_half > m_ref + kTau)) {
+                    const float m_new = fmaxf(m_ref, m_half);
+                    if (h > 0) {
+                        wait_o_quiescent();
+                        rescale_o(m_new);
+                    }
                     m_ref = m_new;
                 }
-                l_tile = 0.f;
+                l_half = 0.f;
 #pragma unroll 1
-                for (int c = 0; c < kKV; c += 32) {
+                for (int c = 0; c < kHalf; c += 32) {
                     uint32_t v[32];
                     tmem_ld32(s_addr + c, v);
                     tmem_ld_wait();
@@ -291,16 +305,15 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
                     for (int i = 0; i < 32; i += 2) {
                         float s0 = __uint_as_float(v[i]) * sl2, s1 = __uint_as_float(v[i + 1]) * sl2;
                         if (mask_row) {
-                            if (c + i < kvalid) s0 += mask_row[j * kKV + c + i] * 1.4426950408889634f;
-                            if (c + i + 1 < kvalid) s1 += mask_row[j * kKV + c + i + 1] * 1.4426950408889634f;
+                            if (c + i < kvalid) s0 += mask_row[h * kHalf + c + i] * 1.4426950408889634f;
+                            if (c + i + 1 < kvalid) s1 += mask_row[h * kHalf + c + i + 1] * 1.4426950408889634f;
                         }
                         const float p0 = (c + i < kvalid) ? ex2_approx(s0 - m_ref) : 0.f;
                         const float p1 = (c + i + 1 < kvalid) ? ex2_approx(s1 - m_ref) : 0.f;
-                        l_tile += p0 + p1;
+                        l_half += p0 + p1;
                         pk[i >> 1] = pack_half2(p0, p1);
                     }
-                    uint8_t* dst = p_row + (c >> 6) * kTileBytes;
-                    const int piece0 = (c & 63) >> 3;
+                    const int piece0 = c >> 3;
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         uint4 val = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
@@ -308,14 +321,14 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
                     }
                 }
             }
-            l_run += l_tile;
+            l_run += l_half;
             tc_fence_before();
-            mbar_arrive(s_empty);
+            mbar_arrive(&s_empty[b]);
             fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
-            mbar_arrive(p_full);
+            mbar_arrive(&p_full[b]);
         }
-        // ---- normalise and store ----
-        mbar_wait(o_full, (n_kv - 1) & 1);
+        // ---- normalise and store (the last commit covers every earlier P V) ----
+        mbar_wait(&o_full[(n_half - 1) & 1], ((n_half - 1) >> 1) & 1);
         tc_fence_after();
         const float inv_l = 1.0f / l_run;
         const bool store = q0 + row < p.sq;

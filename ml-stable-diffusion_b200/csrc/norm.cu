@@ -248,23 +248,29 @@ __global__ void gn_cluster_kernel(const __half* __restrict__ x0, const __half* _
 
     extern __shared__ __align__(16) uint8_t csm[];
     uint4* slab = reinterpret_cast<uint4*>(csm);                                   // [rows_per_cta][vpr]
-    float* red = reinterpret_cast<float*>(slab + static_cast<size_t>(rows_per_cta) * vpr);  // [TY][chunk_ch]
-    float* chsum = red + TY * chunk_ch;                                            // [chunk_ch]
+    float* red = reinterpret_cast<float*>(slab + static_cast<size_t>(rows_per_cta) * vpr);  // [TY][chunk_ch + 1]
+    float* chsum = red + TY * (chunk_ch + 1);                                      // [chunk_ch]
     float* xchg = chsum + chunk_ch;                                                // [2][ng]  (read by the peers)
     float* stat = xchg + 2 * ng;                                                   // [2][ng]  mean, rstd
     pdl_wait();
 
-    // fold the threads' per-channel registers: rows -> channels -> groups, then across the cluster
+    // fold the threads' per-channel registers: rows -> channels -> groups, then across the cluster.  Row stride
+    // chunk_ch + 1 (odd) keeps the column reads of the second step free of bank conflicts; every sum has a
+    // fixed association order (bitwise reproducible).
+    const int ldred = chunk_ch + 1;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     auto cluster_total = [&](float (&v)[8], int slot) {
         if (active) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) red[ty * chunk_ch + cv * 8 + e] = v[e];
+            for (int e = 0; e < 8; ++e) red[ty * ldred + cv * 8 + e] = v[e];
         }
         __syncthreads();
-        if (threadIdx.x < chunk_ch) {
+        for (int c = warp; c < chunk_ch; c += nwarps) {  // one warp per channel column, lanes stride the rows
             float a = 0.f;
-            for (int r = 0; r < TY; ++r) a += red[r * chunk_ch + threadIdx.x];
-            chsum[threadIdx.x] = a;
+            for (int r = lane; r < TY; r += 32) a += red[r * ldred + c];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+            if (lane == 0) chsum[c] = a;
         }
         __syncthreads();
         if (threadIdx.x < ng) {
@@ -533,7 +539,7 @@ extern "C" int b200sd_group_norm(const void* x0, const void* x1, int32_t c0, int
         const int threads = static_cast<long>(rows_per_cta) * vpr >= 2048 ? 512 : 256;
         const int TY = threads / std::max(1, vpr);
         const size_t csmem = static_cast<size_t>(rows_per_cta) * vpr * 16 +
-                             (static_cast<size_t>(TY) * chunk + chunk + 4 * (chunk / cpg)) * sizeof(float);
+                             (static_cast<size_t>(TY) * (chunk + 1) + chunk + 4 * (chunk / cpg)) * sizeof(float);
         if (mode == 1 && vpr <= 64 && C % chunk == 0 && csmem <= 200 * 1024 && n_img <= 65535 && C / chunk <= 65535) {
             static bool attr = false;
             if (!attr) {
