@@ -93,8 +93,12 @@ class ControlNetModel(B200Model):
     """``controlnet(sample, timestep, encoder_hidden_states, controlnet_cond) -> {"additional_residual_i": ...}``
     (pipeline.py:259-284, torch2coreml.py:1382-1412)."""
 
-    def __init__(self, cfg, state_dict, batch=2, height=64, width=64, seq_len=77, device="cuda", io_dtype=np.float16):
+    def __init__(self, cfg, state_dict, batch=2, height=64, width=64, seq_len=77, device="cuda", io_dtype=np.float16,
+                 use_cuda_graph=True):
         self.engine = ControlNetEngine(cfg, state_dict, device)
+        self.use_cuda_graph = use_cuda_graph
+        self._graph = None
+        self._outs = None
         e = self.engine
         self.batch, self.h, self.w, self.seq = batch, height, width, seq_len
         dt = np.dtype(io_dtype)
@@ -111,12 +115,31 @@ class ControlNetModel(B200Model):
         self._ctx = torch.zeros(spec["encoder_hidden_states"]["shape"], dtype=torch.float16, device=dev)
         self._cond = torch.zeros(spec["controlnet_cond"]["shape"], dtype=torch.float16, device=dev)
 
-    def forward_device(self):
+    def _run(self):
         e = self.engine
         x = L.nchw_to_nhwc(self._sample, c_pad=e.in_pad)
         ctx = L.ctx_to_tokens(self._ctx)
         cond = L.nchw_to_nhwc(self._cond, c_pad=8)
         return e.forward(x, self._t, ctx, self.seq, cond)
+
+    def forward_device(self):
+        """Static input buffers -> list of NHWC fp16 residuals.  With CUDA graphs the list is a set of static
+        tensors owned by the captured graph (overwritten by the next call)."""
+        if not self.use_cuda_graph:
+            return self._run()
+        if self._graph is None:
+            s = torch.cuda.Stream(device=self.device)  # warm-up outside capture: workspace / weight tiling
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                self._run()
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._outs = self._run()
+            self._graph = g
+        self._graph.replay()
+        return self._outs
 
     def __call__(self, **kwargs):
         self._verify_inputs(**kwargs)

@@ -293,7 +293,8 @@ __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + _
 // the GEGLU epilogue evaluates 128 of these per thread per tile and was the bottleneck of those GEMMs.
 __device__ __forceinline__ float erf_as(float x) {
     const float ax = fabsf(x);
-    const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+    float t;  // 1 / (1 + p |x|): MUFU.RCP (1 ulp) -- __frcp_rn would add an IEEE fix-up sequence
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, ax, 1.0f)));
     float poly = fmaf(1.061405429f, t, -1.453152027f);
     poly = fmaf(poly, t, 1.421413741f);
     poly = fmaf(poly, t, -0.284496736f);

@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __half* __restrict_
 __global__ void gn_cluster_kernel(const __half* __restrict__ x0, const __half* __restrict__ x1, int c0, int c1, int hw,
                                   int groups, int chunk_ch, int rows_per_cta, float eps,
                                   const float* __restrict__ gamma, const float* __restrict__ beta, int silu,
-                                  __half* __restrict__ out) {
+                                  __half* __restrict__ out, int fold_mode) {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     const int cs = gridDim.x, rank = blockIdx.x;
@@ -248,29 +248,34 @@ __global__ void gn_cluster_kernel(const __half* __restrict__ x0, const __half* _
 
     extern __shared__ __align__(16) uint8_t csm[];
     uint4* slab = reinterpret_cast<uint4*>(csm);                                   // [rows_per_cta][vpr]
-    float* red = reinterpret_cast<float*>(slab + static_cast<size_t>(rows_per_cta) * vpr);  // [TY][chunk_ch + 1]
-    float* chsum = red + TY * (chunk_ch + 1);                                      // [chunk_ch]
+    float* red = reinterpret_cast<float*>(slab + static_cast<size_t>(rows_per_cta) * vpr);  // [TY][chunk_ch]
+    float* chsum = red + TY * chunk_ch;                                            // [chunk_ch]
     float* xchg = chsum + chunk_ch;                                                // [2][ng]  (read by the peers)
     float* stat = xchg + 2 * ng;                                                   // [2][ng]  mean, rstd
     pdl_wait();
 
-    // fold the threads' per-channel registers: rows -> channels -> groups, then across the cluster.  Row stride
-    // chunk_ch + 1 (odd) keeps the column reads of the second step free of bank conflicts; every sum has a
-    // fixed association order (bitwise reproducible).
-    const int ldred = chunk_ch + 1;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    // fold the threads' per-channel registers: rows -> channels -> groups, then across the cluster
     auto cluster_total = [&](float (&v)[8], int slot) {
         if (active) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) red[ty * ldred + cv * 8 + e] = v[e];
+            for (int e = 0; e < 8; ++e) red[ty * chunk_ch + cv * 8 + e] = v[e];
         }
         __syncthreads();
-        for (int c = warp; c < chunk_ch; c += nwarps) {  // one warp per channel column, lanes stride the rows
-            float a = 0.f;
-            for (int r = lane; r < TY; r += 32) a += red[r * ldred + c];
+        if (fold_mode == 0) {
+            if (threadIdx.x < chunk_ch) {
+                float a = 0.f;
+                for (int r = 0; r < TY; ++r) a += red[r * chunk_ch + threadIdx.x];
+                chsum[threadIdx.x] = a;
+            }
+        } else {  // one warp per channel column, lanes stride the rows, fixed-order butterfly
+            const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+            for (int c = warp; c < chunk_ch; c += nwarps) {
+                float a = 0.f;
+                for (int r = lane; r < TY; r += 32) a += red[r * chunk_ch + c];
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-            if (lane == 0) chsum[c] = a;
+                for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+                if (lane == 0) chsum[c] = a;
+            }
         }
         __syncthreads();
         if (threadIdx.x < ng) {
@@ -527,6 +532,8 @@ extern "C" int b200sd_group_norm(const void* x0, const void* x1, int32_t c0, int
             const char* e = getenv("B200SD_GN_CLUSTER");
             mode = (e && e[0] == '0') ? 0 : 1;
         }
+        const char* fe = getenv("B200SD_GN_FOLD");  // tuning switch: 0 = serial column fold, 1 = warp per column
+        const int fold_mode = (fe && fe[0] == '1') ? 1 : 0;
         const int cpg = C / groups;
         int chunk = cpg;
         while (chunk % 8 != 0) chunk += cpg;                       // lcm(cpg, 8)
@@ -536,10 +543,12 @@ extern "C" int b200sd_group_norm(const void* x0, const void* x1, int32_t c0, int
         int cs = 8;
         while (cs > 1 && (hw / cs < 32 || clusters * cs > 4L * num_sms())) cs >>= 1;
         const int rows_per_cta = (hw + cs - 1) / cs;
-        const int threads = static_cast<long>(rows_per_cta) * vpr >= 2048 ? 512 : 256;
+        const char* te = getenv("B200SD_GN_T512_MIN");  // tuning switch: vectors per CTA from which 512 threads are used
+        const long t512_min = te ? atol(te) : 2048;
+        const int threads = static_cast<long>(rows_per_cta) * vpr >= t512_min ? 512 : 256;
         const int TY = threads / std::max(1, vpr);
         const size_t csmem = static_cast<size_t>(rows_per_cta) * vpr * 16 +
-                             (static_cast<size_t>(TY) * (chunk + 1) + chunk + 4 * (chunk / cpg)) * sizeof(float);
+                             (static_cast<size_t>(TY) * chunk + chunk + 4 * (chunk / cpg)) * sizeof(float);
         if (mode == 1 && vpr <= 64 && C % chunk == 0 && csmem <= 200 * 1024 && n_img <= 65535 && C / chunk <= 65535) {
             static bool attr = false;
             if (!attr) {
@@ -569,7 +578,7 @@ extern "C" int b200sd_group_norm(const void* x0, const void* x1, int32_t c0, int
                                                  reinterpret_cast<const __half*>(x1), static_cast<int>(c0),
                                                  static_cast<int>(c1), static_cast<int>(hw), static_cast<int>(groups), chunk,
                                                  rows_per_cta, eps, gamma, beta, static_cast<int>(silu),
-                                                 reinterpret_cast<__half*>(out)));
+                                                 reinterpret_cast<__half*>(out), fold_mode));
             B200SD_CHECK_CUDA(cudaGetLastError());
             count_launch(1);
             return 0;

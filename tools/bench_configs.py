@@ -69,5 +69,5 @@ ms = time_it(step)
 assert torch.isfinite(unet._out).all()
 out["sd21_controlnet"] = {"ms_per_iter": round(ms, 3), "iter_per_s": round(1e3 / ms, 2),
                           "tflops": round((1.609 + 0.567) / ms * 1e3, 1),
-                          "note": "ControlNet run eagerly (not graph-captured), UNet graph replay"}
+                          "note": "ControlNet and UNet both CUDA-graph replays"}
 print(json.dumps(out))
