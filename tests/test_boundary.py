@@ -28,14 +28,32 @@ def test_library_exports_every_declared_symbol():
     assert isinstance(l.b200sd_last_error(), bytes)
 
 
-def test_struct_layouts_match_header():
-    from b200sd import lib
+def test_struct_layouts_match_header(tmp_path):
+    """sizeof / offsetof of the C-ABI structs as gcc sees include/b200sd.h == the ctypes mirrors in lib.py."""
+    import shutil
+    import subprocess
 
-    # b200sd_gemm_args: 16 int32 (64 B) + 7 pointers + size_t
-    assert ctypes.sizeof(lib.GemmArgs) == 64 + 7 * 8 + 8
-    assert lib.GemmArgs.a0.offset == 64
-    # b200sd_step_coeffs: 13 floats + 4 int32
-    assert ctypes.sizeof(lib.StepCoeffs) == 13 * 4 + 4 * 4
+    from b200sd import lib
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    fields_g = [f[0] for f in lib.GemmArgs._fields_]
+    fields_s = [f[0] for f in lib.StepCoeffs._fields_]
+    src = ['#include <stdio.h>', '#include <stddef.h>', '#include "b200sd.h"', 'int main(void) {',
+           'printf("%zu\\n", sizeof(b200sd_gemm_args));']
+    src += [f'printf("%zu\\n", offsetof(b200sd_gemm_args, {f}));' for f in fields_g]
+    src += ['printf("%zu\\n", sizeof(b200sd_step_coeffs));']
+    src += [f'printf("%zu\\n", offsetof(b200sd_step_coeffs, {f}));' for f in fields_s]
+    src += ['return 0; }']
+    c = tmp_path / "layout.c"
+    c.write_text("\n".join(src))
+    exe = tmp_path / "layout"
+    subprocess.run([gcc, "-I", os.path.join(root, "include"), str(c), "-o", str(exe)], check=True)
+    vals = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    want = [ctypes.sizeof(lib.GemmArgs)] + [getattr(lib.GemmArgs, f).offset for f in fields_g]
+    want += [ctypes.sizeof(lib.StepCoeffs)] + [getattr(lib.StepCoeffs, f).offset for f in fields_s]
+    assert vals == want
 
 
 def test_sass_contains_blackwell_tensor_and_tma_instructions():
