@@ -38,6 +38,8 @@ struct __align__(64) GemmParams {
     int bias_rows, bias_stride, geglu, out_f32;
     int act;         // 0 none, 1 SiLU after bias (generic variant only)
     int cluster;     // split-K on a thread-block cluster: the `splits` CTAs of a tile reduce it through DSMEM
+    int two_cta;     // CTA pairs: one tcgen05.mma cta_group::2 computes two M tiles, each CTA stages half of B
+    int m_pairs;     // ceil(m_tiles / 2)
     int wgt_tiled;   // B operand pre-tiled: tile (n_tile, kb) starts at row (n_tile * kb_total + kb) * block_n
     int bias_mode;   // 0 none, 1 staged in smem (<= 2 vectors per tile), 2 read from global per chunk
     int res_smem;    // 1: residual tile prefetched into smem with cp.async
@@ -52,9 +54,13 @@ struct TileCoord {
     int n0, h0, w0;  // conv: output-space origin of the 128-pixel box
 };
 
-__device__ __forceinline__ TileCoord decode_work(const GemmParams& p, int work) {
+__device__ __forceinline__ TileCoord decode_work(const GemmParams& p, int work, int cta_rank = 0) {
     TileCoord t;
-    if (p.cluster) {  // the CTAs of a cluster (consecutive blockIdx.x) are the k-splits of one tile
+    if (p.two_cta) {  // work = (pair of M tiles, N tile); the two CTAs of the pair take M tiles 2i and 2i + 1
+        t.split = 0;
+        t.m_tile = 2 * (work % p.m_pairs) + cta_rank;  // may be == m_tiles for an odd count: an all-padding tile
+        t.n_tile = work / p.m_pairs;
+    } else if (p.cluster) {  // the CTAs of a cluster (consecutive blockIdx.x) are the k-splits of one tile
         t.split = work % p.splits;
         const int r = work / p.splits;
         t.m_tile = r % p.m_tiles;
@@ -230,11 +236,14 @@ __device__ __forceinline__ float4 ld_dsmem_f4(uint32_t local_addr, uint32_t cta_
     return v;
 }
 
-template <bool kGeneric, bool kGeglu, bool kOutF32, bool kPartial>
+template <bool kGeneric, bool kGeglu, bool kOutF32, bool kPartial, bool kTwoCta = false>
 __global__ void __launch_bounds__(kGemmThreads, 1) umma_gemm_kernel(const __grid_constant__ GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int b_stage = p.block_n * (kBK * 2);
+    // a CTA of a pair stages only its half of the B tile (block_n / 2 rows); the MMA reads both halves
+    const int b_rows = kTwoCta ? (p.block_n >> 1) : p.block_n;
+    const int b_stage = b_rows * (kBK * 2);
+    const int cta_rank = kTwoCta ? static_cast<int>(cluster_ctarank()) : 0;
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + p.stages * kAStage;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b + p.stages * b_stage);
@@ -259,23 +268,31 @@ __global__ void __launch_bounds__(kGemmThreads, 1) umma_gemm_kernel(const __grid
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tmem_full[s], 1);
-            mbar_init(&tmem_empty[s], kEpiThreads);
+            mbar_init(&tmem_empty[s], kTwoCta ? 2 * kEpiThreads : kEpiThreads);  // pair: both CTAs' epilogues
         }
         fence_barrier_init();
     }
     if (warp == 1) {
-        tmem_alloc(tmem_ptr, 512);
-        tmem_relinquish();
+        if (kTwoCta) {
+            tmem_alloc_pair(tmem_ptr, 512);
+            tmem_relinquish_pair();
+        } else {
+            tmem_alloc(tmem_ptr, 512);
+            tmem_relinquish();
+        }
     }
     tc_fence_before();
     __syncthreads();
+    if (kTwoCta) cluster_arrive_wait();  // the peer's barriers are initialised before anything signals them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
     // PDL: everything above overlapped the previous kernel's tail; from here on we touch its outputs
     pdl_wait();
     pdl_trigger();
 
-    const int total_work = p.m_tiles * p.n_tiles * p.splits;
+    const int total_work = kTwoCta ? p.m_pairs * p.n_tiles : p.m_tiles * p.n_tiles * p.splits;
+    const int work0 = kTwoCta ? (blockIdx.x >> 1) : blockIdx.x;
+    const int work_step = kTwoCta ? (gridDim.x >> 1) : gridDim.x;
 
     if (warp == 0) {
         // ------------------------------- TMA producer -------------------------------
@@ -283,13 +300,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) umma_gemm_kernel(const __grid
             int stage = 0;
             uint32_t phase = 0;
             const uint32_t tx_bytes = kAStage + b_stage;
-            for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
-                const TileCoord t = decode_work(p, work);
+            for (int work = work0; work < total_work; work += work_step) {
+                const TileCoord t = decode_work(p, work, cta_rank);
                 int kb0, kb1;
                 split_range(p, t.split, kb0, kb1);
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
-                    mbar_expect_tx(&full_bar[stage], tx_bytes);
                     const int tap = kb / p.kc;
                     const int j = kb - tap * p.kc;
                     const bool src1 = j >= p.kc0;
@@ -297,19 +313,34 @@ __global__ void __launch_bounds__(kGemmThreads, 1) umma_gemm_kernel(const __grid
                     const int wk = tap * p.Kpt + (src1 ? p.C0 : 0) + c;
                     const CUtensorMap* tmA = src1 ? &p.tmA1 : &p.tmA0;
                     void* dst_a = smem_a + stage * kAStage;
-                    if (p.mode == 0) {
-                        tma_load_2d(dst_a, tmA, &full_bar[stage], c, t.m_tile * kBM, kEvictNormal);
+                    void* dst_b = smem_b + stage * b_stage;
+                    const int brow = p.wgt_tiled ? (t.n_tile * p.kb_total + kb) * p.block_n + cta_rank * b_rows
+                                                 : t.n_tile * p.block_n + cta_rank * b_rows;
+                    if (kTwoCta) {
+                        // both CTAs' loads are credited to the leader's full barrier: it sees 2 x tx_bytes per stage
+                        if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * tx_bytes);
+                        const uint32_t fb = mapa_u32(smem_u32(&full_bar[stage]), 0);
+                        if (p.mode == 0) {
+                            tma_load_2d_pair(dst_a, tmA, fb, c, t.m_tile * kBM, kEvictNormal);
+                        } else {
+                            const int r = tap / 3, s3 = tap - 3 * r;
+                            tma_load_4d_pair(dst_a, tmA, fb, c, t.w0 * p.stride + s3 - 1, t.h0 * p.stride + r - 1, t.n0,
+                                             kEvictNormal);
+                        }
+                        tma_load_2d_pair(dst_b, &p.tmB, fb, p.wgt_tiled ? 0 : wk, brow,
+                                         p.wgt_tiled ? kEvictFirst : kEvictLast);
                     } else {
-                        const int r = tap / 3, s = tap - 3 * r;
-                        tma_load_4d(dst_a, tmA, &full_bar[stage], c, t.w0 * p.stride + s - 1,
-                                    t.h0 * p.stride + r - 1, t.n0, kEvictNormal);
+                        mbar_expect_tx(&full_bar[stage], tx_bytes);
+                        if (p.mode == 0) {
+                            tma_load_2d(dst_a, tmA, &full_bar[stage], c, t.m_tile * kBM, kEvictNormal);
+                        } else {
+                            const int r = tap / 3, s3 = tap - 3 * r;
+                            tma_load_4d(dst_a, tmA, &full_bar[stage], c, t.w0 * p.stride + s3 - 1,
+                                        t.h0 * p.stride + r - 1, t.n0, kEvictNormal);
+                        }
+                        tma_load_2d(dst_b, &p.tmB, &full_bar[stage], p.wgt_tiled ? 0 : wk, brow,
+                                    p.wgt_tiled ? kEvictFirst : kEvictLast);
                     }
-                    if (p.wgt_tiled)
-                        tma_load_2d(smem_b + stage * b_stage, &p.tmB, &full_bar[stage], 0,
-                                    (t.n_tile * p.kb_total + kb) * p.block_n, kEvictFirst);
-                    else
-                        tma_load_2d(smem_b + stage * b_stage, &p.tmB, &full_bar[stage], wk, t.n_tile * p.block_n,
-                                    kEvictLast);
                     if (++stage == p.stages) {
                         stage = 0;
                         phase ^= 1;
@@ -319,37 +350,48 @@ __global__ void __launch_bounds__(kGemmThreads, 1) umma_gemm_kernel(const __grid
         }
     } else if (warp == 1) {
         // ------------------------------- MMA issuer ---------------------------------
-        const uint32_t idesc = make_idesc_f16(kBM, p.block_n, 0, 0);
+        // a pair issues M = 256 (128 rows from each CTA) from the leader only; the peer's MMA warp idles
+        const uint32_t idesc = make_idesc_f16(kTwoCta ? 2 * kBM : kBM, p.block_n, 0, 0);
         int stage = 0;
         uint32_t phase = 0;
         int iter = 0;
-        for (int work = blockIdx.x; work < total_work; work += gridDim.x, ++iter) {
-            const TileCoord t = decode_work(p, work);
-            int kb0, kb1;
-            split_range(p, t.split, kb0, kb1);
-            const int as = iter & 1;
-            const uint32_t aphase = (iter >> 1) & 1;
-            mbar_wait(&tmem_empty[as], aphase ^ 1);
-            tc_fence_after();
-            const uint32_t tmem_d = tmem_base + as * 256;
-            for (int kb = kb0; kb < kb1; ++kb) {
-                mbar_wait(&full_bar[stage], phase);
+        if (!kTwoCta || cta_rank == 0) {
+            for (int work = work0; work < total_work; work += work_step, ++iter) {
+                const TileCoord t = decode_work(p, work, cta_rank);
+                int kb0, kb1;
+                split_range(p, t.split, kb0, kb1);
+                const int as = iter & 1;
+                const uint32_t aphase = (iter >> 1) & 1;
+                mbar_wait(&tmem_empty[as], aphase ^ 1);
                 tc_fence_after();
-                if (lane == 0) {
-                    const uint64_t adesc = make_smem_desc_sw128(smem_u32(smem_a + stage * kAStage), 1024, 0);
-                    const uint64_t bdesc = make_smem_desc_sw128(smem_u32(smem_b + stage * b_stage), 1024, 0);
+                const uint32_t tmem_d = tmem_base + as * 256;
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    if (lane == 0) {
+                        const uint64_t adesc = make_smem_desc_sw128(smem_u32(smem_a + stage * kAStage), 1024, 0);
+                        const uint64_t bdesc = make_smem_desc_sw128(smem_u32(smem_b + stage * b_stage), 1024, 0);
 #pragma unroll
-                    for (int k = 0; k < kBK / 16; ++k) {
-                        // +32 B per K=16 step inside the 128 B swizzle row (start address is in 16 B units)
-                        umma_f16_ss(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                        for (int k = 0; k < kBK / 16; ++k) {
+                            // +32 B per K=16 step inside the 128 B swizzle row (start address is in 16 B units)
+                            if (kTwoCta)
+                                umma_f16_ss_pair(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                            else
+                                umma_f16_ss(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                        }
+                        if (kTwoCta) {  // release the stage / publish the accumulator in both CTAs
+                            umma_commit_pair(&empty_bar[stage], 3);
+                            if (kb == kb1 - 1) umma_commit_pair(&tmem_full[as], 3);
+                        } else {
+                            umma_commit(&empty_bar[stage]);
+                            if (kb == kb1 - 1) umma_commit(&tmem_full[as]);
+                        }
                     }
-                    umma_commit(&empty_bar[stage]);
-                    if (kb == kb1 - 1) umma_commit(&tmem_full[as]);
-                }
-                __syncwarp();
-                if (++stage == p.stages) {
-                    stage = 0;
-                    phase ^= 1;
+                    __syncwarp();
+                    if (++stage == p.stages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
                 }
             }
         }
@@ -360,8 +402,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) umma_gemm_kernel(const __grid
         const int row = lane_group * 32 + lane;
         const int tid_e = threadIdx.x - 64;  // 0..255 among the epilogue warps
         int iter = 0;
-        for (int work = blockIdx.x; work < total_work; work += gridDim.x, ++iter) {
-            const TileCoord t = decode_work(p, work);
+        for (int work = work0; work < total_work; work += work_step, ++iter) {
+            const TileCoord t = decode_work(p, work, cta_rank);
             const int as = iter & 1;
             const uint32_t aphase = (iter >> 1) & 1;
             const int ncol0 = t.n_tile * p.block_n;
@@ -465,7 +507,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) umma_gemm_kernel(const __grid
                 }
             }
             tc_fence_before();
-            mbar_arrive(&tmem_empty[as]);
+            if (kTwoCta) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[as]), 0));  // the leader's MMA warp waits
+            else mbar_arrive(&tmem_empty[as]);
         }
     }
 
@@ -520,9 +563,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) umma_gemm_kernel(const __grid
 
     tc_fence_before();
     __syncthreads();
+    if (kTwoCta) cluster_arrive_wait();  // the pair retires together: remote barrier arrivals, peer smem / TMEM reads
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 512);
+        if (kTwoCta) tmem_dealloc_pair(tmem_base, 512);
+        else tmem_dealloc(tmem_base, 512);
     }
 }
 
@@ -572,12 +617,20 @@ struct GemmPlan {
     int Hout, Wout, bw, bh, bn_img, tiles_w, tiles_h, tiles_n;
     int bias_mode, res_smem, epi_smem;
     int cluster;  // split-K reduced inside a thread-block cluster of `splits` CTAs (DSMEM) instead of a second kernel
+    int two_cta;  // CTA pairs (tcgen05.mma cta_group::2, M = 256): each CTA stages half of the B tile
 };
 
 static bool cluster_splitk_enabled() {
     // B200SD_CLUSTER_SPLITK=0: always take the workspace + reduce-kernel path (read per call: tuning scripts flip it)
     const char* e = getenv("B200SD_CLUSTER_SPLITK");
     return !(e && e[0] == '0');
+}
+
+static bool two_cta_enabled() {
+    // opt-in (B200SD_2CTA=1, read per call: tuning scripts flip it).  Correct on every parity test, but measured
+    // 2 % slower end to end than single-CTA tiles on the SD-2.1 UNet (199.2 vs 203.5 iter/s): see profiles/README.md
+    const char* e = getenv("B200SD_2CTA");
+    return e && e[0] == '1';
 }
 
 static int ilog2(int v) {
@@ -706,7 +759,13 @@ static int plan_gemm(const b200sd_gemm_args& a, GemmPlan& pl) {
         }
         if (a.residual != nullptr && !a.geglu && a.n % 8 == 0) pl.res_smem = 1;
     }
-    const int per_stage = kAStage + pl.block_n * kBK * 2;
+    // ---- CTA pairs: two M tiles share one B tile (each CTA loads half of it), which halves the L2 -> SM operand
+    // traffic per flop of B -- the limiter of these GEMMs (~42 B/clk/SM of L2 bandwidth vs 48 KiB per k-block) ----
+    const bool regular = (a.act == 0) && (a.n % 16 == 0) && ((a.geglu ? a.n / 2 : a.n) % 8 == 0) && (pl.block_n % 32 == 0) &&
+                         pl.bias_mode != 2 && (a.residual == nullptr || pl.res_smem);
+    pl.two_cta = (two_cta_enabled() && pl.splits == 1 && regular && pl.m_tiles >= 2 &&
+                  static_cast<long>((pl.m_tiles + 1) / 2) * pl.n_tiles * 2 >= num_sms() / 2) ? 1 : 0;
+    const int per_stage = kAStage + (pl.two_cta ? pl.block_n / 2 : pl.block_n) * kBK * 2;
     pl.epi_smem = 2 * 256 * 4 + (pl.res_smem ? kBM * (pl.block_n + 8) * 2 : 0);
     pl.stages = std::max(2, std::min(kMaxStages, (kSmemBudget - pl.epi_smem) / per_stage));
     return 0;
@@ -769,13 +828,13 @@ static int launch_gemm(const b200sd_gemm_args& a, cudaStream_t stream) {
         const uint64_t rows = static_cast<uint64_t>(pl.n_tiles) * pl.kb_total * pl.block_n;
         const uint64_t dims[2] = {kBK, rows};
         const uint64_t str[1] = {kBK * 2};
-        const uint32_t box[2] = {kBK, static_cast<uint32_t>(pl.block_n)};
+        const uint32_t box[2] = {kBK, static_cast<uint32_t>(pl.two_cta ? pl.block_n / 2 : pl.block_n)};
         if (int rc = encode_tmap_f16(&p.tmB, a.wgt, 2, dims, str, box, es1)) return rc;
     } else {
         const uint64_t ktot = static_cast<uint64_t>(pl.taps) * pl.Kpt;
         const uint64_t dims[2] = {ktot, static_cast<uint64_t>(a.n)};
         const uint64_t str[1] = {ktot * 2};
-        const uint32_t box[2] = {kBK, static_cast<uint32_t>(pl.block_n)};
+        const uint32_t box[2] = {kBK, static_cast<uint32_t>(pl.two_cta ? pl.block_n / 2 : pl.block_n)};
         if (int rc = encode_tmap_f16(&p.tmB, a.wgt, 2, dims, str, box, es1)) return rc;
     }
     p.mode = a.mode;
@@ -815,8 +874,10 @@ static int launch_gemm(const b200sd_gemm_args& a, cudaStream_t stream) {
     p.residual = reinterpret_cast<const __half*>(a.residual);
     p.partial = (pl.splits > 1 && !pl.cluster) ? a.workspace : nullptr;
     p.cluster = pl.cluster;
+    p.two_cta = pl.two_cta;
+    p.m_pairs = (pl.m_tiles + 1) / 2;
 
-    const int smem_bytes = pl.stages * (kAStage + pl.block_n * kBK * 2) + (2 * kMaxStages + 4) * 8 + 16 + pl.epi_smem + 1024;
+    const int smem_bytes = pl.stages * (kAStage + (pl.two_cta ? pl.block_n / 2 : pl.block_n) * kBK * 2) + (2 * kMaxStages + 4) * 8 + 16 + pl.epi_smem + 1024;
     const int total = pl.m_tiles * pl.n_tiles * pl.splits;
     const int grid = std::min(total, num_sms());
     // compile-time epilogue variants for the hot shapes; anything irregular takes the generic kernel
@@ -831,33 +892,39 @@ static int launch_gemm(const b200sd_gemm_args& a, cudaStream_t stream) {
     } else if (pl.splits > 1) {
         fn = umma_gemm_kernel<false, false, false, true>, variant = 1;
     } else if (a.geglu) {
-        fn = umma_gemm_kernel<false, true, false, false>, variant = 2;
+        fn = pl.two_cta ? umma_gemm_kernel<false, true, false, false, true> : umma_gemm_kernel<false, true, false, false>;
+        variant = pl.two_cta ? 5 : 2;
     } else if (a.out_f32) {
-        fn = umma_gemm_kernel<false, false, true, false>, variant = 3;
+        fn = pl.two_cta ? umma_gemm_kernel<false, false, true, false, true> : umma_gemm_kernel<false, false, true, false>;
+        variant = pl.two_cta ? 6 : 3;
     } else {
-        fn = umma_gemm_kernel<false, false, false, false>, variant = 4;
+        fn = pl.two_cta ? umma_gemm_kernel<false, false, false, false, true> : umma_gemm_kernel<false, false, false, false>;
+        variant = pl.two_cta ? 7 : 4;
     }
+    B200SD_REQUIRE(!pl.two_cta || variant >= 5, "b200sd_gemm: CTA pairs need a regular single-split epilogue variant");
     if (pl.splits > 1 && !pl.cluster) {
         // the separate reduce kernel applies bias / residual; the partial writer must not
         p.bias = nullptr;
         p.residual = nullptr;
     }
-    static bool attr_set[5] = {false, false, false, false, false};
+    static bool attr_set[8] = {false, false, false, false, false, false, false, false};
     if (!attr_set[variant]) {
         B200SD_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set[variant] = true;
     }
-    if (pl.cluster) {
-        B200SD_REQUIRE(variant == 1, "b200sd_gemm: cluster split-K needs the regular epilogue variant");
+    if (pl.cluster || pl.two_cta) {
+        B200SD_REQUIRE(pl.two_cta || variant == 1, "b200sd_gemm: cluster split-K needs the regular epilogue variant");
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof(cfg));
-        cfg.gridDim = dim3(total);  // one (tile, split) per CTA; the splits of a tile are one cluster
+        // split-K: one (tile, split) per CTA, the splits of a tile are one cluster;  pairs: persistent clusters of 2
+        const int pair_units = ((pl.m_tiles + 1) / 2) * pl.n_tiles;
+        cfg.gridDim = pl.two_cta ? dim3(2 * std::min(pair_units, num_sms() / 2)) : dim3(total);
         cfg.blockDim = dim3(kGemmThreads);
         cfg.dynamicSmemBytes = smem_bytes;
         cfg.stream = stream;
         cudaLaunchAttribute at[2];
         at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = pl.splits;
+        at[0].val.clusterDim.x = pl.two_cta ? 2 : pl.splits;
         at[0].val.clusterDim.y = 1;
         at[0].val.clusterDim.z = 1;
         cfg.attrs = at;
@@ -911,9 +978,9 @@ extern "C" int b200sd_gemm_describe_plan(const b200sd_gemm_args* args, char* buf
     if (int rc = b200sd::plan_gemm(*args, pl)) return rc;
     snprintf(buf, buf_size,
              "M=%d N=%d kb_total=%d m_tiles=%d n_tiles=%d block_n=%d splits=%d kb_per_split=%d stages=%d "
-             "box=%dx%dx%d bias_mode=%d res_smem=%d epi_smem=%d cluster=%d",
+             "box=%dx%dx%d bias_mode=%d res_smem=%d epi_smem=%d cluster=%d two_cta=%d",
              pl.M, pl.N, pl.kb_total, pl.m_tiles, pl.n_tiles, pl.block_n, pl.splits, pl.kb_per_split, pl.stages,
-             pl.bn_img, pl.bh, pl.bw, pl.bias_mode, pl.res_smem, pl.epi_smem, pl.cluster);
+             pl.bn_img, pl.bh, pl.bw, pl.bias_mode, pl.res_smem, pl.epi_smem, pl.cluster, pl.two_cta);
     return 0;
 }
 

@@ -124,6 +124,29 @@ def test_conv3x3_split_k_cluster_temb_residual(cuda_lib):
         _close(out, ref, 4e-3, 3e-3, f"conv cluster split-K {split}")
 
 
+def test_gemm_cta_pairs(cuda_lib, monkeypatch):
+    """tcgen05.mma cta_group::2 path (opt-in): M = 256 per CTA pair, each CTA stages half of the B tile; linear with
+    bias + residual, GEGLU, conv with per-image bias, odd number of M tiles (the last pair has a padding tile)."""
+    monkeypatch.setenv("B200SD_2CTA", "1")
+    m, n, k = 8192 + 128, 320, 640  # 65 M tiles -> 33 pairs
+    x, w, r = _rand(m, k, seed=1), _rand(n, k, scale=k ** -0.5, seed=2), _rand(m, n, seed=3)
+    b = torch.randn(n, device="cuda")
+    assert "two_cta=1" in cuda_lib.describe_plan(0, m=m, n=n, c0=k, has_residual=True)
+    _close(cuda_lib.linear(x, w, b, r), x.float() @ w.float().t() + b + r.float(), 3e-3, 2e-3, "pair linear")
+    w2 = _rand(1280, 320, scale=320 ** -0.5, seed=4)
+    x2 = _rand(4096, 320, seed=5)
+    b2 = torch.randn(1280, device="cuda")
+    y = x2.float() @ w2.float().t() + b2
+    ref = y[:, 0::2] * F.gelu(y[:, 1::2])
+    _close(cuda_lib.linear(x2, w2, b2, geglu=True), ref, 4e-3, 3e-3, "pair GEGLU")
+    xc = _rand(2, 64, 64, 64, seed=6)
+    wc = _rand(128, 64, 3, 3, scale=576 ** -0.5, seed=7)
+    bi = torch.randn(2, 128, device="cuda")
+    assert "two_cta=1" in cuda_lib.describe_plan(1, n=128, c0=64, n_img=2, h=64, w=64, bias_rows=4096)
+    out = cuda_lib.conv3x3(xc, _pack(wc), bi, bias_rows=4096)
+    _close(out, _conv_ref(xc, wc) + bi[:, None, None, :], 3e-3, 3e-3, "pair conv")
+
+
 def test_conv3x3_small_channels(cuda_lib):
     # conv_in: 4 channels padded to 8; conv_out: 4 output channels, fp32 out
     x = _rand(2, 64, 64, 8, seed=1)
