@@ -55,7 +55,9 @@ uint64_t b200sd_launch_count(void);
  *             ; GEGLU a*gelu_erf(g) on interleaved column pairs (unet.py:616-617), output N/2 cols
  *             ; + residual[row, col] (unet.py:484-487, :563, :587-589)
  *             ; store fp16 or fp32.
- *   split_k > 1 accumulates fp32 partials in `workspace` and finishes with a reduce kernel.
+ *   split_k > 1: the k-splits of a tile run as one thread-block cluster (2 / 4 / 8 CTAs) and reduce their fp32
+ *   tiles through distributed shared memory; other split counts accumulate fp32 partials in `workspace` and
+ *   finish with a reduce kernel (b200sd_gemm_workspace_bytes() says how much scratch a call needs, 0 = none).
  */
 typedef struct {
     int32_t mode;          /* 0 linear, 1 conv3x3 */
@@ -79,7 +81,7 @@ typedef struct {
     const float* bias;     /* or NULL */
     const void* residual;  /* fp16 [M, N_out] or NULL */
     void* out;             /* [M, N_out] fp16 / fp32 */
-    float* workspace;      /* split-K scratch (may be NULL when split_k == 1) */
+    float* workspace;      /* split-K scratch (may be NULL when b200sd_gemm_workspace_bytes() == 0) */
     size_t workspace_bytes;
 } b200sd_gemm_args;
 
@@ -107,7 +109,9 @@ int b200sd_timestep_embedding(const float* timesteps, float* out, int32_t m, int
  * GroupNorm (torch.nn.GroupNorm, unet.py:430,448,528,966) on NHWC fp16, fp32 statistics, optional
  * fused SiLU (unet.py:472-473,480-481), reading one or two channel-concatenated sources and writing
  * the concatenated normalised tensor (the torch.cat of unet.py:215,270 never materialises raw).
- * Two launches: partial (mean, M2) per (image, group, chunk), then apply (Chan merge in prologue). */
+ * One launch on thread-block clusters: a cluster owns one (image, channel chunk), keeps its pixels in shared
+ * memory, computes exact two-pass statistics exchanged through DSMEM and normalises from the slab.  Tensors too
+ * large for that (slab > 200 KB per CTA) take two launches (chunk partials in `stats_ws`, then apply). */
 int b200sd_group_norm(const void* x0, const void* x1, int32_t c0, int32_t c1, int32_t n_img, int32_t hw,
                       int32_t groups, float eps, const float* gamma, const float* beta, int32_t silu,
                       void* out, float* stats_ws, size_t stats_ws_bytes, void* stream);
