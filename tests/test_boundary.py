@@ -122,3 +122,37 @@ def test_synthetic_text_path_shapes():
     out = SyntheticTextEncoder(1024)(input_ids=ids)["last_hidden_state"]
     assert out.shape == (1, 77, 1024)
     assert np.array_equal(out, SyntheticTextEncoder(1024)(input_ids=ids)["last_hidden_state"])
+
+
+def test_gemm_planner_invariants_over_unet_shapes():
+    """Host-only: the tiling plan for every conv / linear shape class of SD-2.1-base and SDXL-base (batch 2)
+    satisfies the constraints the kernels rely on (no GPU needed: b200sd_gemm_describe_plan)."""
+    import re
+
+    from b200sd import lib
+
+    shapes = []
+    for hw, chans in ((64, (320, 640, 960)), (32, (320, 640, 960, 1280, 1920)), (16, (640, 1280, 1920, 2560)),
+                      (8, (1280, 2560)), (96, (320, 640, 960)), (48, (320, 640, 1280, 1920)), (24, (640, 1280, 2560))):
+        for cin in chans:
+            for cout in (320, 640, 1280):
+                shapes.append(dict(mode=1, n=cout, c0=cin, n_img=2, h=hw, w=hw, bias_rows=hw * hw))
+                shapes.append(dict(mode=1, n=cout, c0=cin, n_img=2, h=hw, w=hw, has_residual=True))
+        for c in (320, 640, 1280):
+            m = 2 * hw * hw
+            shapes += [dict(mode=0, m=m, n=3 * c, c0=c, has_bias=False), dict(mode=0, m=m, n=c, c0=c, has_residual=True),
+                       dict(mode=0, m=m, n=8 * c, c0=c, geglu=True), dict(mode=0, m=m, n=c, c0=4 * c, has_residual=True)]
+    shapes += [dict(mode=0, m=154, n=2560, c0=1024, has_bias=False), dict(mode=0, m=154, n=640, c0=2048, has_bias=False)]
+    for kw in shapes:
+        plan = lib.describe_plan(**kw)
+        f = {k: int(v) for k, v in re.findall(r"(\w+)=(-?\d+)(?:\s|$)", plan)}
+        bn, splits, stages, kb = f["block_n"], f["splits"], f["stages"], f["kb_total"]
+        assert bn % 16 == 0 and 16 <= bn <= 256 and 2 <= stages <= 8, plan
+        assert f["n_tiles"] * bn >= f["N"] and (f["n_tiles"] - 1) * bn < f["N"], plan
+        assert 1 <= splits <= kb, plan
+        if kw.get("geglu"):
+            assert splits == 1, plan
+        per_stage = 16384 + (bn // 2 if f["two_cta"] else bn) * 128
+        assert stages * per_stage + f["epi_smem"] <= 220 * 1024, plan
+        if f["cluster"]:
+            assert splits in (2, 4, 8) and bn % 32 == 0 and 512 * (bn + 4) <= stages * per_stage, plan
