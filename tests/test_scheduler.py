@@ -114,3 +114,22 @@ def test_pndm_matches_oracle(n):
 def test_unknown_scheduler():
     with pytest.raises(ValueError):
         S.make_scheduler("Euler", 20)
+
+
+def test_prepare_latents_follows_the_reference_rng_vector():
+    """The reference seeds numpy globally and draws the initial latents with np.random.randn (pipeline.py:322-344,
+    main :735); its Swift twin pins that stream with a known-answer test (StableDiffusionTests.swift:46-61:
+    seed 12345, last five of 10 000 normals).  prepare_latents must consume the same stream in the same order."""
+    import types
+
+    from b200sd.pipeline import B200StableDiffusionPipeline
+
+    stub = types.SimpleNamespace(vae_scale_factor=8)
+    np.random.seed(12345)
+    lat = B200StableDiffusionPipeline.prepare_latents(stub, 1, 4, 400, 400)  # 4 * 50 * 50 = 10 000 draws
+    assert lat.shape == (1, 4, 50, 50) and lat.dtype == np.float32
+    expected = np.array([-0.86285345, 2.15229409, -0.00670556, -1.21472309, 0.65498866])
+    got = lat.reshape(-1)[-5:]
+    assert np.allclose(got, expected.astype(np.float16).astype(np.float32), atol=0, rtol=0), got
+    with pytest.raises(ValueError, match="Unexpected latents shape"):
+        B200StableDiffusionPipeline.prepare_latents(stub, 1, 4, 400, 400, latents=np.zeros((1, 4, 8, 8)))
