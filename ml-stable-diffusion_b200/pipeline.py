@@ -69,8 +69,10 @@ class B200StableDiffusionPipeline:
     """Drop-in for ``CoreMLStableDiffusionPipeline`` on one B200."""
 
     def __init__(self, unet: UNetModel, vae_decoder: VAEDecoderModel, scheduler="DDIM", text_encoder=None,
-                 tokenizer=None, force_zeros_for_empty_prompt=True, xl=False, controlnet=None):
+                 tokenizer=None, force_zeros_for_empty_prompt=True, xl=False, controlnet=None, loop_graph=True):
         self.unet = unet
+        self.loop_graph = bool(loop_graph) and unet.use_cuda_graph  # whole-loop CUDA graph (denoise())
+        self._loop_graphs = {}
         self.controlnet = list(controlnet) if controlnet else None  # pipeline.py:66,106: Optional[List[model]]
         if self.controlnet and not unet.engine.support_controlnet:
             raise ValueError("the UNet was not built with support_controlnet=True (no additional_residual inputs)")
@@ -196,34 +198,86 @@ class B200StableDiffusionPipeline:
         return [Image.fromarray(im) for im in images]
 
     # ---------------------------------------------------------------- device loop
+    @staticmethod
+    def _coeffs(st, guidance_scale, k=None):
+        k = k or L.StepCoeffs()
+        k.guidance = float(guidance_scale)
+        k.cx, k.ce, k.x0_cx, k.x0_ce = st.cx, st.ce, st.x0_cx, st.x0_ce
+        for j in range(4):
+            k.ch[j] = st.ch[j]
+            k.x0_ch[j] = st.x0_ch[j]
+        k.n_hist, k.push_eps_slot, k.push_x0_slot, k.push_x_slot = (st.n_hist, st.push_eps_slot,
+                                                                    st.push_x0_slot, st.push_x_slot)
+        return k
+
+    def _loop_on_static_buffers(self, plan, guidance_scale):
+        """The whole N-step loop on the UNet's static input buffers (no host-side tensor arguments): what the
+        loop graph captures.  Per step: timestep fill, latents -> both CFG halves of `sample`, the UNet launch
+        sequence, one fused CFG + scheduler kernel (its coefficients are baked into the launch)."""
+        u, n = self.unet, self.images_per_call
+        self._hist.zero_()
+        for st in plan:
+            u._t.fill_(float(st.timestep))
+            u._sample[:n].copy_(self._latents)   # pipeline.py:502 np.concatenate([latents] * 2)
+            u._sample[n:].copy_(self._latents)
+            u._run()
+            L.cfg_scheduler_step(u._out, self._latents, self._coeffs(st, guidance_scale), hist=self._hist,
+                                 denoised=self._denoised)
+
+    def _loop_graph_for(self, key, plan, guidance_scale):
+        g = self._loop_graphs.get(key)
+        if g is None:
+            keep = self._latents.clone()
+            s = torch.cuda.Stream(device=self.device)  # eager warm-up off the capture: workspaces, weight tiling
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                self._loop_on_static_buffers(plan[:1], guidance_scale)
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            self._latents.copy_(keep)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._loop_on_static_buffers(plan, guidance_scale)
+            self._latents.copy_(keep)  # capture does not execute, but keep the contract obvious
+            if len(self._loop_graphs) >= 4:
+                self._loop_graphs.pop(next(iter(self._loop_graphs)))
+            self._loop_graphs[key] = g
+        return g
+
     def denoise(self, text_embeddings, latents, num_inference_steps, guidance_scale, callback=None,
                 callback_steps=1, time_ids=None, text_embeds=None, return_denoised=False, record=None,
                 controlnet_cond=None):
         """Runs the N-step loop entirely on the device.  ``text_embeddings`` (2B, D, 1, S) and ``latents``
         (B, C, h, w) may be numpy (copied once, before the loop) or CUDA tensors.  ``record`` (a list) receives
-        (timestep, noise_pred, latents_after_step) clones per step -- a debugging / testing aid."""
+        (timestep, noise_pred, latents_after_step) clones per step -- a debugging / testing aid.  Without
+        callback / record / ControlNet the whole loop replays as ONE CUDA graph: the scheduler
+        history lives on the device and no host synchronisation happens between the first and the last step."""
         sched = S.make_scheduler(self.scheduler_name, num_inference_steps)
+        plan = list(sched.plan())
         n = self.images_per_call
         self._ctx.copy_(torch.as_tensor(text_embeddings), non_blocking=True)
         self._latents.copy_(torch.as_tensor(latents), non_blocking=True)
-        self._hist.zero_()
         if controlnet_cond:
             controlnet_cond = [torch.as_tensor(c).to(self.device, torch.float16) for c in controlnet_cond]
+        if self.loop_graph and callback is None and record is None and not controlnet_cond:
+            u = self.unet
+            u._ctx.copy_(self._ctx)
+            if u.engine.xl:
+                u._time_ids.copy_(torch.as_tensor(time_ids).reshape(u._time_ids.shape))
+                u._text_embeds.copy_(torch.as_tensor(text_embeds))
+            key = (self.scheduler_name, int(num_inference_steps), float(guidance_scale))
+            self._loop_graph_for(key, plan, guidance_scale).replay()
+            return self._denoised if return_denoised else self._latents
+        self._hist.zero_()
         k = L.StepCoeffs()
-        for i, st in enumerate(sched.plan()):
+        for i, st in enumerate(plan):
             self._t.fill_(float(st.timestep))
             sample = torch.cat([self._latents, self._latents], 0)  # pipeline.py:502
             residuals = None
             if controlnet_cond:  # pipeline.py:515-529
                 residuals = self.run_controlnet(sample, self._t, self._ctx, controlnet_cond)
             noise_pred = self.unet.forward_device(sample, self._t, self._ctx, time_ids, text_embeds, residuals)
-            k.guidance = float(guidance_scale)
-            k.cx, k.ce, k.x0_cx, k.x0_ce = st.cx, st.ce, st.x0_cx, st.x0_ce
-            for j in range(4):
-                k.ch[j] = st.ch[j]
-                k.x0_ch[j] = st.x0_ch[j]
-            k.n_hist, k.push_eps_slot, k.push_x0_slot, k.push_x_slot = (st.n_hist, st.push_eps_slot,
-                                                                        st.push_x0_slot, st.push_x_slot)
+            self._coeffs(st, guidance_scale, k)
             if record is not None:
                 eps_copy = noise_pred.clone()
             L.cfg_scheduler_step(noise_pred, self._latents, k, hist=self._hist, denoised=self._denoised)

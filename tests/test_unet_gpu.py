@@ -156,6 +156,16 @@ def test_pipeline_tiny_end_to_end_vs_oracle(cuda_lib):
     err = float(np.abs(img - ref).max())
     print(f"pipeline tiny: image max_abs={err:.3e}")
     assert err < 3e-2
+    # the call above replayed the whole loop as one CUDA graph; the step-by-step path must agree bit for bit
+    assert pipe.loop_graph and len(pipe._loop_graphs) == 1
+    pipe.loop_graph = False
+    img2 = pipe("a photo of an astronaut riding a horse", height=64, width=64, num_inference_steps=steps,
+                guidance_scale=g, latents=lat0, output_type="np").images
+    pipe.loop_graph = True
+    assert np.array_equal(img, img2), float(np.abs(img - img2).max())
+    img3 = pipe("a photo of an astronaut riding a horse", height=64, width=64, num_inference_steps=steps,
+                guidance_scale=g, latents=lat0, output_type="np").images  # second replay of the cached graph
+    assert np.array_equal(img, img3)
     # PIL output + generate() alias + return_dict=False
     out = pipe.generate("x", num_inference_steps=2, guidance_scale=7.5, height=64, width=64, return_dict=False)
     assert out[1] is None and out[0][0].size == (64, 64)
