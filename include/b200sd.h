@@ -72,7 +72,8 @@ typedef struct {
     int32_t bias_stride;   /* elements between consecutive bias vectors (0 = n) */
     int32_t split_k;       /* 0 = auto */
     int32_t block_n;       /* 0 = auto; else multiple of 16 in [16, 256] */
-    int32_t act;           /* 0 none; 1 SiLU after the bias (ControlNet conditioning embedder, controlnet.py:36-44) */
+    int32_t act;           /* after the bias: 0 none; 1 SiLU (ControlNet conditioning embedder, controlnet.py:36-44);
+                              2 GELU (erf) / 3 quick-GELU x*sigmoid(1.702x): the CLIP text encoders' MLP */
     int32_t wgt_tiled;     /* 1: `wgt` is pre-tiled [n_tiles][k_blocks][block_n][64] (block_n must be given): every
                               weight tile is one contiguous block_n*128-byte burst instead of block_n strided rows */
     const void* a0;
@@ -133,7 +134,8 @@ int b200sd_softmax_rows(const float* in, void* out, int32_t rows, int32_t cols, 
  * q [batch, sq, ldq] / k,v [batch, sk, ldk] fp16 token-major with head h in columns
  * [h*d, (h+1)*d) of the given base pointers; out [batch, sq, ldo].  d must be 64.
  * mask: optional fp32 additive [batch, sk] (unet.py:99-114) or NULL.
- * impl: 0 ORIGINAL, 1 SPLIT_EINSUM, 2 SPLIT_EINSUM_V2 (tile policy only; same result). */
+ * impl: 0 ORIGINAL, 1 SPLIT_EINSUM, 2 SPLIT_EINSUM_V2 (tile policy only; same result);
+ *       | 0x100 adds the causal mask of the CLIP text encoder (key j visible to query i iff j <= i). */
 int b200sd_attention(const void* q, const void* k, const void* v, void* out, const float* mask,
                      int32_t batch, int32_t heads, int32_t sq, int32_t sk, int32_t d,
                      int32_t ldq, int32_t ldk, int32_t ldv, int32_t ldo, float scale, int32_t impl,
@@ -153,6 +155,11 @@ int b200sd_add(const void* a, const void* b, void* out, size_t numel, void* stre
 /* BC1S fp16/fp32 context (B, D, 1, S) -> token-major fp16 [B*S, D] */
 int b200sd_ctx_to_tokens(const void* in, int32_t in_f32, void* out, int32_t b, int32_t d, int32_t s,
                          void* stream);
+
+/* CLIP text-encoder input embeddings (transformers CLIPTextEmbeddings as called through pipeline.py:151-175):
+ * out[b*s + t, :] = token_embedding[ids[b, t]] + position_embedding[t]; ids float32 [batch, s]; tables fp16 */
+int b200sd_embed_tokens(const float* ids, const void* token_embedding, const void* position_embedding, void* out,
+                        int32_t batch, int32_t s, int32_t d, int32_t vocab, void* stream);
 
 /* ---- CFG + scheduler step (single fused elementwise kernel) -------------------------------
  * eps = eps_u + g (eps_c - eps_u)           (pipeline.py:559-562; performGuidance

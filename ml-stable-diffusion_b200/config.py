@@ -258,3 +258,56 @@ def random_state_dict(shapes, seed=0, dtype=torch.float32):
             t = 0.1 * torch.randn(shp, generator=g)
         sd[name] = t.to(dtype)
     return sd
+
+
+# ---------------------------------------------------------------------------------------------------
+# CLIP text encoders (transformers.CLIPTextModel, the `text_encoder` the reference converts:
+# torch2coreml.py:408-441; called with float input_ids, returns last_hidden_state: pipeline.py:151-175)
+# ---------------------------------------------------------------------------------------------------
+# SD-2.x: OpenCLIP ViT-H/14 text tower truncated to its penultimate layer (23 layers in the checkpoint's config)
+OPENCLIP_H_TEXT = dict(vocab_size=49408, hidden_size=1024, intermediate_size=4096, num_hidden_layers=23,
+                       num_attention_heads=16, max_position_embeddings=77, hidden_act="gelu", layer_norm_eps=1e-5)
+# SD-1.x: CLIP ViT-L/14 text tower
+CLIP_L_TEXT = dict(vocab_size=49408, hidden_size=768, intermediate_size=3072, num_hidden_layers=12,
+                   num_attention_heads=12, max_position_embeddings=77, hidden_act="quick_gelu", layer_norm_eps=1e-5)
+TINY_CLIP_TEXT = dict(vocab_size=1000, hidden_size=128, intermediate_size=512, num_hidden_layers=2,
+                      num_attention_heads=2, max_position_embeddings=77, hidden_act="gelu", layer_norm_eps=1e-5)
+
+
+def clip_text_param_shapes(cfg):
+    """State-dict schema of transformers.CLIPTextModel (names as in the diffusers checkpoints)."""
+    d, f = cfg["hidden_size"], cfg["intermediate_size"]
+    s = OrderedDict()
+    s["text_model.embeddings.token_embedding.weight"] = (cfg["vocab_size"], d)
+    s["text_model.embeddings.position_embedding.weight"] = (cfg["max_position_embeddings"], d)
+    for i in range(cfg["num_hidden_layers"]):
+        p = f"text_model.encoder.layers.{i}."
+        for nm in ("q_proj", "k_proj", "v_proj", "out_proj"):
+            s[p + f"self_attn.{nm}.weight"] = (d, d)
+            s[p + f"self_attn.{nm}.bias"] = (d,)
+        for ln in ("layer_norm1", "layer_norm2"):
+            s[p + ln + ".weight"] = (d,)
+            s[p + ln + ".bias"] = (d,)
+        s[p + "mlp.fc1.weight"], s[p + "mlp.fc1.bias"] = (f, d), (f,)
+        s[p + "mlp.fc2.weight"], s[p + "mlp.fc2.bias"] = (d, f), (d,)
+    s["text_model.final_layer_norm.weight"] = (d,)
+    s["text_model.final_layer_norm.bias"] = (d,)
+    return s
+
+
+def random_clip_text_state_dict(cfg, seed=0, dtype=torch.float32):
+    """Random-init text-encoder weights: U(+-1/sqrt(fan_in)) linears, N(0, 1) embeddings scaled to unit-ish
+    activations, non-trivial LayerNorm affines (same conventions as random_state_dict)."""
+    g = torch.Generator().manual_seed(seed)
+    sd = OrderedDict()
+    for name, shp in clip_text_param_shapes(cfg).items():
+        if "embedding" in name:
+            t = 0.5 * torch.randn(shp, generator=g)
+        elif "layer_norm" in name:
+            t = (1.0 + 0.1 * torch.randn(shp, generator=g)) if name.endswith("weight") else 0.1 * torch.randn(shp, generator=g)
+        elif len(shp) == 2:
+            t = (torch.rand(shp, generator=g) * 2 - 1) * shp[1] ** -0.5
+        else:
+            t = 0.1 * torch.randn(shp, generator=g)
+        sd[name] = t.to(dtype)
+    return sd

@@ -31,6 +31,7 @@ struct __align__(64) AttnParams {
     __half* out;
     const float* mask;  // [batch, sk] additive or null
     int sq, sk, ldo;
+    int causal;  // 1: key j is visible to query i only if j <= i (CLIP text encoder)
     float scale_log2;  // scale * log2(e)
     int* error_flag;
 };
@@ -60,8 +61,11 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
     const int q0 = blockIdx.x * kQ;
     const int head = blockIdx.y;
     const int batch = blockIdx.z;
-    const int n_kv = (p.sk + kKV - 1) / kKV;
-    const int n_half = (p.sk + kHalf - 1) / kHalf;  // the pipeline runs on 64-key halves of the 128-key tiles
+    // the pipeline runs on 64-key halves of the 128-key tiles; under a causal mask the halves entirely above this
+    // query tile's diagonal are never visited
+    const int sk_eff = p.causal ? min(p.sk, q0 + kQ) : p.sk;
+    const int n_kv = (sk_eff + kKV - 1) / kKV;
+    const int n_half = (sk_eff + kHalf - 1) / kHalf;
 
     if (threadIdx.x == 0) {
         if ((smem_u32(smem) & 1023u) != 0) atomicExch(p.error_flag, 1);  // swizzle needs 1024 B alignment
@@ -241,6 +245,9 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
         for (int h = 0; h < n_half; ++h) {
             const int b = h & 1;
             const int kvalid = min(kHalf, p.sk - h * kHalf);  // >= 1
+            // causal: a half whose last key is <= the tile's first query is fully visible to every row
+            const bool diag = p.causal && (h * kHalf + kHalf - 1 > q0);
+            const int qi = q0 + row;  // this thread's query index
             const uint32_t s_addr = tmem_s + lane_addr + b * kHalf;
             uint8_t* dst = p_row + b * kTileBytes;
             mbar_wait(&s_full[b], (h >> 1) & 1);
@@ -254,7 +261,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
                 }
             };
             float l_half;
-            if (mask_row == nullptr && kvalid == kHalf) {
+            if (mask_row == nullptr && kvalid == kHalf && !diag) {
                 if (h == 0) {
                     m_ref = row_max_lean(s_addr) * sl2;
                     float unused;
@@ -282,8 +289,9 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
                         float sc = __uint_as_float(v[i]) * sl2;
-                        if (mask_row && c + i < kvalid) sc += mask_row[h * kHalf + c + i] * 1.4426950408889634f;
-                        if (c + i < kvalid) m_half = fmaxf(m_half, sc);
+                        const bool vis = c + i < kvalid && (!diag || h * kHalf + c + i <= qi);
+                        if (mask_row && vis) sc += mask_row[h * kHalf + c + i] * 1.4426950408889634f;
+                        if (vis) m_half = fmaxf(m_half, sc);
                     }
                 }
                 if (__any_sync(0xffffffffu, m_half > m_ref + kTau)) {
@@ -304,12 +312,14 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
 #pragma unroll
                     for (int i = 0; i < 32; i += 2) {
                         float s0 = __uint_as_float(v[i]) * sl2, s1 = __uint_as_float(v[i + 1]) * sl2;
+                        const bool vis0 = c + i < kvalid && (!diag || h * kHalf + c + i <= qi);
+                        const bool vis1 = c + i + 1 < kvalid && (!diag || h * kHalf + c + i + 1 <= qi);
                         if (mask_row) {
-                            if (c + i < kvalid) s0 += mask_row[h * kHalf + c + i] * 1.4426950408889634f;
-                            if (c + i + 1 < kvalid) s1 += mask_row[h * kHalf + c + i + 1] * 1.4426950408889634f;
+                            if (vis0) s0 += mask_row[h * kHalf + c + i] * 1.4426950408889634f;
+                            if (vis1) s1 += mask_row[h * kHalf + c + i + 1] * 1.4426950408889634f;
                         }
-                        const float p0 = (c + i < kvalid) ? ex2_approx(s0 - m_ref) : 0.f;
-                        const float p1 = (c + i + 1 < kvalid) ? ex2_approx(s1 - m_ref) : 0.f;
+                        const float p0 = vis0 ? ex2_approx(s0 - m_ref) : 0.f;
+                        const float p1 = vis1 ? ex2_approx(s1 - m_ref) : 0.f;
                         l_half += p0 + p1;
                         pk[i >> 1] = pack_half2(p0, p1);
                     }
@@ -380,7 +390,7 @@ extern "C" int b200sd_attention(const void* q, const void* k, const void* v, voi
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     B200SD_REQUIRE(q && k && v && out, "b200sd_attention: null pointer");
     B200SD_REQUIRE(d == kD, "b200sd_attention: head dim %d not supported by this kernel (needs 64)", d);
-    B200SD_REQUIRE(impl >= 0 && impl <= 2, "b200sd_attention: unknown attention implementation %d", impl);
+    B200SD_REQUIRE(impl >= 0 && (impl & 0xff) <= 2 && (impl & ~0x1ff) == 0, "b200sd_attention: unknown attention implementation %d", impl);
     B200SD_REQUIRE(batch > 0 && heads > 0 && sq > 0 && sk > 0, "b200sd_attention: bad sizes");
     B200SD_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0,
                    "b200sd_attention: leading dimensions must be multiples of 8");
@@ -403,6 +413,7 @@ extern "C" int b200sd_attention(const void* q, const void* k, const void* v, voi
     p.sq = sq;
     p.sk = sk;
     p.ldo = ldo;
+    p.causal = (impl & 0x100) ? 1 : 0;
     p.scale_log2 = scale * 1.4426950408889634f;
     p.error_flag = attn_error_flag();
     B200SD_REQUIRE(p.error_flag != nullptr, "b200sd_attention: could not allocate the error flag");

@@ -64,6 +64,27 @@ __global__ void ctx_to_tokens_kernel(const T* __restrict__ in, __half* __restric
     }
 }
 
+// ---- CLIP text embeddings: out[b*s + t, :] = token_embedding[ids[b, t]] + position_embedding[t] -----------
+// ids arrive as float32 (the reference feeds input_ids as floats, pipeline.py:173); out-of-range ids clamp.
+__global__ void embed_tokens_kernel(const float* __restrict__ ids, const uint4* __restrict__ tok,
+                                    const uint4* __restrict__ pos, uint4* __restrict__ out, int rows, int s, int vecs,
+                                    int vocab) {
+    pdl_wait();
+    const size_t total = static_cast<size_t>(rows) * vecs;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int r = static_cast<int>(i / vecs), v = static_cast<int>(i - static_cast<size_t>(r) * vecs);
+        const int id = min(max(__float2int_rn(ids[r]), 0), vocab - 1);
+        uint4 a = tok[static_cast<size_t>(id) * vecs + v];
+        const uint4 b = pos[static_cast<size_t>(r % s) * vecs + v];
+        __half2* ah = reinterpret_cast<__half2*>(&a);
+        const __half2* bh = reinterpret_cast<const __half2*>(&b);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) ah[q] = __hadd2(ah[q], bh[q]);
+        out[i] = a;
+    }
+}
+
 // ---- nearest x2 upsample, NHWC fp16, 16-byte vectors ------------------------------------------
 __global__ void upsample2x_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int n, int h, int w,
                                   int vecs) {
@@ -291,6 +312,21 @@ extern "C" int b200sd_ctx_to_tokens(const void* in, int32_t in_f32, void* out, i
     else
         B200SD_CHECK_CUDA(launch_kernel(ctx_to_tokens_kernel<__half>, dim3(grid), dim3(block), 0, stream, reinterpret_cast<const __half*>(in),
                                                                  reinterpret_cast<__half*>(out), d, s));
+    B200SD_CHECK_CUDA(cudaGetLastError());
+    count_launch(1);
+    return 0;
+}
+
+extern "C" int b200sd_embed_tokens(const float* ids, const void* token_embedding, const void* position_embedding,
+                                   void* out, int32_t batch, int32_t s, int32_t d, int32_t vocab, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    B200SD_REQUIRE(ids && token_embedding && position_embedding && out && d % 8 == 0 && vocab > 0,
+                   "b200sd_embed_tokens: bad arguments (d=%d must be a multiple of 8)", d);
+    const size_t total = static_cast<size_t>(batch) * s * (d / 8);
+    B200SD_CHECK_CUDA(launch_kernel(embed_tokens_kernel, dim3(grid_for(total, 256)), dim3(256), 0, stream, ids,
+                                    reinterpret_cast<const uint4*>(token_embedding),
+                                    reinterpret_cast<const uint4*>(position_embedding), reinterpret_cast<uint4*>(out),
+                                    batch * s, s, d / 8, vocab));
     B200SD_CHECK_CUDA(cudaGetLastError());
     count_launch(1);
     return 0;

@@ -131,9 +131,13 @@ __device__ __forceinline__ void epilogue_store16(const GemmParams& p, float (&ac
                 if (col0 + j < p.N) acc[j] += bias[j];
         }
     }
-    if (kGeneric && p.act == 1) {
+    if (kGeneric && p.act != 0) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) acc[j] = silu_f(acc[j]);
+        for (int j = 0; j < 16; ++j) {
+            if (p.act == 1) acc[j] = silu_f(acc[j]);
+            else if (p.act == 2) acc[j] = gelu_erf_f(acc[j]);                              // OpenCLIP MLP ("gelu")
+            else acc[j] = __fdividef(acc[j], 1.0f + __expf(-1.702f * acc[j]));             // CLIP "quick_gelu"
+        }
     }
     int ocol0 = col0;
     const int nvals = geglu ? 8 : 16;
@@ -881,7 +885,7 @@ static int launch_gemm(const b200sd_gemm_args& a, cudaStream_t stream) {
     const int total = pl.m_tiles * pl.n_tiles * pl.splits;
     const int grid = std::min(total, num_sms());
     // compile-time epilogue variants for the hot shapes; anything irregular takes the generic kernel
-    B200SD_REQUIRE(a.act == 0 || (a.act == 1 && pl.splits == 1 && !a.geglu), "b200sd_gemm: act=%d unsupported here", a.act);
+    B200SD_REQUIRE(a.act == 0 || (a.act >= 1 && a.act <= 3 && pl.splits == 1 && !a.geglu), "b200sd_gemm: act=%d unsupported here", a.act);
     const bool regular = (a.act == 0) && (a.n % 16 == 0) && (p.n_store % 8 == 0) && (pl.block_n % 32 == 0) && pl.bias_mode != 2 &&
                          (a.residual == nullptr || pl.res_smem || pl.splits > 1);
     using KernelFn = void (*)(GemmParams);

@@ -73,6 +73,8 @@ _SIGNATURES = {
     "b200sd_add": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "b200sd_ctx_to_tokens": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                        C.c_void_p]),
+    "b200sd_embed_tokens": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                      C.c_int32, C.c_void_p]),
     "b200sd_cfg_scheduler_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                             C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(StepCoeffs),
                                             C.c_void_p]),
@@ -253,7 +255,7 @@ def _workspace(nbytes, device):
 
 
 def linear(x, wgt, bias=None, residual=None, *, x1=None, geglu=False, out_dtype=torch.float16, split_k=0,
-           block_n=0, bias_rows=0, bias_stride=0, out=None, static_w=False):
+           block_n=0, bias_rows=0, bias_stride=0, out=None, static_w=False, act=0):
     """out[M, N] = epilogue([x | x1] @ wgt^T).  x [M, C0] fp16, wgt [N, C0(+C1)] fp16, bias fp32 [N].
     static_w: `wgt` is a model weight (constant address/content) and may be re-tiled + cached."""
     _req(x, torch.float16, "linear x")
@@ -263,7 +265,7 @@ def linear(x, wgt, bias=None, residual=None, *, x1=None, geglu=False, out_dtype=
     if out is None:
         out = torch.empty(m, n_out, dtype=out_dtype, device=x.device)
     args = gemm_args(0, x, wgt, out, a1=x1, bias=bias, residual=residual, m=m, n=n, geglu=geglu,
-                     bias_rows=bias_rows, bias_stride=bias_stride, split_k=split_k, block_n=block_n)
+                     bias_rows=bias_rows, bias_stride=bias_stride, split_k=split_k, block_n=block_n, act=act)
     if static_w and TILED_WEIGHTS:
         _maybe_tile_weights(args, wgt, 1)
     need = gemm_workspace_bytes(args)
@@ -343,8 +345,9 @@ def layer_norm(x, gamma, beta, eps=1e-5, out=None):
     return out
 
 
-def attention(q, k, v, batch, heads, sq, sk, d=64, mask=None, impl=0, out=None, scale=None):
-    """q: view [batch*sq, >=heads*d] (row stride = q.stride(0)), k/v: [batch*sk, ...]; out [batch*sq, heads*d]."""
+def attention(q, k, v, batch, heads, sq, sk, d=64, mask=None, impl=0, out=None, scale=None, causal=False):
+    """q: view [batch*sq, >=heads*d] (row stride = q.stride(0)), k/v: [batch*sk, ...]; out [batch*sq, heads*d].
+    causal: key j is visible to query i only if j <= i (CLIP text encoder)."""
     for t, nm in ((q, "q"), (k, "k"), (v, "v")):
         if t.dtype != torch.float16 or not t.is_cuda or t.stride(-1) != 1:
             raise B200SDError(f"attention {nm}: expected CUDA fp16 with unit inner stride")
@@ -352,7 +355,8 @@ def attention(q, k, v, batch, heads, sq, sk, d=64, mask=None, impl=0, out=None, 
         out = torch.empty(batch * sq, heads * d, dtype=torch.float16, device=q.device)
     scale = float(d) ** -0.5 if scale is None else float(scale)
     _check(load().b200sd_attention(_ptr(q), _ptr(k), _ptr(v), _ptr(out), _ptr(mask), batch, heads, sq, sk, d,
-                                   q.stride(0), k.stride(0), v.stride(0), out.stride(0), scale, int(impl),
+                                   q.stride(0), k.stride(0), v.stride(0), out.stride(0), scale,
+                                   int(impl) | (0x100 if causal else 0),
                                    _stream()), "b200sd_attention")
     return out
 
@@ -393,6 +397,22 @@ def add(a, b, out=None):
     if out is None:
         out = torch.empty_like(a)
     _check(load().b200sd_add(_ptr(a), _ptr(b), _ptr(out), a.numel(), _stream()), "b200sd_add")
+    return out
+
+
+def embed_tokens(ids, token_embedding, position_embedding, out=None):
+    """ids fp32 [B, S]; tables fp16 [V, D] / [S, D] -> fp16 [B*S, D] (token + position embedding)."""
+    _req(ids, torch.float32, "embed_tokens ids")
+    _req(token_embedding, torch.float16, "embed_tokens token_embedding")
+    _req(position_embedding, torch.float16, "embed_tokens position_embedding")
+    b, s = ids.shape
+    v, d = token_embedding.shape
+    if position_embedding.shape[0] < s or position_embedding.shape[1] != d:
+        raise B200SDError("embed_tokens: position table does not cover the sequence")
+    if out is None:
+        out = torch.empty(b * s, d, dtype=torch.float16, device=ids.device)
+    _check(load().b200sd_embed_tokens(_ptr(ids), _ptr(token_embedding), _ptr(position_embedding), _ptr(out), b, s, d, v,
+                                      _stream()), "b200sd_embed_tokens")
     return out
 
 

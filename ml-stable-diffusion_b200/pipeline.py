@@ -99,9 +99,13 @@ class B200StableDiffusionPipeline:
     # ---------------------------------------------------------------- factory
     @classmethod
     def from_random_init(cls, model_version="sd21-base", images_per_call=1, device="cuda", seed=0,
-                         scheduler="DDIM", height=512, width=512, unet_cfg=None, vae_cfg=None, controlnet_cfgs=None):
+                         scheduler="DDIM", height=512, width=512, unet_cfg=None, vae_cfg=None, controlnet_cfgs=None,
+                         text_encoder_cfg=None, tokenizer=None):
         """Random-init weights of the named architecture (no checkpoints exist offline).  ``controlnet_cfgs``:
-        list of ControlNet configs (seeded seed+2, seed+3, ...); switches the UNet to its control variant."""
+        list of ControlNet configs (seeded seed+2, seed+3, ...); switches the UNet to its control variant.
+        ``text_encoder_cfg``: a CLIP text config (config.OPENCLIP_H_TEXT for SD-2.x) -> the text encoder runs on the
+        device (random-init, seed+100) instead of the synthetic embedding table; ``tokenizer``: e.g. a
+        ``tokenizer.BPETokenizer`` built from the checkpoint's vocab.json / merges.txt."""
         unet_cfg = unet_cfg or {"sd21-base": C.SD21_BASE_UNET, "sdxl-base": C.SDXL_BASE_UNET,
                                 "tiny": C.TINY_UNET}[model_version]
         vae_cfg = vae_cfg or (C.TINY_VAE if model_version == "tiny" else C.SD_VAE)
@@ -121,7 +125,16 @@ class B200StableDiffusionPipeline:
                                                            dtype=torch.float16),
                                     batch=2 * images_per_call, height=height // f, width=width // f, device=device)
                     for i, c in enumerate(controlnet_cfgs)]
-        return cls(unet, vae, scheduler=scheduler, xl=unet.engine.xl, controlnet=nets)
+        enc = None
+        if text_encoder_cfg is not None:
+            from .text_encoder import TextEncoderModel
+            if text_encoder_cfg["hidden_size"] != unet_cfg["cross_attention_dim"]:
+                raise ValueError("text encoder width does not match the UNet's cross_attention_dim")
+            enc = TextEncoderModel(text_encoder_cfg, C.random_clip_text_state_dict(text_encoder_cfg, seed=seed + 100,
+                                                                                   dtype=torch.float16),
+                                   batch=1, device=device)
+        return cls(unet, vae, scheduler=scheduler, xl=unet.engine.xl, controlnet=nets, text_encoder=enc,
+                   tokenizer=tokenizer)
 
     # ---------------------------------------------------------------- reference-named helpers
     def check_inputs(self, prompt, height, width, callback_steps):

@@ -221,6 +221,30 @@ def test_attention(cuda_lib, batch, heads, sq, sk):
     _close(out, _attn_ref(q, k, v, batch, heads, sq, sk), 3e-3, 3e-3, f"attention {batch}x{heads}x{sq}x{sk}")
 
 
+@pytest.mark.parametrize("batch,heads,s", [(2, 2, 77), (1, 3, 300), (2, 16, 128)])
+def test_attention_causal(cuda_lib, batch, heads, s):
+    """Causal mask of the CLIP text encoder (key j visible to query i iff j <= i), incl. halves above the diagonal
+    that are skipped and the diagonal halves that take the predicated path."""
+    c = heads * 64
+    q, k, v = _rand(batch * s, c, seed=1), _rand(batch * s, c, seed=2), _rand(batch * s, c, seed=3)
+    qh, kh, vh = (t.float().view(batch, s, heads, 64).transpose(1, 2) for t in (q, k, v))
+    sc = qh @ kh.transpose(-1, -2) * 64 ** -0.5 + torch.full((s, s), float("-inf"), device="cuda").triu(1)
+    ref = (torch.softmax(sc, -1) @ vh).transpose(1, 2).reshape(batch * s, c)
+    _close(cuda_lib.attention(q, k, v, batch, heads, s, s, causal=True), ref, 3e-3, 3e-3, f"causal attention {s}")
+
+
+def test_text_encoder_ops(cuda_lib):
+    ids = torch.randint(0, 500, (2, 77), device="cuda").float()
+    tok, pos = _rand(500, 128, seed=1), _rand(77, 128, seed=2)
+    ref = (tok[ids.long()] + pos[None]).reshape(2 * 77, 128).float()
+    _close(cuda_lib.embed_tokens(ids, tok, pos), ref, 1e-3, 2e-3, "embed_tokens")
+    x, w = _rand(154, 256, seed=3), _rand(512, 256, scale=256 ** -0.5, seed=4)
+    b = torch.randn(512, device="cuda")
+    y = x.float() @ w.float().t() + b
+    _close(cuda_lib.linear(x, w, b, act=2), F.gelu(y), 3e-3, 3e-3, "linear + GELU")
+    _close(cuda_lib.linear(x, w, b, act=3), y * torch.sigmoid(1.702 * y), 3e-3, 3e-3, "linear + quick-GELU")
+
+
 def test_attention_fused_qkv_and_mask(cuda_lib):
     batch, heads, s = 2, 5, 256
     c = heads * 64

@@ -140,3 +140,23 @@ def test_vae_decoder_restatement_shapes_and_postprocess():
     sd2["decoder.conv_out.bias"] = sd["decoder.conv_out.bias"] * 2
     with torch.no_grad():
         assert torch.allclose(R.vae_decode(sd2, cfg, z), 2 * img, atol=1e-5)
+
+
+@pytest.mark.parametrize("cfg_name", ["TINY_CLIP_TEXT", "CLIP_L_TEXT"])
+def test_clip_text_restatement_matches_transformers(cfg_name):
+    """The text-encoder restatement against the library class the reference converts (transformers.CLIPTextModel)."""
+    from b200sd import config
+    from oracle import clip_text
+
+    if not clip_text.available():
+        pytest.skip("transformers not importable")
+    cfg = dict(getattr(config, cfg_name))
+    if cfg_name == "CLIP_L_TEXT":
+        cfg["num_hidden_layers"] = 2  # quick_gelu path; two layers keep the CPU test fast
+    sd = config.random_clip_text_state_dict(cfg, seed=5)
+    ids = torch.randint(0, cfg["vocab_size"], (2, 77), generator=torch.Generator().manual_seed(6))
+    ids[:, -1] = cfg["vocab_size"] - 1
+    ref = clip_text.library_forward(cfg, sd, ids)
+    out = clip_text.clip_text_forward(cfg, sd, ids)
+    assert out.shape == ref.shape == (2, 77, cfg["hidden_size"])
+    assert float((out - ref).abs().max()) < 2e-5

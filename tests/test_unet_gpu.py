@@ -361,3 +361,26 @@ def test_vae_decoder_sd_full_size_vs_oracle(cuda_lib):
     with torch.no_grad():
         ref = R.vae_decode(sd, cfg, z.half().float()).numpy()
     _check(img, ref, "SD vae decoder 512x512", max_abs=2e-2 * max(1.0, float(np.abs(ref).max())))
+
+
+@pytest.mark.parametrize("cfg_name", ["TINY_CLIP_TEXT", "OPENCLIP_H_TEXT", "CLIP_L_TEXT"])
+def test_text_encoder_vs_oracle(cuda_lib, cfg_name):
+    """the CLIP text encoder (float input_ids -> last_hidden_state, pipeline.py:151-175) against
+    transformers.CLIPTextModel on the host -- the class the reference converts (torch2coreml.py:408-441)."""
+    from b200sd.text_encoder import TextEncoderModel
+    from oracle import clip_text
+
+    cfg = getattr(config, cfg_name)
+    sd = config.random_clip_text_state_dict(cfg, seed=7, dtype=torch.float16)
+    ids = torch.randint(0, cfg["vocab_size"] - 2, (2, 77), generator=torch.Generator().manual_seed(8))
+    ids[:, 0] = cfg["vocab_size"] - 2
+    ids[0, 20:] = cfg["vocab_size"] - 1  # padded with the end token, like a real prompt
+    ids[1, 76] = cfg["vocab_size"] - 1
+    m = TextEncoderModel(cfg, sd, batch=2)
+    out = m(input_ids=ids.float().numpy())["last_hidden_state"]
+    assert out.shape == (2, 77, cfg["hidden_size"]) and out.dtype == np.float32
+    with torch.no_grad():
+        ref = (clip_text.library_forward if clip_text.available() else clip_text.clip_text_forward)(cfg, sd, ids).numpy()
+    _check(out, ref, f"text encoder {cfg_name}", max_abs=2e-2 * max(1.0, float(np.abs(ref).max())))
+    with pytest.raises(TypeError):
+        m(input_ids=ids.numpy())  # integer ids: the reference's model call wants float32 (coreml_model.py:97-116)
