@@ -365,8 +365,9 @@ def test_vae_decoder_sd_full_size_vs_oracle(cuda_lib):
 
 @pytest.mark.parametrize("cfg_name", ["TINY_CLIP_TEXT", "OPENCLIP_H_TEXT", "CLIP_L_TEXT"])
 def test_text_encoder_vs_oracle(cuda_lib, cfg_name):
-    """the CLIP text encoder (float input_ids -> last_hidden_state, pipeline.py:151-175) against
-    transformers.CLIPTextModel on the host -- the class the reference converts (torch2coreml.py:408-441)."""
+    """the CLIP text encoder (float input_ids -> last_hidden_state, pipeline.py:151-175) against the
+    oracle's restatement of transformers.CLIPTextModel (the class the reference converts, torch2coreml.py:408-441);
+    the restatement itself is pinned to the library in tests/test_oracle.py (CPU suite)."""
     from b200sd.text_encoder import TextEncoderModel
     from oracle import clip_text
 
@@ -380,7 +381,7 @@ def test_text_encoder_vs_oracle(cuda_lib, cfg_name):
     out = m(input_ids=ids.float().numpy())["last_hidden_state"]
     assert out.shape == (2, 77, cfg["hidden_size"]) and out.dtype == np.float32
     with torch.no_grad():
-        ref = (clip_text.library_forward if clip_text.available() else clip_text.clip_text_forward)(cfg, sd, ids).numpy()
+        ref = clip_text.clip_text_forward(cfg, sd, ids).numpy()
     _check(out, ref, f"text encoder {cfg_name}", max_abs=2e-2 * max(1.0, float(np.abs(ref).max())))
     with pytest.raises(TypeError):
         m(input_ids=ids.numpy())  # integer ids: the reference's model call wants float32 (coreml_model.py:97-116)
