@@ -1,3 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-( timeout 400 python -m pytest tests/test_ops_gpu.py tests/test_unet_gpu.py -m gpu -q -x -k "causal or text_encoder or attention" 2>&1 | tail -15 ) | tee gpurun_out/tests_text.log
+( time timeout 600 python -m pytest tests -m gpu -q -x 2>&1 | tail -4 ) 2>&1 | tee gpurun_out/tests.log
+( timeout 120 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2 ) | tee gpurun_out/smoke.log
