@@ -270,6 +270,13 @@ OPENCLIP_H_TEXT = dict(vocab_size=49408, hidden_size=1024, intermediate_size=409
 # SD-1.x: CLIP ViT-L/14 text tower
 CLIP_L_TEXT = dict(vocab_size=49408, hidden_size=768, intermediate_size=3072, num_hidden_layers=12,
                    num_attention_heads=12, max_position_embeddings=77, hidden_act="quick_gelu", layer_norm_eps=1e-5)
+# SDXL second encoder: OpenCLIP ViT-bigG/14 text tower with text_projection (CLIPTextModelWithProjection)
+OPENCLIP_BIGG_TEXT = dict(vocab_size=49408, hidden_size=1280, intermediate_size=5120, num_hidden_layers=32,
+                          num_attention_heads=20, max_position_embeddings=77, hidden_act="gelu", layer_norm_eps=1e-5,
+                          projection_dim=1280)
+TINY_CLIP_TEXT_PROJ = dict(vocab_size=1000, hidden_size=128, intermediate_size=512, num_hidden_layers=3,
+                           num_attention_heads=2, max_position_embeddings=77, hidden_act="quick_gelu",
+                           layer_norm_eps=1e-5, projection_dim=64)
 TINY_CLIP_TEXT = dict(vocab_size=1000, hidden_size=128, intermediate_size=512, num_hidden_layers=2,
                       num_attention_heads=2, max_position_embeddings=77, hidden_act="gelu", layer_norm_eps=1e-5)
 
@@ -292,6 +299,8 @@ def clip_text_param_shapes(cfg):
         s[p + "mlp.fc2.weight"], s[p + "mlp.fc2.bias"] = (d, f), (d,)
     s["text_model.final_layer_norm.weight"] = (d,)
     s["text_model.final_layer_norm.bias"] = (d,)
+    if cfg.get("projection_dim"):  # CLIPTextModelWithProjection
+        s["text_projection.weight"] = (cfg["projection_dim"], d)
     return s
 
 

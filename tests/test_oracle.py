@@ -160,3 +160,26 @@ def test_clip_text_restatement_matches_transformers(cfg_name):
     out = clip_text.clip_text_forward(cfg, sd, ids)
     assert out.shape == ref.shape == (2, 77, cfg["hidden_size"])
     assert float((out - ref).abs().max()) < 2e-5
+
+
+@pytest.mark.parametrize("cfg_name", ["TINY_CLIP_TEXT", "TINY_CLIP_TEXT_PROJ"])
+def test_clip_text_hidden_states_and_pooled_match_transformers(cfg_name):
+    """hidden_states[-2] / pooler_output / text_embeds: the tensors torch2coreml.py:416-433 exports for SDXL."""
+    from b200sd import config
+    from oracle import clip_text
+
+    if not clip_text.available():
+        pytest.skip("transformers not importable")
+    cfg = getattr(config, cfg_name)
+    sd = config.random_clip_text_state_dict(cfg, seed=9)
+    ids = torch.randint(0, cfg["vocab_size"] - 2, (3, 77), generator=torch.Generator().manual_seed(10))
+    ids[0, 5:] = cfg["vocab_size"] - 1
+    ids[1, 76] = cfg["vocab_size"] - 1
+    ids[2, 30] = cfg["vocab_size"] - 1
+    ref = clip_text.library_forward_all(cfg, sd, ids)
+    out = clip_text.clip_text_forward(cfg, sd, ids, return_all=True)
+    assert len(out["hidden_states"]) == len(ref["hidden_states"]) == cfg["num_hidden_layers"] + 1
+    assert float((out["hidden_states"][-2] - ref["hidden_states"][-2]).abs().max()) < 2e-5
+    assert float((out["last_hidden_state"] - ref["last_hidden_state"]).abs().max()) < 2e-5
+    key = "text_embeds" if cfg.get("projection_dim") else "pooler_output"
+    assert out[key].shape == ref[key].shape and float((out[key] - ref[key]).abs().max()) < 2e-5

@@ -385,3 +385,26 @@ def test_text_encoder_vs_oracle(cuda_lib, cfg_name):
     _check(out, ref, f"text encoder {cfg_name}", max_abs=2e-2 * max(1.0, float(np.abs(ref).max())))
     with pytest.raises(TypeError):
         m(input_ids=ids.numpy())  # integer ids: the reference's model call wants float32 (coreml_model.py:97-116)
+
+
+def test_text_encoder_sdxl_outputs_vs_oracle(cuda_lib):
+    """SDXL text encoders export hidden_states[-2] and the pooled / projected embedding (torch2coreml.py:416-446)."""
+    from b200sd.text_encoder import TextEncoderModel
+    from oracle import clip_text
+
+    for cfg_name in ("TINY_CLIP_TEXT_PROJ", "TINY_CLIP_TEXT"):
+        cfg = getattr(config, cfg_name)
+        sd = config.random_clip_text_state_dict(cfg, seed=11, dtype=torch.float16)
+        ids = torch.randint(0, cfg["vocab_size"] - 2, (2, 77), generator=torch.Generator().manual_seed(12))
+        ids[0, 9:] = cfg["vocab_size"] - 1
+        ids[1, 40] = cfg["vocab_size"] - 1
+        m = TextEncoderModel(cfg, sd, batch=2, hidden_layer=-2)
+        out = m(input_ids=ids.float().numpy())
+        assert set(out) == {"hidden_embeds", "pooled_outputs"}
+        with torch.no_grad():
+            ref = clip_text.clip_text_forward(cfg, sd, ids, return_all=True)
+        _check(out["hidden_embeds"], ref["hidden_states"][-2].numpy(), f"{cfg_name} hidden_states[-2]",
+               max_abs=2e-2 * max(1.0, float(ref["hidden_states"][-2].abs().max())))
+        pooled = ref["text_embeds" if cfg.get("projection_dim") else "pooler_output"].numpy()
+        assert out["pooled_outputs"].shape == pooled.shape
+        _check(out["pooled_outputs"], pooled, f"{cfg_name} pooled", max_abs=2e-2 * max(1.0, float(np.abs(pooled).max())))
