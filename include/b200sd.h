@@ -76,6 +76,8 @@ typedef struct {
                               2 GELU (erf) / 3 quick-GELU x*sigmoid(1.702x): the CLIP text encoders' MLP */
     int32_t wgt_tiled;     /* 1: `wgt` is pre-tiled [n_tiles][k_blocks][block_n][64] (block_n must be given): every
                               weight tile is one contiguous block_n*128-byte burst instead of block_n strided rows */
+    int32_t pad_after_only; /* conv, stride 2: zero-pad one pixel after the last row / column only, i.e. diffusers'
+                               Downsample2D(padding=0) = F.pad(x, (0, 1, 0, 1)) + conv (VAE encoder); 0 = pad 1 all round */
     const void* a0;
     const void* a1;
     const void* wgt;

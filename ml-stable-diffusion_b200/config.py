@@ -236,6 +236,34 @@ def vae_decoder_param_shapes(cfg) -> "OrderedDict[str, tuple]":
     return sh
 
 
+def vae_encoder_param_shapes(cfg) -> "OrderedDict[str, tuple]":
+    """diffusers ``AutoencoderKL`` encoder + quant_conv keys (what ``convert_vae_encoder`` wraps,
+    torch2coreml.py:739-749: ``quant_conv(encoder(x))``; double_z: 2 * latent_channels moments)."""
+    sh = OrderedDict()
+    boc = list(cfg["block_out_channels"])
+    lpb = cfg.get("layers_per_block", 2)
+    lc = cfg.get("latent_channels", 4)
+    _conv(sh, "encoder.conv_in", boc[0], cfg.get("out_channels", 3), 3)
+    out = boc[0]
+    for i in range(len(boc)):
+        prev, out = out, boc[i]
+        for j in range(lpb):
+            _resnet(sh, f"encoder.down_blocks.{i}.resnets.{j}", prev if j == 0 else out, out, 0)
+        if i != len(boc) - 1:
+            _conv(sh, f"encoder.down_blocks.{i}.downsamplers.0.conv", out, out, 3)
+    top = boc[-1]
+    _resnet(sh, "encoder.mid_block.resnets.0", top, top, 0)
+    a = "encoder.mid_block.attentions.0"
+    _norm(sh, a + ".group_norm", top)
+    for n in ("to_q", "to_k", "to_v", "to_out.0"):
+        _conv(sh, f"{a}.{n}", top, top, 1)
+    _resnet(sh, "encoder.mid_block.resnets.1", top, top, 0)
+    _norm(sh, "encoder.conv_norm_out", top)
+    _conv(sh, "encoder.conv_out", 2 * lc, top, 3)
+    _conv(sh, "quant_conv", 2 * lc, 2 * lc, 1)
+    return sh
+
+
 def random_state_dict(shapes, seed=0, dtype=torch.float32):
     """Deterministic random-init weights with torch's default conv statistics
     (U(-1/sqrt(fan_in), 1/sqrt(fan_in)) for weights and biases) and *non-trivial* norm affines

@@ -38,6 +38,8 @@ struct __align__(64) GemmParams {
     int bias_rows, bias_stride, geglu, out_f32;
     int act;         // 0 none, 1 SiLU after bias (generic variant only)
     int cluster;     // split-K on a thread-block cluster: the `splits` CTAs of a tile reduce it through DSMEM
+    int pad_lo;      // conv: zero padding before the first row / column (1 = symmetric pad 1; 0 = pad only after: the
+                     // VAE encoder's F.pad(x, (0, 1, 0, 1)) + stride-2 conv)
     int two_cta;     // CTA pairs: one tcgen05.mma cta_group::2 computes two M tiles, each CTA stages half of B
     int m_pairs;     // ceil(m_tiles / 2)
     int wgt_tiled;   // B operand pre-tiled: tile (n_tile, kb) starts at row (n_tile * kb_total + kb) * block_n
@@ -328,7 +330,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) umma_gemm_kernel(const __grid
                             tma_load_2d_pair(dst_a, tmA, fb, c, t.m_tile * kBM, kEvictNormal);
                         } else {
                             const int r = tap / 3, s3 = tap - 3 * r;
-                            tma_load_4d_pair(dst_a, tmA, fb, c, t.w0 * p.stride + s3 - 1, t.h0 * p.stride + r - 1, t.n0,
+                            tma_load_4d_pair(dst_a, tmA, fb, c, t.w0 * p.stride + s3 - p.pad_lo, t.h0 * p.stride + r - p.pad_lo, t.n0,
                                              kEvictNormal);
                         }
                         tma_load_2d_pair(dst_b, &p.tmB, fb, p.wgt_tiled ? 0 : wk, brow,
@@ -339,8 +341,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) umma_gemm_kernel(const __grid
                             tma_load_2d(dst_a, tmA, &full_bar[stage], c, t.m_tile * kBM, kEvictNormal);
                         } else {
                             const int r = tap / 3, s3 = tap - 3 * r;
-                            tma_load_4d(dst_a, tmA, &full_bar[stage], c, t.w0 * p.stride + s3 - 1,
-                                        t.h0 * p.stride + r - 1, t.n0, kEvictNormal);
+                            tma_load_4d(dst_a, tmA, &full_bar[stage], c, t.w0 * p.stride + s3 - p.pad_lo,
+                                        t.h0 * p.stride + r - p.pad_lo, t.n0, kEvictNormal);
                         }
                         tma_load_2d(dst_b, &p.tmB, &full_bar[stage], p.wgt_tiled ? 0 : wk, brow,
                                     p.wgt_tiled ? kEvictFirst : kEvictLast);
@@ -645,6 +647,7 @@ static int ilog2(int v) {
 
 static int plan_gemm(const b200sd_gemm_args& a, GemmPlan& pl) {
     B200SD_REQUIRE(a.mode == 0 || a.mode == 1, "b200sd_gemm: bad mode %d", a.mode);
+    B200SD_REQUIRE(!a.pad_after_only || (a.mode == 1 && a.stride == 2), "b200sd_gemm: pad_after_only is for stride-2 convolutions");
     B200SD_REQUIRE(a.c0 > 0 && a.c0 % 8 == 0 && a.c1 >= 0 && a.c1 % 8 == 0,
                    "b200sd_gemm: channel counts must be positive multiples of 8 (c0=%d c1=%d)", a.c0, a.c1);
     B200SD_REQUIRE(a.n > 0, "b200sd_gemm: n=%d", a.n);
@@ -870,6 +873,7 @@ static int launch_gemm(const b200sd_gemm_args& a, cudaStream_t stream) {
     p.geglu = a.geglu;
     p.out_f32 = a.out_f32;
     p.act = a.act;
+    p.pad_lo = a.pad_after_only ? 0 : 1;
     p.wgt_tiled = a.wgt_tiled;
     p.bias_mode = pl.bias_mode;
     p.res_smem = pl.res_smem;

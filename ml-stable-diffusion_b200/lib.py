@@ -24,7 +24,7 @@ class GemmArgs(C.Structure):
         ("n_img", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("stride", C.c_int32),
         ("geglu", C.c_int32), ("out_f32", C.c_int32), ("bias_rows", C.c_int32), ("bias_stride", C.c_int32),
         ("split_k", C.c_int32),
-        ("block_n", C.c_int32), ("act", C.c_int32), ("wgt_tiled", C.c_int32),
+        ("block_n", C.c_int32), ("act", C.c_int32), ("wgt_tiled", C.c_int32), ("pad_after_only", C.c_int32),
         ("a0", C.c_void_p), ("a1", C.c_void_p), ("wgt", C.c_void_p), ("bias", C.c_void_p),
         ("residual", C.c_void_p), ("out", C.c_void_p), ("workspace", C.c_void_p),
         ("workspace_bytes", C.c_size_t),
@@ -144,7 +144,7 @@ def _req(t, dtype, what):
 
 
 def gemm_args(mode, a0, wgt, out, *, a1=None, bias=None, residual=None, m=0, n=0, n_img=0, h=0, w=0, stride=1,
-              geglu=False, bias_rows=0, bias_stride=0, split_k=0, block_n=0, workspace=None, act=0):
+              geglu=False, bias_rows=0, bias_stride=0, split_k=0, block_n=0, workspace=None, act=0, pad_after_only=False):
     args = GemmArgs()
     args.mode = mode
     args.m = m
@@ -159,6 +159,7 @@ def gemm_args(mode, a0, wgt, out, *, a1=None, bias=None, residual=None, m=0, n=0
     args.split_k = split_k
     args.block_n = block_n
     args.act = act
+    args.pad_after_only = int(pad_after_only)
     args.a0 = a0.data_ptr()
     args.a1 = None if a1 is None else a1.data_ptr()
     args.wgt = wgt.data_ptr()
@@ -278,7 +279,7 @@ def linear(x, wgt, bias=None, residual=None, *, x1=None, geglu=False, out_dtype=
 
 
 def conv3x3(x, wgt, bias=None, residual=None, *, x1=None, stride=1, out_dtype=torch.float16, split_k=0,
-            block_n=0, bias_rows=0, bias_stride=0, out=None, act=0, static_w=True):
+            block_n=0, bias_rows=0, bias_stride=0, out=None, act=0, static_w=True, pad_after_only=False):
     """3x3 pad-1 convolution.  x NHWC fp16 [N, H, W, C0]; wgt [Cout, 9*(C0+C1)] fp16 (OHWI);
     bias fp32 [Cout] or [N_img, Cout] with bias_rows = Hout*Wout."""
     _req(x, torch.float16, "conv3x3 x")
@@ -289,7 +290,8 @@ def conv3x3(x, wgt, bias=None, residual=None, *, x1=None, stride=1, out_dtype=to
     if out is None:
         out = torch.empty(nimg, ho, wo, cout, dtype=out_dtype, device=x.device)
     args = gemm_args(1, x, wgt, out, a1=x1, bias=bias, residual=residual, n=cout, n_img=nimg, h=h, w=w,
-                     stride=stride, bias_rows=bias_rows, bias_stride=bias_stride, split_k=split_k, block_n=block_n, act=act)
+                     stride=stride, bias_rows=bias_rows, bias_stride=bias_stride, split_k=split_k, block_n=block_n, act=act,
+                     pad_after_only=pad_after_only)
     if static_w and TILED_WEIGHTS:
         _maybe_tile_weights(args, wgt, 9)
     need = gemm_workspace_bytes(args)

@@ -273,6 +273,33 @@ def vae_decode(sd, cfg, z):
     return _conv(sd, "decoder.conv_out", x, padding=1)
 
 
+def vae_encode(sd, cfg, x):
+    """moments = quant_conv(encoder(x)) (torch2coreml.py:739-749); x in [-1, 1], (B, 3, H, W) ->
+    (B, 2 * latent_channels, H/8, W/8).  diffusers Encoder: conv_in, DownEncoderBlock2D x N (ResNets, then
+    Downsample2D(padding=0): F.pad(x, (0, 1, 0, 1)) + 3x3 stride-2 conv), mid block, GroupNorm + SiLU, conv_out.
+    parity unpinned (diffusers is not installed; same status as vae_decode)."""
+    boc = list(cfg.get("block_out_channels", (128, 256, 512, 512)))
+    lpb = cfg.get("layers_per_block", 2)
+    h = _conv(sd, "encoder.conv_in", x.float(), padding=1)
+    for i in range(len(boc)):
+        for j in range(lpb):
+            h = _vae_resnet(sd, f"encoder.down_blocks.{i}.resnets.{j}", h)
+        if i != len(boc) - 1:
+            h = _conv(sd, f"encoder.down_blocks.{i}.downsamplers.0.conv", F.pad(h, (0, 1, 0, 1)), stride=2)
+    h = _vae_resnet(sd, "encoder.mid_block.resnets.0", h)
+    h = _vae_attn(sd, "encoder.mid_block.attentions.0", h)
+    h = _vae_resnet(sd, "encoder.mid_block.resnets.1", h)
+    h = F.silu(_gn(sd, "encoder.conv_norm_out", h, 32, 1e-6))
+    return _conv(sd, "quant_conv", _conv(sd, "encoder.conv_out", h, padding=1))
+
+
+def sample_latents(moments, noise, scaling_factor=0.18215):
+    """DiagonalGaussianDistribution.sample (Encoder.swift: mean + exp(0.5 * clamp(logvar, -30, 20)) * noise),
+    times the scaling factor."""
+    mean, logvar = moments.chunk(2, dim=1)
+    return (mean + torch.exp(0.5 * logvar.clamp(-30.0, 20.0)) * noise) * scaling_factor
+
+
 def postprocess_image(img):
     """pipeline.py:317-318: clip(x/2+0.5, 0, 1), NCHW -> NHWC."""
     return (img / 2 + 0.5).clamp(0, 1).permute(0, 2, 3, 1)

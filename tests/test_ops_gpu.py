@@ -178,6 +178,18 @@ def test_conv3x3_stride2(cuda_lib, n, h, w, c):
     _close(cuda_lib.conv3x3(x, _pack(wt), b, stride=2), _conv_ref(x, wt, b, stride=2), 3e-3, 3e-3, "conv s2")
 
 
+@pytest.mark.parametrize("n,h,w,c", [(1, 64, 64, 64), (2, 16, 16, 128), (1, 24, 40, 64)])
+def test_conv3x3_stride2_pad_after_only(cuda_lib, n, h, w, c):
+    """diffusers Downsample2D(padding=0): F.pad(x, (0, 1, 0, 1)) then a 3x3 stride-2 convolution (VAE encoder)."""
+    x = _rand(n, h, w, c, seed=1)
+    wt = _rand(c, c, 3, 3, scale=(9 * c) ** -0.5, seed=2)
+    b = torch.randn(c, device="cuda")
+    ref = F.conv2d(F.pad(x.float().permute(0, 3, 1, 2), (0, 1, 0, 1)), wt.float(), b, stride=2).permute(0, 2, 3, 1)
+    out = cuda_lib.conv3x3(x, _pack(wt), b, stride=2, pad_after_only=True)
+    assert out.shape == ref.shape
+    _close(out, ref.contiguous(), 3e-3, 3e-3, "conv s2 pad-after-only")
+
+
 @pytest.mark.parametrize("n,hw,c0,c1,silu", [(2, 64, 320, 0, True), (2, 32, 640, 0, False), (2, 16, 1280, 640, True),
                                              (2, 8, 64, 0, True), (1, 64, 128, 128, False)])
 def test_group_norm(cuda_lib, n, hw, c0, c1, silu):

@@ -408,3 +408,22 @@ def test_text_encoder_sdxl_outputs_vs_oracle(cuda_lib):
         pooled = ref["text_embeds" if cfg.get("projection_dim") else "pooler_output"].numpy()
         assert out["pooled_outputs"].shape == pooled.shape
         _check(out["pooled_outputs"], pooled, f"{cfg_name} pooled", max_abs=2e-2 * max(1.0, float(np.abs(pooled).max())))
+
+
+def test_vae_encoder_tiny_vs_oracle(cuda_lib):
+    """vae_encoder(x) -> moments = quant_conv(encoder(x)) (torch2coreml.py:739-756) and the Swift sampling rule."""
+    from b200sd.vae import VAEEncoderModel
+
+    cfg = config.TINY_VAE
+    sd = config.random_state_dict(config.vae_encoder_param_shapes(cfg), seed=13)
+    x = torch.rand(1, 3, 64, 64, generator=torch.Generator().manual_seed(14)) * 2 - 1
+    m = VAEEncoderModel(cfg, sd, batch=1, height=64, width=64)
+    mom = m(x=x.half().numpy())["latent"]
+    assert mom.shape == (1, 8, 16, 16)
+    with torch.no_grad():
+        ref = R.vae_encode(sd, cfg, x.half().float())
+    _check(mom, ref.numpy(), "tiny vae encoder moments", max_abs=2e-2 * max(1.0, float(ref.abs().max())))
+    noise = torch.randn(1, 4, 16, 16, generator=torch.Generator().manual_seed(15))
+    lat = m.encode(x.half().numpy(), noise)
+    _check(lat.numpy(), R.sample_latents(ref, noise).numpy(), "tiny vae encoder sample",
+           max_abs=2e-2 * max(1.0, float(R.sample_latents(ref, noise).abs().max())))
