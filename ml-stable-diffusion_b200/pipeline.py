@@ -69,8 +69,10 @@ class B200StableDiffusionPipeline:
     """Drop-in for ``CoreMLStableDiffusionPipeline`` on one B200."""
 
     def __init__(self, unet: UNetModel, vae_decoder: VAEDecoderModel, scheduler="DDIM", text_encoder=None,
-                 tokenizer=None, force_zeros_for_empty_prompt=True, xl=False, controlnet=None, loop_graph=True):
+                 tokenizer=None, force_zeros_for_empty_prompt=True, xl=False, controlnet=None, loop_graph=True,
+                 vae_encoder=None):
         self.unet = unet
+        self.vae_encoder = vae_encoder  # VAEEncoderModel or None (image-to-image, StableDiffusionPipeline.swift:371-376)
         self.loop_graph = bool(loop_graph) and unet.use_cuda_graph  # whole-loop CUDA graph (denoise())
         self._loop_graphs = {}
         self.controlnet = list(controlnet) if controlnet else None  # pipeline.py:66,106: Optional[List[model]]
@@ -100,7 +102,7 @@ class B200StableDiffusionPipeline:
     @classmethod
     def from_random_init(cls, model_version="sd21-base", images_per_call=1, device="cuda", seed=0,
                          scheduler="DDIM", height=512, width=512, unet_cfg=None, vae_cfg=None, controlnet_cfgs=None,
-                         text_encoder_cfg=None, tokenizer=None):
+                         text_encoder_cfg=None, tokenizer=None, with_vae_encoder=False):
         """Random-init weights of the named architecture (no checkpoints exist offline).  ``controlnet_cfgs``:
         list of ControlNet configs (seeded seed+2, seed+3, ...); switches the UNet to its control variant.
         ``text_encoder_cfg``: a CLIP text config (config.OPENCLIP_H_TEXT for SD-2.x) -> the text encoder runs on the
@@ -133,8 +135,13 @@ class B200StableDiffusionPipeline:
             enc = TextEncoderModel(text_encoder_cfg, C.random_clip_text_state_dict(text_encoder_cfg, seed=seed + 100,
                                                                                    dtype=torch.float16),
                                    batch=1, device=device)
+        venc = None
+        if with_vae_encoder:
+            from .vae import VAEEncoderModel
+            esd = C.random_state_dict(C.vae_encoder_param_shapes(vae_cfg), seed=seed + 50, dtype=torch.float16)
+            venc = VAEEncoderModel(vae_cfg, esd, batch=images_per_call, height=height, width=width, device=device)
         return cls(unet, vae, scheduler=scheduler, xl=unet.engine.xl, controlnet=nets, text_encoder=enc,
-                   tokenizer=tokenizer)
+                   tokenizer=tokenizer, vae_encoder=venc)
 
     # ---------------------------------------------------------------- reference-named helpers
     def check_inputs(self, prompt, height, width, callback_steps):
@@ -259,14 +266,14 @@ class B200StableDiffusionPipeline:
 
     def denoise(self, text_embeddings, latents, num_inference_steps, guidance_scale, callback=None,
                 callback_steps=1, time_ids=None, text_embeds=None, return_denoised=False, record=None,
-                controlnet_cond=None):
-        """Runs the N-step loop entirely on the device.  ``text_embeddings`` (2B, D, 1, S) and ``latents``
+                controlnet_cond=None, start_step=0):
+        """Runs the N-step loop (from ``start_step``: image-to-image) entirely on the device.  ``text_embeddings`` (2B, D, 1, S) and ``latents``
         (B, C, h, w) may be numpy (copied once, before the loop) or CUDA tensors.  ``record`` (a list) receives
         (timestep, noise_pred, latents_after_step) clones per step -- a debugging / testing aid.  Without
         callback / record / ControlNet the whole loop replays as ONE CUDA graph: the scheduler
         history lives on the device and no host synchronisation happens between the first and the last step."""
         sched = S.make_scheduler(self.scheduler_name, num_inference_steps)
-        plan = list(sched.plan())
+        plan = list(sched.plan(start=start_step)) if start_step else list(sched.plan())
         n = self.images_per_call
         self._ctx.copy_(torch.as_tensor(text_embeddings), non_blocking=True)
         self._latents.copy_(torch.as_tensor(latents), non_blocking=True)
@@ -278,7 +285,7 @@ class B200StableDiffusionPipeline:
             if u.engine.xl:
                 u._time_ids.copy_(torch.as_tensor(time_ids).reshape(u._time_ids.shape))
                 u._text_embeds.copy_(torch.as_tensor(text_embeds))
-            key = (self.scheduler_name, int(num_inference_steps), float(guidance_scale))
+            key = (self.scheduler_name, int(num_inference_steps), float(guidance_scale), int(start_step))
             self._loop_graph_for(key, plan, guidance_scale).replay()
             return self._denoised if return_denoised else self._latents
         self._hist.zero_()
@@ -313,7 +320,11 @@ class B200StableDiffusionPipeline:
                  negative_prompt=None, num_images_per_prompt=1, eta=0.0, latents=None, output_type="pil",
                  return_dict=True, callback=None, callback_steps=1, controlnet_cond=None,
                  original_size: Optional[Tuple[int, int]] = None, crops_coords_top_left: Tuple[int, int] = (0, 0),
-                 target_size: Optional[Tuple[int, int]] = None, unet_batch_one=False, prompt_embeds=None, **kwargs):
+                 target_size: Optional[Tuple[int, int]] = None, unet_batch_one=False, prompt_embeds=None,
+                 starting_image=None, strength=0.5, **kwargs):
+        """``starting_image`` ((B, 3, H, W) in [-1, 1], the vae_encoder input) + ``strength`` select the Swift
+        pipeline's image-to-image mode (StableDiffusionPipeline.swift:250-262, 361-378): the encoded image is noised
+        to timestep ``timeSteps[startStep]`` and only the remaining steps run."""
         self.check_inputs(prompt, height, width, callback_steps)
         height = height or self.height
         width = width or self.width
@@ -343,10 +354,23 @@ class B200StableDiffusionPipeline:
             if text_embeds is None:
                 text_embeds = torch.zeros(2 * self.images_per_call, 1280, device=self.device)
         lat = self.prepare_latents(len(prompts), self.unet.in_channels, height, width, latents)
+        start_step = 0
+        if starting_image is not None:
+            if self.vae_encoder is None:
+                raise ValueError("a starting image was provided but the pipeline has no vae_encoder")
+            sched = S.make_scheduler(self.scheduler_name, num_inference_steps)
+            start_step = sched.start_step(strength)
+            if start_step >= num_inference_steps:
+                raise ValueError(f"strength {strength} leaves no denoising steps")
+            # same draw order as the Swift pipeline: the noise samples first (above), then the encoder's noise
+            enc_noise = np.random.randn(*lat.shape).astype(np.float32)
+            x0 = self.vae_encoder.encode(np.asarray(starting_image, dtype=self.vae_encoder.expected_inputs["x"]["dtype"]),
+                                         enc_noise, self.vae_decoder.engine.scaling).numpy()
+            lat = sched.add_noise(x0.astype(np.float32), lat, strength)
         if controlnet_cond:  # pipeline.py:488-494
             controlnet_cond = self.prepare_control_cond(controlnet_cond, do_cfg, len(prompts), 1)
         final = self.denoise(text_embeddings, lat, num_inference_steps, guidance_scale, callback, callback_steps,
-                             time_ids, text_embeds, controlnet_cond=controlnet_cond or None)
+                             time_ids, text_embeds, controlnet_cond=controlnet_cond or None, start_step=start_step)
         image = self.decode_latents(final).cpu().numpy()  # single device->host copy of the result
         has_nsfw = None  # the safety checker is out of scope
         if output_type == "pil":

@@ -69,8 +69,25 @@ class _Base:
     def timesteps(self):
         return [p.timestep for p in self.plan()]
 
-    def plan(self) -> List[StepPlan]:
+    def plan(self, start: int = 0) -> List[StepPlan]:
+        """Steps ``start`` .. end of the schedule, with the multistep state starting empty at ``start`` (what a
+        fresh Swift scheduler does when the pipeline feeds it ``calculateTimesteps(strength)``)."""
         raise NotImplementedError
+
+    # ---- image-to-image (Scheduler.swift:83-114) ----
+    def start_step(self, strength: float) -> int:
+        """max(inferenceStepCount - Int(Float(inferenceStepCount) * strength), 0)."""
+        return max(self.n - int(np.float32(self.n) * np.float32(strength)), 0)
+
+    def calculate_timesteps(self, strength=None):
+        ts = self.timesteps
+        return ts if strength is None else ts[self.start_step(strength):]
+
+    def add_noise(self, original_sample, noise, strength):
+        """sqrt(abar_t) * x0 + sqrt(1 - abar_t) * noise at t = timeSteps[startStep]."""
+        t = self.timesteps[self.start_step(strength)]
+        a = np.float32(self.abar[t])
+        return np.float32(np.sqrt(a)) * original_sample + np.float32(np.sqrt(np.float32(1.0) - a)) * noise
 
 
 class DDIMScheduler(_Base):
@@ -80,11 +97,11 @@ class DDIMScheduler(_Base):
         super().__init__(num_inference_steps, **kw)
         self.steps_offset = steps_offset
 
-    def plan(self):
+    def plan(self, start=0):
         ratio = self.n_train // self.n
         ts = [int(round(i * ratio)) + self.steps_offset for i in range(self.n)][::-1]
         out = []
-        for t in ts:
+        for t in ts[start:]:
             tp = t - ratio
             a_t = self.abar[t]
             a_p = self.abar[tp] if tp >= 0 else self.abar[0]
@@ -101,7 +118,7 @@ class DPMSolverMultistepScheduler(_Base):
     steps) the last two steps are first order (DPMSolverMultistepScheduler.swift:216-244).
     History ring: x0 of the previous step in slots 0/1."""
 
-    def plan(self):
+    def plan(self, start=0):
         n = self.n
         ts = [int(round(v)) for v in np.linspace(0, self.n_train - 1, n + 1)[1:][::-1]]
         alpha = np.sqrt(self.abar)
@@ -110,6 +127,8 @@ class DPMSolverMultistepScheduler(_Base):
         out = []
         lower_order_stepped = 0
         for i, t in enumerate(ts):
+            if i < start:
+                continue
             p = ts[i + 1] if i + 1 < n else 0
             lower_final = (i == n - 1) and n < 15
             lower_second = (i == n - 2) and n < 15
@@ -155,7 +174,10 @@ class PNDMScheduler(_Base):
         denom = a_t * math.sqrt(b_p) + math.sqrt(a_t * b_t * a_p)
         return sample_coeff, -(a_p - a_t) / denom
 
-    def plan(self):
+    def plan(self, start=0):
+        if start != 0:
+            raise ValueError("image-to-image start steps are not implemented for PNDM (its timestep list repeats "
+                             "the second entry; use DDIM or DPMSolverMultistep)")
         ratio = self.n_train // self.n
         fwd = [int(round(i * float(ratio))) + self.steps_offset for i in range(self.n)]
         ts = fwd[:-1]

@@ -133,3 +133,28 @@ def test_prepare_latents_follows_the_reference_rng_vector():
     assert np.allclose(got, expected.astype(np.float16).astype(np.float32), atol=0, rtol=0), got
     with pytest.raises(ValueError, match="Unexpected latents shape"):
         B200StableDiffusionPipeline.prepare_latents(stub, 1, 4, 400, 400, latents=np.zeros((1, 4, 8, 8)))
+
+
+def test_image_to_image_start_step_add_noise_and_truncated_plans():
+    """Scheduler.swift:83-114: startStep = max(n - Int(Float(n) * strength), 0), timesteps[startStep...],
+    noisy = sqrt(abar_t) x0 + sqrt(1 - abar_t) noise at t = timesteps[startStep]."""
+    from b200sd import scheduler as S
+
+    d = S.DDIMScheduler(20)
+    assert d.start_step(0.5) == 10 and d.start_step(1.0) == 0 and d.start_step(0.0) == 20 - 0
+    assert d.start_step(0.75) == 5 and d.start_step(0.3) == 20 - int(np.float32(20) * np.float32(0.3))
+    assert d.calculate_timesteps(0.5) == d.timesteps[10:] and d.calculate_timesteps() == d.timesteps
+    x0, nz = np.full((1, 4, 2, 2), 2.0, np.float32), np.full((1, 4, 2, 2), -1.0, np.float32)
+    t = d.timesteps[10]
+    a = float(S.alphas_cumprod()[t])
+    assert np.allclose(d.add_noise(x0, nz, 0.5), np.sqrt(a) * 2.0 - np.sqrt(1 - a), rtol=1e-6)
+    assert [p.timestep for p in d.plan(start=10)] == d.timesteps[10:]
+    full, cut = d.plan(), d.plan(start=10)
+    assert all(abs(a_.cx - b_.cx) < 1e-15 and abs(a_.ce - b_.ce) < 1e-15 for a_, b_ in zip(full[10:], cut))
+    m = S.DPMSolverMultistepScheduler(20)
+    cut = m.plan(start=8)
+    assert [p.timestep for p in cut] == m.timesteps[8:]
+    assert cut[0].n_hist == 0 and cut[1].n_hist == 2          # the multistep state starts empty at the start step
+    assert m.plan()[8].n_hist == 2                            # ... unlike step 8 of the full schedule
+    with pytest.raises(ValueError, match="PNDM"):
+        S.PNDMScheduler(20).plan(start=3)

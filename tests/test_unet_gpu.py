@@ -427,3 +427,45 @@ def test_vae_encoder_tiny_vs_oracle(cuda_lib):
     lat = m.encode(x.half().numpy(), noise)
     _check(lat.numpy(), R.sample_latents(ref, noise).numpy(), "tiny vae encoder sample",
            max_abs=2e-2 * max(1.0, float(R.sample_latents(ref, noise).abs().max())))
+
+
+def test_pipeline_tiny_image_to_image_vs_oracle(cuda_lib):
+    """Swift image-to-image mode (StableDiffusionPipeline.swift:250-262, 361-378; Scheduler.swift:83-114): encode,
+    noise to timeSteps[startStep], run the remaining steps, decode -- against the same procedure on the oracle."""
+    from b200sd.pipeline import B200StableDiffusionPipeline
+    from b200sd import scheduler as S
+
+    pipe = B200StableDiffusionPipeline.from_random_init("tiny", images_per_call=1, height=64, width=64, seed=31,
+                                                        with_vae_encoder=True)
+    img0 = (torch.rand(1, 3, 64, 64, generator=torch.Generator().manual_seed(32)) * 2 - 1).half().numpy()
+    steps, g, strength = 8, 6.0, 0.5
+    np.random.seed(33)
+    out = pipe("a cat", height=64, width=64, num_inference_steps=steps, guidance_scale=g, starting_image=img0,
+               strength=strength, output_type="np").images
+    assert out.shape == (1, 64, 64, 3)
+    # oracle: same RNG stream (noise samples first, then the encoder noise), same schedule truncation
+    np.random.seed(33)
+    noise = np.random.randn(1, 4, 16, 16).astype(np.float16).astype(np.float32)
+    enc_noise = np.random.randn(1, 4, 16, 16).astype(np.float32)
+    ucfg, vcfg = config.TINY_UNET, config.TINY_VAE
+    usd = config.random_state_dict(config.unet_param_shapes(ucfg), seed=31, dtype=torch.float16)
+    vsd = config.random_state_dict(config.vae_decoder_param_shapes(vcfg), seed=32, dtype=torch.float16)
+    esd = config.random_state_dict(config.vae_encoder_param_shapes(vcfg), seed=81, dtype=torch.float16)
+    sched = S.DDIMScheduler(steps)
+    start = sched.start_step(strength)
+    assert start == 4
+    emb = torch.from_numpy(pipe._encode_prompt(["a cat"], True, None)).float()
+    abar = R.alphas_cumprod()
+    with torch.no_grad():
+        x0 = R.sample_latents(R.vae_encode(esd, vcfg, torch.from_numpy(img0).float()), torch.from_numpy(enc_noise))
+        x = torch.from_numpy(sched.add_noise(x0.numpy(), noise, strength))
+        for t in sched.timesteps[start:]:
+            eps = R.unet_forward(usd, ucfg, torch.cat([x, x]).half().float(), torch.tensor([float(t)] * 2), emb)
+            x = R.ddim_step(R.cfg_combine(eps[:1], eps[1:], g), t, x, abar, steps)
+        ref = R.postprocess_image(R.vae_decode(vsd, vcfg, x / 0.18215)).numpy()
+    err = float(np.abs(out - ref).max())
+    print(f"img2img tiny: image max_abs={err:.3e}")
+    assert err < 3e-2
+    plain = B200StableDiffusionPipeline.from_random_init("tiny", images_per_call=1, height=64, width=64, seed=31)
+    with pytest.raises(ValueError, match="no vae_encoder"):
+        plain("a cat", height=64, width=64, num_inference_steps=2, starting_image=img0)
