@@ -70,8 +70,10 @@ class B200StableDiffusionPipeline:
 
     def __init__(self, unet: UNetModel, vae_decoder: VAEDecoderModel, scheduler="DDIM", text_encoder=None,
                  tokenizer=None, force_zeros_for_empty_prompt=True, xl=False, controlnet=None, loop_graph=True,
-                 vae_encoder=None):
+                 vae_encoder=None, text_encoder_2=None, tokenizer_2=None):
         self.unet = unet
+        self.text_encoder_2 = text_encoder_2  # SDXL: CLIPTextModelWithProjection slot (pipeline.py:64-65, 136-141)
+        self.tokenizer_2 = tokenizer_2
         self.vae_encoder = vae_encoder  # VAEEncoderModel or None (image-to-image, StableDiffusionPipeline.swift:371-376)
         self.loop_graph = bool(loop_graph) and unet.use_cuda_graph  # whole-loop CUDA graph (denoise())
         self._loop_graphs = {}
@@ -172,6 +174,44 @@ class B200StableDiffusionPipeline:
                 unconds.append(self._encode_one(ng))
         emb = np.stack(unconds + conds, 0)  # (2B, S, D)
         return np.ascontiguousarray(emb.transpose(0, 2, 1)[:, :, None, :]).astype(np.float16)
+
+    def _encode_prompt_xl(self, prompts, do_cfg, negative_prompt=None, prompts_2=None, negative_prompt_2=None):
+        """SDXL branch of pipeline.py:123-257: both encoders' ``hidden_embeds`` concatenated along the feature axis
+        (encoder 1 first), the pooled output of the LAST encoder, zeros for the negative branch when no negative
+        prompt is given and force_zeros_for_empty_prompt.  The refiner has only encoder 2 (text_encoder is None).
+        -> ((2B, D1 + D2, 1, S) fp16, (2B, P) fp32), uncond half first."""
+        pairs = [(self.tokenizer, self.text_encoder), (self.tokenizer_2, self.text_encoder_2)]
+        if self.text_encoder is None:
+            pairs = pairs[1:]
+        texts = [prompts, prompts_2 if prompts_2 is not None else prompts][-len(pairs):]
+
+        def run(text_lists):
+            per_prompt, pooled = [], []
+            for i in range(len(text_lists[0])):
+                feats = []
+                for (tok, enc), tl in zip(pairs, text_lists):
+                    o = enc(input_ids=np.asarray(tok(tl[i]), dtype=np.float32))
+                    feats.append(np.asarray(o["hidden_embeds"], dtype=np.float32)[0])
+                    last_pooled = np.asarray(o["pooled_outputs"], dtype=np.float32)[0]
+                per_prompt.append(np.concatenate(feats, axis=-1))  # (S, D1 + D2)
+                pooled.append(last_pooled)
+            return np.stack(per_prompt, 0), np.stack(pooled, 0)
+
+        emb, pooled = run(texts)
+        if do_cfg:
+            if negative_prompt is None and self.force_zeros_for_empty_prompt:
+                neg, neg_pooled = np.zeros_like(emb), np.zeros_like(pooled)
+            else:
+                neg_1 = negative_prompt or ""
+                neg_2 = negative_prompt_2 or neg_1
+                as_list = lambda v: [v] * len(prompts) if isinstance(v, str) else list(v)  # noqa: E731
+                neg_1, neg_2 = as_list(neg_1), as_list(neg_2)
+                if len(neg_1) != len(prompts):
+                    raise ValueError(f"`negative_prompt` has batch size {len(neg_1)}, but `prompt` has batch size "
+                                     f"{len(prompts)}")
+                neg, neg_pooled = run([neg_1, neg_2][-len(pairs):])
+            emb, pooled = np.concatenate([neg, emb], 0), np.concatenate([neg_pooled, pooled], 0)
+        return np.ascontiguousarray(emb.transpose(0, 2, 1)[:, :, None, :]).astype(np.float16), pooled
 
     def prepare_latents(self, batch, channels, height, width, latents=None):
         """pipeline.py:322-344: np.random.randn(...).astype(fp16) * init_noise_sigma."""
@@ -340,10 +380,14 @@ class B200StableDiffusionPipeline:
             raise ValueError(f"this pipeline instance generates {self.images_per_call} image(s) per call, "
                              f"got {len(prompts)} prompt(s)")
         do_cfg = guidance_scale > 1.0  # pipeline.py:443
-        if prompt_embeds is None:
-            text_embeddings = self._encode_prompt(prompts, do_cfg, negative_prompt)
-        else:
+        xl_pooled = None
+        if prompt_embeds is not None:
             text_embeddings = prompt_embeds
+        elif self.xl and self.text_encoder_2 is not None:
+            text_embeddings, xl_pooled = self._encode_prompt_xl(prompts, do_cfg, negative_prompt,
+                                                                negative_prompt_2=kwargs.get("negative_prompt_2"))
+        else:
+            text_embeddings = self._encode_prompt(prompts, do_cfg, negative_prompt)
         time_ids = text_embeds = None
         if self.xl:
             original_size = original_size or (height, width)
@@ -351,6 +395,8 @@ class B200StableDiffusionPipeline:
             ids = list(original_size) + list(crops_coords_top_left) + list(target_size)
             time_ids = torch.tensor([ids] * (2 * self.images_per_call), dtype=torch.float32, device=self.device)
             text_embeds = kwargs.get("pooled_prompt_embeds")
+            if text_embeds is None and xl_pooled is not None:
+                text_embeds = torch.as_tensor(xl_pooled, dtype=torch.float32, device=self.device)
             if text_embeds is None:
                 text_embeds = torch.zeros(2 * self.images_per_call, 1280, device=self.device)
         lat = self.prepare_latents(len(prompts), self.unet.in_channels, height, width, latents)

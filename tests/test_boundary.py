@@ -156,3 +156,35 @@ def test_gemm_planner_invariants_over_unet_shapes():
         assert stages * per_stage + f["epi_smem"] <= 220 * 1024, plan
         if f["cluster"]:
             assert splits in (2, 4, 8) and bn % 32 == 0 and 512 * (bn + 4) <= stages * per_stage, plan
+
+
+def test_sdxl_prompt_encoding_follows_the_reference_branch():
+    """pipeline.py:123-257 (xl): hidden_embeds of both encoders concatenated on the feature axis, pooled output of the
+    last encoder, zero negatives by default, uncond half first.  Host logic only (stub encoders, no GPU)."""
+    import types
+
+    from b200sd.pipeline import B200StableDiffusionPipeline as P
+
+    def enc(d, p, scale):
+        def call(input_ids):
+            s = float(np.asarray(input_ids).sum())
+            return {"hidden_embeds": np.full((1, 77, d), scale * s, np.float32),
+                    "pooled_outputs": np.full((1, p), -scale * s, np.float32)}
+        return call
+
+    tok = lambda text: np.full((1, 77), float(len(text)), np.float32)  # noqa: E731
+    stub = types.SimpleNamespace(tokenizer=tok, tokenizer_2=tok, text_encoder=enc(6, 3, 1.0), text_encoder_2=enc(10, 5, 2.0),
+                                 force_zeros_for_empty_prompt=True)
+    emb, pooled = P._encode_prompt_xl(stub, ["ab", "abcd"], True)
+    assert emb.shape == (4, 16, 1, 77) and emb.dtype == np.float16 and pooled.shape == (4, 5)
+    assert not emb[:2].any() and not pooled[:2].any()                      # zero negatives, uncond half first
+    assert emb[2, 0, 0, 0] == 2 * 77 and emb[2, 6, 0, 0] == 2 * 2 * 77    # encoder 1 features first, then encoder 2
+    assert pooled[3, 0] == -2.0 * 4 * 77                                   # pooled output of the LAST encoder
+    emb2, pooled2 = P._encode_prompt_xl(stub, ["ab"], True, negative_prompt="xyz")
+    assert emb2.shape == (2, 16, 1, 77) and emb2[0, 0, 0, 0] == 3 * 77 and pooled2[0, 0] == -2.0 * 3 * 77
+    refiner = types.SimpleNamespace(tokenizer=None, tokenizer_2=tok, text_encoder=None, text_encoder_2=enc(10, 5, 2.0),
+                                    force_zeros_for_empty_prompt=True)
+    emb3, pooled3 = P._encode_prompt_xl(refiner, ["ab"], False)
+    assert emb3.shape == (1, 10, 1, 77) and pooled3.shape == (1, 5)
+    with pytest.raises(ValueError, match="batch size"):
+        P._encode_prompt_xl(stub, ["ab", "cd"], True, negative_prompt=["x"])

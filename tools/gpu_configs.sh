@@ -1,3 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-( timeout 200 python -m pytest tests/test_unet_gpu.py -m gpu -q -x -k "image_to_image or pipeline_tiny_end" 2>&1 | tail -15 ) | tee gpurun_out/tests_new.log
+( timeout 400 python -m pytest tests -m gpu -q -x 2>&1 | tail -4 ) 2>&1 | tee gpurun_out/tests.log
+( timeout 100 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2 ) | tee gpurun_out/smoke.log
