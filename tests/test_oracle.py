@@ -183,3 +183,24 @@ def test_clip_text_hidden_states_and_pooled_match_transformers(cfg_name):
     assert float((out["last_hidden_state"] - ref["last_hidden_state"]).abs().max()) < 2e-5
     key = "text_embeds" if cfg.get("projection_dim") else "pooler_output"
     assert out[key].shape == ref[key].shape and float((out[key] - ref[key]).abs().max()) < 2e-5
+
+
+def test_restated_controlnet_sd21_matches_reference_golden():
+    """BASELINE configs[4] network at full size (361 M parameters, 512x512 condition image): the restatement
+    against the residuals of the unmodified reference module (tests/golden/make_golden_controlnet.py)."""
+    gold = _load("controlnet_sd21.npz")
+    cfg = config.SD21_CONTROLNET
+    sd = config.random_state_dict(config.controlnet_param_shapes(cfg), seed=int(gold["weight_seed"]), dtype=torch.float16)
+    g = torch.Generator().manual_seed(int(gold["input_seed"]))
+    x = torch.randn(2, 4, 64, 64, generator=g)
+    c = torch.randn(2, 1024, 1, 77, generator=g)
+    cond = torch.rand(2, 3, 512, 512, generator=torch.Generator().manual_seed(int(gold["cond_seed"])))
+    st = int(gold["stride"])
+    with torch.no_grad():
+        outs = R.controlnet_forward(sd, cfg, x.half().float(), torch.tensor([501.0, 501.0]), c.half().float(),
+                                    cond.half().float())
+    assert len(outs) == 13
+    for i, o in enumerate(outs):
+        ref = torch.from_numpy(gold[f"residual_{i}"].astype(np.float32))
+        err = float((o[:, :, ::st, ::st] - ref).abs().max())
+        assert err < 2e-3 * max(1.0, float(ref.abs().max())), (i, err)  # the fixture is stored in fp16
