@@ -12,6 +12,21 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu")
 
 
+def pytest_sessionstart(session):
+    """Test convenience only: a fresh checkout has no libb200sd.so (build artefacts are not in git).  If nvcc is
+    here, build it once so the boundary tests (dlopen + exported symbols + SASS check) can run; the product itself
+    never builds or falls back on its own -- lib.load() raises when the library is missing."""
+    import shutil
+
+    lib = os.path.join(ROOT, "ml-stable-diffusion_b200", "libb200sd.so")
+    if not os.path.exists(lib) and (shutil.which("nvcc") or os.path.exists("/usr/local/cuda/bin/nvcc")):
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("_b200sd_build", os.path.join(ROOT, "ml-stable-diffusion_b200", "build.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        mod.build()
+
+
 @pytest.fixture(scope="session")
 def cuda_lib():
     import torch
