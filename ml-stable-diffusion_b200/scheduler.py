@@ -175,14 +175,14 @@ class PNDMScheduler(_Base):
         return sample_coeff, -(a_p - a_t) / denom
 
     def plan(self, start=0):
-        if start != 0:
-            raise ValueError("image-to-image start steps are not implemented for PNDM (its timestep list repeats "
-                             "the second entry; use DDIM or DPMSolverMultistep)")
         ratio = self.n_train // self.n
         fwd = [int(round(i * float(ratio))) + self.steps_offset for i in range(self.n)]
         ts = fwd[:-1]
         ts = ts + [ts[-1]] if ts else []
         ts = (ts + [fwd[-1]])[::-1]
+        # image-to-image: the Swift pipeline slices this list (timeSteps[startStep...], Scheduler.swift:109-114) and
+        # feeds it to a fresh scheduler, whose counter-driven branches then apply to whatever comes first
+        ts = ts[start:]
         alpha = np.sqrt(self.abar)
         sigma = np.sqrt(1.0 - self.abar)
         out = []

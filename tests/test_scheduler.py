@@ -9,11 +9,11 @@ from b200sd import scheduler as S
 from oracle import restated as R
 
 
-def _run_plan(sched, eps_fn, x0, guidance=7.5):
+def _run_plan(sched, eps_fn, x0, guidance=7.5, start=0):
     x = x0.copy()
     hist = [np.zeros_like(x) for _ in range(4)]
     xs, x0s = [], []
-    for st in sched.plan():
+    for st in sched.plan(start=start):
         eu, ec = eps_fn(x, st.timestep)
         x, den = S.apply_plan_host(st, guidance, eu, ec, x, hist)
         xs.append(x.copy())
@@ -156,5 +156,32 @@ def test_image_to_image_start_step_add_noise_and_truncated_plans():
     assert [p.timestep for p in cut] == m.timesteps[8:]
     assert cut[0].n_hist == 0 and cut[1].n_hist == 2          # the multistep state starts empty at the start step
     assert m.plan()[8].n_hist == 2                            # ... unlike step 8 of the full schedule
-    with pytest.raises(ValueError, match="PNDM"):
-        S.PNDMScheduler(20).plan(start=3)
+
+
+@pytest.mark.parametrize("n,start", [(20, 10), (20, 3), (10, 5), (14, 9)])
+def test_truncated_dpm_and_pndm_plans_match_fresh_oracle_schedulers(n, start):
+    """A fresh scheduler fed timeSteps[startStep...] (Scheduler.swift:109-114): the multistep state starts empty."""
+    rng = np.random.RandomState(1)
+    x = rng.randn(4, 8, 8)
+    f = _eps_fn(2)
+    # DPM-Solver++: step index into the FULL timestep list, empty history
+    s = S.DPMSolverMultistepScheduler(n)
+    s.abar = R.alphas_cumprod().double().numpy()
+    ref = R.DPMSolverPP2M(n, abar=R.alphas_cumprod().double())
+    xs, _ = _run_plan(s, f, x, start=start)
+    xr = torch.from_numpy(x.copy())
+    for j, i in enumerate(range(start, n)):
+        eu, ec = f(xr.numpy(), ref.timesteps[i])
+        xr = ref.step(torch.from_numpy(R.cfg_combine(eu, ec, 7.5)), i, xr)
+        assert np.allclose(xs[j], xr.numpy(), rtol=1e-8, atol=1e-8), ("dpm", n, start, i)
+    # PNDM: counter-driven branches applied to the sliced list
+    p = S.PNDMScheduler(n)
+    p.abar = R.alphas_cumprod().double().numpy()
+    refp = R.PNDM(n, abar=R.alphas_cumprod().double())
+    xs, _ = _run_plan(p, f, x, start=start)
+    assert [st.timestep for st in p.plan(start=start)] == refp.timesteps[start:]
+    xr = torch.from_numpy(x.copy())
+    for j, t in enumerate(refp.timesteps[start:]):
+        eu, ec = f(xr.numpy(), t)
+        xr = refp.step(torch.from_numpy(R.cfg_combine(eu, ec, 7.5)), t, xr)
+        assert np.allclose(xs[j], xr.numpy(), rtol=1e-8, atol=1e-8), ("pndm", n, start, j)
