@@ -469,3 +469,27 @@ def test_pipeline_tiny_image_to_image_vs_oracle(cuda_lib):
     plain = B200StableDiffusionPipeline.from_random_init("tiny", images_per_call=1, height=64, width=64, seed=31)
     with pytest.raises(ValueError, match="no vae_encoder"):
         plain("a cat", height=64, width=64, num_inference_steps=2, starting_image=img0)
+
+
+def test_controlnet_sd21_vs_reference_golden(cuda_lib):
+    """BASELINE configs[4] network at full size (SD-2.1 ControlNet, 361 M parameters, 512x512 condition image):
+    the 13 residuals against the unmodified reference module run on the CPU (make_golden_controlnet.py; measured
+    on a B200: worst max-abs 4.4e-3 on a residual of magnitude 2.2)."""
+    from b200sd.controlnet import ControlNetModel
+
+    gold = np.load(os.path.join(GOLD, "controlnet_sd21.npz"))
+    cfg = config.SD21_CONTROLNET
+    sd = config.random_state_dict(config.controlnet_param_shapes(cfg), seed=int(gold["weight_seed"]), dtype=torch.float16)
+    g = torch.Generator().manual_seed(int(gold["input_seed"]))
+    x = torch.randn(2, 4, 64, 64, generator=g)
+    c = torch.randn(2, 1024, 1, 77, generator=g)
+    cond = torch.rand(2, 3, 512, 512, generator=torch.Generator().manual_seed(int(gold["cond_seed"])))
+    m = ControlNetModel(cfg, sd, batch=2, height=64, width=64)
+    out = m(sample=x.half().numpy(), timestep=np.array([501.0, 501.0], np.float16),
+            encoder_hidden_states=c.half().numpy(), controlnet_cond=cond.half().numpy())
+    st = int(gold["stride"])
+    assert len(out) == 13
+    for i in range(13):
+        ref = gold[f"residual_{i}"].astype(np.float32)
+        _check(out[f"additional_residual_{i}"][:, :, ::st, ::st], ref, f"SD-2.1 controlnet residual {i}",
+               max_abs=MAX_ABS * max(1.0, float(np.abs(ref).max())))

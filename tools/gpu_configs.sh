@@ -1,3 +1,3 @@
 #!/bin/bash
 mkdir -p gpurun_out
-( timeout 60 python -m pytest tests/test_unet_gpu.py -m gpu -q -x -k "pipeline_tiny_end or xl_text" 2>&1 | tail -4 ) | tee gpurun_out/tests_new.log
+( timeout 45 python tools/check_controlnet_golden.py 2>&1 | tail -15 ) | tee gpurun_out/cn_golden.log
