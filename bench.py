@@ -271,6 +271,16 @@ def run_gpu_arm(args, rank, local_rank, world):
     e1.record()
     barrier()
     ms_dev = e0.elapsed_time(e1)
+    if args.quick:
+        if rank == 0:
+            print(json.dumps({"quick": True, "iter_per_s": round(world * args.steps / (ms_dev * 1e-3), 2),
+                              "ms_per_step": round(ms_dev / args.steps, 4), "launches_per_step": int(launches_per_step),
+                              "pdl": os.environ.get("B200SD_PDL", "0"), "smem_kb": os.environ.get("B200SD_SMEM_KB", "")}),
+                  flush=True)
+        sampler.stop()
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     # ---- e2e: the reference-facing boundary call with pinned host buffers, copies inside the timed region ----
     h_sample = torch.empty(2, 4, 64, 64, dtype=torch.float16).pin_memory()
@@ -391,6 +401,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200sd", choices=["b200sd", "reference"])
     ap.add_argument("--no-batched", action="store_true", help="skip the 8-prompts-per-GPU images/s measurement")
+    ap.add_argument("--quick", action="store_true", help="device-resident iter/s only (tuning runs; not a bench line)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -86,12 +86,49 @@ typedef struct {
     void* out;             /* [M, N_out] fp16 / fp32 */
     float* workspace;      /* split-K scratch (may be NULL when b200sd_gemm_workspace_bytes() == 0) */
     size_t workspace_bytes;
+    /* ---- fused normalisation (all optional; zero / NULL = off) ---------------------------------------------------
+     * GroupNorm -> SiLU -> conv (unet.py:470-489, 1044-1046) and LayerNormANE -> linear (layer_norm.py:66-78,
+     * unet.py:575-590) run without a normalisation launch: the PRODUCER of a tensor leaves its statistics behind
+     * (per-channel sums for GroupNorm, per-row sums for LayerNorm) and the CONSUMER applies them -- in the operand
+     * path of the halo convolution (GroupNorm + SiLU, applied once per activation patch in shared memory) or as a
+     * row scale in the epilogue (LayerNorm folded into the weights). */
+    int32_t halo;          /* mode 1, stride 1, pad 1: halo-reuse kernel: one (rows + 2) x (w + 1) activation patch per
+                              64-channel chunk in shared memory, the nine taps are row-shifted MMA descriptors; `wgt`
+                              must be pre-tiled chunk-major: k-block = chunk * 9 + tap */
+    int32_t upsample2x;    /* halo: a0 is [n_img, h/2, w/2, c0] and is read nearest-x2 upsampled (Upsample2D, unet.py:499) */
+    int32_t gn_groups;     /* halo: > 0 = y = silu?(groupnorm(a0 ++ a1)) feeds the convolution */
+    int32_t gn_silu;
+    float gn_eps;
+    const float* gn_chan0; /* [n_img][c0][2] (sum, sum of squares) per channel of a0 over its h*w pixels */
+    const float* gn_chan1; /* same for a1 */
+    const float* gn_gamma; /* [c0 + c1] */
+    const float* gn_beta;
+    /* statistics of THIS call's fp16 output (from the rounded values, deterministic; needs split_k == 1):
+     * per-channel sums for a consumer GroupNorm: cs_partial [n_img][slots][n][2] scratch (slots from
+     * b200sd_gemm_plan_ex), cs_chan [n_img][n][2] result, cs_tickets [n_img][n_tiles] zero-initialised counters
+     * (self-resetting); cs_hw = output rows per image.  rs_out [n_tiles][m][2]: per-row sums for a consumer
+     * LayerNorm (mode 0). */
+    float* cs_partial;
+    float* cs_chan;
+    uint32_t* cs_tickets;
+    int32_t cs_hw;
+    float* rs_out;
+    /* LayerNorm folded into this GEMM (mode 0): `wgt` holds gamma (.) W, `bias` holds W beta + b, ln_wg[j] = sum_k
+     * of the packed row j, ln_stat [ln_parts][m][2] are the producer's rs_out partials:
+     * out = rstd_r * (acc - mu_r * ln_wg) + bias. */
+    const float* ln_stat;
+    const float* ln_wg;
+    int32_t ln_parts;
+    float ln_eps;
 } b200sd_gemm_args;
 
 int b200sd_gemm(const b200sd_gemm_args* args, void* stream);
 /* host-only: block_n / split count / k-block count the launcher would choose: out[0..3] = block_n, splits,
  * kb_total, n_tiles */
 int b200sd_gemm_plan(const b200sd_gemm_args* args, int32_t* out4);
+/* host-only: out[0..7] = block_n, splits, kb_total, n_tiles, statistics slots per image (0: this plan cannot emit
+ * column statistics), staged epilogue (0/1), pipeline stages, m_tiles */
+int b200sd_gemm_plan_ex(const b200sd_gemm_args* args, int32_t* out8);
 /* host-only: human-readable tiling plan (tile shape, split-K, pipeline depth) the launcher would use */
 int b200sd_gemm_describe_plan(const b200sd_gemm_args* args, char* buf, size_t buf_size);
 /* bytes of fp32 scratch b200sd_gemm would need for these args (0 if no split-K) */

@@ -27,6 +27,19 @@ static constexpr int kGemmThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 
 static constexpr int kEpiThreads = 256;
 static constexpr int kMaxStages = 8;
 static constexpr int kSmemBudget = 220 * 1024;
+static constexpr int kEpiFixed = 2 * 256 * 4 + 256 * 4 + 32;  // bias vectors, LayerNorm fold vector, flags
+
+// Shared-memory budget of one GEMM CTA.  B200SD_SMEM_KB (read per call: tuning scripts flip it) caps the pipeline
+// depth: at <= ~110 KB (and <= 256 TMEM columns) two CTAs fit on one SM, so under programmatic dependent launch the
+// next kernel's CTAs become resident -- and prefetch their weights -- while the previous kernel still runs.
+static int smem_budget() {
+    const char* e = getenv("B200SD_SMEM_KB");
+    if (e && e[0]) {
+        const int kb = atoi(e);
+        if (kb >= 48 && kb <= 220) return kb * 1024;
+    }
+    return kSmemBudget;
+}
 
 struct __align__(64) GemmParams {
     CUtensorMap tmA0, tmA1, tmB;
@@ -45,10 +58,39 @@ struct __align__(64) GemmParams {
     int wgt_tiled;   // B operand pre-tiled: tile (n_tile, kb) starts at row (n_tile * kb_total + kb) * block_n
     int bias_mode;   // 0 none, 1 staged in smem (<= 2 vectors per tile), 2 read from global per chunk
     int res_smem;    // 1: residual tile prefetched into smem with cp.async
+    int acc_bufs;    // accumulator buffers in TMEM: 2 = double-buffered (persistent CTAs with several tiles), 1 otherwise
+    int acc_stride;  // TMEM columns between the buffers
+    int tmem_cols;   // columns to allocate (power of two >= 32): 256 or less lets two CTAs share an SM (PDL overlap)
     void* out;
     const float* bias;
     const __half* residual;
     float* partial;
+    // ---- mode 2 (halo-reuse 3x3 convolution): the image is walked in padded-linear order q = y * (W + 1) + x ----
+    int H, W, Wp, tiles_per_img, patch_rows, patch_bytes, upsample;
+    int desc_bo;            // 1: row-shifted A descriptors carry (address >> 7) & 7 in the matrix-base-offset field
+    const __half* a0;       // raw NHWC sources (loader warps read them with plain loads)
+    const __half* a1;
+    int C1;
+    // ---- GroupNorm (+SiLU) applied to the A operand by the loader warps (mode 2) ----
+    const float* gn_chan0;  // [n_img][C0][2] per-channel (sum, sum of squares) of a0, produced by a0's producer
+    const float* gn_chan1;
+    const float* gn_gamma;  // [C0 + C1]
+    const float* gn_beta;
+    int gn_groups, gn_silu, gn_hw;  // gn_hw: pixels per image the sums run over
+    float gn_eps;
+    // ---- statistics side outputs of the staged epilogue ----
+    float* cs_partial;         // [n_img][cs_slots][N][2] per-tile column sums
+    float* cs_chan;            // [n_img][N][2] per-channel sums over the image (written by the last CTA to arrive)
+    unsigned int* cs_tickets;  // [n_img][n_tiles], zero-initialised, self-resetting
+    int cs_slots, cs_hw;       // partial slots per image; output rows (pixels) per image
+    float* rs_out;             // [n_tiles][M][2] per-row (sum, sum of squares) over this tile's columns
+    // ---- LayerNorm folded into this GEMM: out = rstd_r * (acc - mu_r * wg) + bias', statistics from the producer ----
+    const float* ln_stat;      // [ln_parts][M][2]
+    const float* ln_wg;        // [N] sum_k W'[j, k]
+    int ln_parts, ln_k;
+    float ln_eps;
+    int staged;                // staged epilogue (fp16 tile in shared memory, coalesced row-wise stores)
+    int stage_dedicated;       // the staging tile has its own shared memory (persistent CTAs with several tiles)
 };
 
 struct TileCoord {
@@ -74,6 +116,10 @@ __device__ __forceinline__ TileCoord decode_work(const GemmParams& p, int work, 
         t.split = r / p.n_tiles;
     }
     t.n0 = t.h0 = t.w0 = 0;
+    if (p.mode == 2) {  // n0 = image, w0 = first padded-linear position of the tile inside the image
+        t.n0 = t.m_tile / p.tiles_per_img;
+        t.w0 = (t.m_tile - t.n0 * p.tiles_per_img) * kBM;
+    }
     if (p.mode == 1) {
         int tw = t.m_tile % p.tiles_w;
         int r2 = t.m_tile / p.tiles_w;
@@ -213,6 +259,12 @@ __device__ __forceinline__ bool tile_row(const GemmParams& p, const TileCoord& t
         out_row = t.m_tile * kBM + row;
         return out_row < p.M;
     }
+    if (p.mode == 2) {  // padded-linear position -> pixel; the pad column (x == W) and the tail are junk rows
+        const int q = t.w0 + row;
+        const int y = q / p.Wp, x = q - y * p.Wp;
+        out_row = (t.n0 * p.H + y) * p.W + x;
+        return y < p.H && x < p.W;
+    }
     const int dw = row & ((1 << p.bw_log2) - 1);
     const int dh = (row >> p.bw_log2) & ((1 << p.bh_log2) - 1);
     const int dn = row >> (p.bw_log2 + p.bh_log2);
@@ -242,7 +294,235 @@ __device__ __forceinline__ float4 ld_dsmem_f4(uint32_t local_addr, uint32_t cta_
     return v;
 }
 
-template <bool kGeneric, bool kGeglu, bool kOutF32, bool kPartial, bool kTwoCta = false>
+
+// image a tile row belongs to (statistics are per image); -1 for rows outside the problem
+__device__ __forceinline__ int row_image(const GemmParams& p, const TileCoord& t, int row) {
+    int out_row;
+    if (!tile_row(p, t, row, out_row)) {
+        if (p.mode != 2) return -1;
+        return t.n0;  // a junk row of a mode-2 tile still belongs to the tile's image
+    }
+    if (p.mode == 2) return t.n0;
+    return out_row / p.cs_hw;
+}
+
+// LayerNorm folded into the GEMM (layer_norm.py:66-78 applied to the A operand): the weights were multiplied by gamma
+// at pack time, so out = rstd_r * (acc - mu_r * wg_j) + bias'_j with the row statistics summed from the producer's
+// per-tile partials.  Returns (rstd, -mu * rstd).
+__device__ __forceinline__ float2 ln_row_coeffs(const GemmParams& p, int out_row, bool valid) {
+    if (p.ln_parts == 0 || !valid) return make_float2(1.f, 0.f);
+    float s = 0.f, q = 0.f;
+    for (int part = 0; part < p.ln_parts; ++part) {
+        const float2 v = *reinterpret_cast<const float2*>(p.ln_stat + (static_cast<size_t>(part) * p.M + out_row) * 2);
+        s += v.x, q += v.y;
+    }
+    const float inv = 1.0f / static_cast<float>(p.ln_k);
+    const float mu = s * inv;
+    const float rstd = rsqrtf(fmaxf(q * inv - mu * mu, 0.f) + p.ln_eps);
+    return make_float2(rstd, -mu * rstd);
+}
+
+// ---- staged epilogue (fp16 outputs) ------------------------------------------------------------------------------
+// Phase A: every epilogue thread owns one accumulator row (TMEM lane): TMEM -> registers -> (+LN fold) + bias -> fp16
+//          -> staging tile in shared memory [128][block_n + 8].
+// Phase B: warp w owns rows [16 w, 16 w + 16); its lanes walk a row as 16-byte vectors, so the residual read and the
+//          output store are contiguous row segments; the same pass accumulates the per-channel (column) sums that the
+//          consumer's GroupNorm needs and the per-row sums its LayerNorm needs, from the ROUNDED outputs.
+// Phase C: column sums: lanes -> warps (shared memory, fixed order) -> one partial per (image, tile); the last CTA to
+//          arrive for an (image, n_tile) adds the partials of all tiles in slot order: deterministic, no float atomics.
+__device__ __forceinline__ void staged_epilogue(const GemmParams& p, const TileCoord& t, uint32_t taddr, __half* tile_s,
+                                                float* scratch, unsigned int* flag_s, const float* bias_row,
+                                                const float* wg_s, int ew, int lane, int row, int out_row, bool valid) {
+    const int bn = p.block_n;
+    const int ldt = bn + 8;
+    const int half = ew >> 2;
+    const int ncol0 = t.n_tile * bn;
+    // ---------------- phase A ----------------
+    {
+        const float2 lc = ln_row_coeffs(p, out_row, valid);
+        const bool ln = p.ln_parts != 0;
+        __half* trow = tile_s + row * ldt;
+        auto convert32 = [&](const uint32_t (&v)[32], int c) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+                float x[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    float a = __uint_as_float(v[j + e]);
+                    if (ln) a = fmaf(a, lc.x, lc.y * wg_s[c + j + e]);
+                    if (bias_row != nullptr) a += bias_row[c + j + e];
+                    x[e] = a;
+                }
+                uint4 pk;
+                pk.x = pack_half2(x[0], x[1]);
+                pk.y = pack_half2(x[2], x[3]);
+                pk.z = pack_half2(x[4], x[5]);
+                pk.w = pack_half2(x[6], x[7]);
+                *reinterpret_cast<uint4*>(trow + c + j) = pk;
+            }
+        };
+        uint32_t va[32], vb[32];
+        int c = 32 * half;
+        if (c < bn) tmem_ld32(taddr + c, va);
+        while (c < bn) {
+            tmem_ld_wait();
+            const int c2 = c + 64;
+            if (c2 < bn) tmem_ld32(taddr + c2, vb);
+            convert32(va, c);
+            if (c2 >= bn) break;
+            tmem_ld_wait();
+            const int c3 = c2 + 64;
+            if (c3 < bn) tmem_ld32(taddr + c3, va);
+            convert32(vb, c2);
+            c = c3;
+        }
+    }
+    epi_bar_sync();
+    // ---------------- phase B ----------------
+    const int vpr = bn >> 3;
+    int L = 8;
+    while (L < vpr) L <<= 1;
+    const int rpi = 32 / L;
+    const int lr = lane / L, lcv = lane - lr * L;
+    const bool col_ok = lcv < vpr && (ncol0 + lcv * 8) < p.N;
+    float cs[8], cq[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) cs[e] = cq[e] = 0.f;
+    for (int it = 0; it < 16 / rpi; ++it) {
+        const int r = ew * 16 + it * rpi + lr;
+        int orow;
+        const bool rv = tile_row(p, t, r, orow);
+        float rsum = 0.f, rsq = 0.f;
+        if (rv && col_ok) {
+            const uint4 raw = *reinterpret_cast<const uint4*>(tile_s + r * ldt + lcv * 8);
+            const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+            float x[8];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float2 f = __half22float2(h2[q]);
+                x[2 * q] = f.x, x[2 * q + 1] = f.y;
+            }
+            const size_t off = static_cast<size_t>(orow) * p.N + ncol0 + lcv * 8;
+            if (p.residual != nullptr) {
+                const uint4 rr = *reinterpret_cast<const uint4*>(p.residual + off);
+                const __half2* r2 = reinterpret_cast<const __half2*>(&rr);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float2 f = __half22float2(r2[q]);
+                    x[2 * q] += f.x, x[2 * q + 1] += f.y;
+                }
+            }
+            uint4 pk;
+            __half2* o2 = reinterpret_cast<__half2*>(&pk);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) o2[q] = __floats2half2_rn(x[2 * q], x[2 * q + 1]);
+            *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out) + off) = pk;
+            if (p.cs_partial != nullptr || p.rs_out != nullptr) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {  // statistics of what the consumer will read: the rounded values
+                    const float2 f = __half22float2(o2[q]);
+                    cs[2 * q] += f.x, cs[2 * q + 1] += f.y;
+                    cq[2 * q] = fmaf(f.x, f.x, cq[2 * q]), cq[2 * q + 1] = fmaf(f.y, f.y, cq[2 * q + 1]);
+                    rsum += f.x + f.y;
+                    rsq = fmaf(f.x, f.x, fmaf(f.y, f.y, rsq));
+                }
+            }
+        }
+        if (p.rs_out != nullptr) {
+            for (int o = 1; o < L; o <<= 1) {
+                rsum += __shfl_xor_sync(0xffffffffu, rsum, o);
+                rsq += __shfl_xor_sync(0xffffffffu, rsq, o);
+            }
+            if (rv && lcv == 0)
+                *reinterpret_cast<float2*>(p.rs_out + (static_cast<size_t>(t.n_tile) * p.M + orow) * 2) = make_float2(rsum, rsq);
+        }
+    }
+    if (p.cs_partial == nullptr) return;
+    // ---------------- phase C ----------------
+    for (int o = L; o < 32; o <<= 1) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            cs[e] += __shfl_xor_sync(0xffffffffu, cs[e], o);
+            cq[e] += __shfl_xor_sync(0xffffffffu, cq[e], o);
+        }
+    }
+    if (lr == 0 && lcv < vpr) {
+        float2* dst = reinterpret_cast<float2*>(scratch) + ew * bn + lcv * 8;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) dst[e] = make_float2(cs[e], cq[e]);
+    }
+    epi_bar_sync();
+    const int tid_e = ew * 32 + lane;
+    // the images of the tile's eight 16-row groups (uniform inside a group by construction, see the launcher)
+    int img_of[8];
+#pragma unroll
+    for (int w = 0; w < 8; ++w) img_of[w] = row_image(p, t, w * 16);
+    int slot = 0;
+    if (p.mode == 2) slot = t.w0 / kBM;
+    else if (p.mode == 0) slot = p.cs_hw >= kBM ? (t.m_tile % (p.cs_hw / kBM)) : 0;
+    else slot = (p.cs_slots > 1) ? ((t.h0 >> p.bh_log2) * p.tiles_w + (t.w0 >> p.bw_log2)) : 0;
+    const float2* sc2 = reinterpret_cast<const float2*>(scratch);
+    for (int col = tid_e; col < bn; col += kEpiThreads) {
+        if (ncol0 + col >= p.N) continue;
+        int w = 0;
+        while (w < 8) {
+            const int img = img_of[w];
+            float a = 0.f, b = 0.f;
+            int w2 = w;
+            while (w2 < 8 && img_of[w2] == img) {
+                a += sc2[w2 * bn + col].x, b += sc2[w2 * bn + col].y;
+                ++w2;
+            }
+            if (img >= 0)
+                *reinterpret_cast<float2*>(p.cs_partial + ((static_cast<size_t>(img) * p.cs_slots + slot) * p.N + ncol0 + col) * 2) =
+                    make_float2(a, b);
+            w = w2;
+        }
+    }
+    __threadfence();
+    epi_bar_sync();
+    if (tid_e == 0) {
+        int w = 0, k = 0;
+        while (w < 8) {
+            const int img = img_of[w];
+            int w2 = w;
+            while (w2 < 8 && img_of[w2] == img) ++w2;
+            unsigned int last = 0;
+            if (img >= 0) {
+                const unsigned int old = atomicAdd(&p.cs_tickets[img * p.n_tiles + t.n_tile], 1u);
+                last = (old == static_cast<unsigned int>(p.cs_slots - 1)) ? 1u : 0u;
+                if (last) p.cs_tickets[img * p.n_tiles + t.n_tile] = 0;  // self-reset for the next launch
+            }
+            flag_s[k++] = last;
+            w = w2;
+        }
+    }
+    epi_bar_sync();
+    {
+        int w = 0, k = 0;
+        while (w < 8) {
+            const int img = img_of[w];
+            int w2 = w;
+            while (w2 < 8 && img_of[w2] == img) ++w2;
+            if (flag_s[k++] != 0) {
+                __threadfence();
+                for (int col = tid_e; col < bn; col += kEpiThreads) {
+                    if (ncol0 + col >= p.N) continue;
+                    float a = 0.f, b = 0.f;
+                    for (int sl = 0; sl < p.cs_slots; ++sl) {
+                        const float2 v = __ldcg(reinterpret_cast<const float2*>(
+                            p.cs_partial + ((static_cast<size_t>(img) * p.cs_slots + sl) * p.N + ncol0 + col) * 2));
+                        a += v.x, b += v.y;
+                    }
+                    *reinterpret_cast<float2*>(p.cs_chan + (static_cast<size_t>(img) * p.N + ncol0 + col) * 2) = make_float2(a, b);
+                }
+            }
+            w = w2;
+        }
+    }
+}
+
+template <bool kGeneric, bool kGeglu, bool kOutF32, bool kPartial, bool kTwoCta = false, bool kStaged = false>
 __global__ void __launch_bounds__(kGemmThreads, 1) umma_gemm_kernel(const __grid_constant__ GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -258,7 +538,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) umma_gemm_kernel(const __grid
     uint64_t* tmem_empty = tmem_full + 2;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
     float* bias_s = reinterpret_cast<float*>(tmem_ptr + 4);           // [2][block_n] (16 B aligned)
-    __half* res_s = reinterpret_cast<__half*>(bias_s + 2 * 256);      // [128][block_n + 8]
+    float* wg_s = bias_s + 2 * 256;                                   // [block_n] LayerNorm fold vector
+    unsigned int* flag_s = reinterpret_cast<unsigned int*>(wg_s + 256);  // [8]
+    __half* res_s = reinterpret_cast<__half*>(flag_s + 8);            // [128][block_n + 8] residual / staging tile
     const int ldr = p.block_n + 8;
 
     const int warp = threadIdx.x >> 5;
@@ -283,7 +565,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) umma_gemm_kernel(const __grid
             tmem_alloc_pair(tmem_ptr, 512);
             tmem_relinquish_pair();
         } else {
-            tmem_alloc(tmem_ptr, 512);
+            tmem_alloc(tmem_ptr, static_cast<uint32_t>(p.tmem_cols));
             tmem_relinquish();
         }
     }
@@ -292,8 +574,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) umma_gemm_kernel(const __grid
     if (kTwoCta) cluster_arrive_wait();  // the peer's barriers are initialised before anything signals them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
-    // PDL: everything above overlapped the previous kernel's tail; from here on we touch its outputs
-    pdl_wait();
+    // PDL: everything above overlapped the previous kernel's tail.  Each role executes griddepcontrol.wait itself,
+    // right before its first access to memory the previous kernels may still be producing: the TMA producer first
+    // prefetches the (constant) weight tiles of its first pipeline stages, so the HBM latency of the weights hides
+    // behind the previous kernel's tail; the next kernel in the stream may be scheduled as soon as every CTA of this
+    // grid is resident.
     pdl_trigger();
 
     const int total_work = kTwoCta ? p.m_pairs * p.n_tiles : p.m_tiles * p.n_tiles * p.splits;
@@ -306,46 +591,72 @@ __global__ void __launch_bounds__(kGemmThreads, 1) umma_gemm_kernel(const __grid
             int stage = 0;
             uint32_t phase = 0;
             const uint32_t tx_bytes = kAStage + b_stage;
+            auto load_b = [&](const TileCoord& t, int kb, int st) {
+                const int tap = kb / p.kc;
+                const int j = kb - tap * p.kc;
+                const bool src1 = j >= p.kc0;
+                const int c = (src1 ? (j - p.kc0) : j) * kBK;
+                const int wk = tap * p.Kpt + (src1 ? p.C0 : 0) + c;
+                void* dst_b = smem_b + st * b_stage;
+                const int brow = p.wgt_tiled ? (t.n_tile * p.kb_total + kb) * p.block_n + cta_rank * b_rows
+                                             : t.n_tile * p.block_n + cta_rank * b_rows;
+                if (kTwoCta)
+                    tma_load_2d_pair(dst_b, &p.tmB, mapa_u32(smem_u32(&full_bar[st]), 0), p.wgt_tiled ? 0 : wk, brow,
+                                     p.wgt_tiled ? kEvictFirst : kEvictLast);
+                else
+                    tma_load_2d(dst_b, &p.tmB, &full_bar[st], p.wgt_tiled ? 0 : wk, brow,
+                                p.wgt_tiled ? kEvictFirst : kEvictLast);
+            };
+            auto load_a = [&](const TileCoord& t, int kb, int st) {
+                const int tap = kb / p.kc;
+                const int j = kb - tap * p.kc;
+                const bool src1 = j >= p.kc0;
+                const int c = (src1 ? (j - p.kc0) : j) * kBK;
+                const CUtensorMap* tmA = src1 ? &p.tmA1 : &p.tmA0;
+                void* dst_a = smem_a + st * kAStage;
+                const int r = tap / 3, s3 = tap - 3 * r;
+                if (kTwoCta) {
+                    const uint32_t fb = mapa_u32(smem_u32(&full_bar[st]), 0);
+                    if (p.mode == 0) tma_load_2d_pair(dst_a, tmA, fb, c, t.m_tile * kBM, kEvictNormal);
+                    else tma_load_4d_pair(dst_a, tmA, fb, c, t.w0 * p.stride + s3 - p.pad_lo, t.h0 * p.stride + r - p.pad_lo, t.n0,
+                                          kEvictNormal);
+                } else {
+                    if (p.mode == 0) tma_load_2d(dst_a, tmA, &full_bar[st], c, t.m_tile * kBM, kEvictNormal);
+                    else tma_load_4d(dst_a, tmA, &full_bar[st], c, t.w0 * p.stride + s3 - p.pad_lo,
+                                     t.h0 * p.stride + r - p.pad_lo, t.n0, kEvictNormal);
+                }
+            };
+            // both CTAs' loads of a pair are credited to the leader's full barrier: it sees 2 x tx_bytes per stage
+            auto arm = [&](int st) {
+                if (!kTwoCta) mbar_expect_tx(&full_bar[st], tx_bytes);
+                else if (cta_rank == 0) mbar_expect_tx(&full_bar[st], 2 * tx_bytes);
+            };
+            // ---- weight prefetch ahead of the grid dependency (constant weights only: pre-tiled B operands) ----
+            int npre = 0;
+            if (p.wgt_tiled && work0 < total_work) {
+                const TileCoord t = decode_work(p, work0, cta_rank);
+                int kb0, kb1;
+                split_range(p, t.split, kb0, kb1);
+                npre = min(p.stages, kb1 - kb0);
+                for (int i = 0; i < npre; ++i) {
+                    arm(i);
+                    load_b(t, kb0 + i, i);
+                }
+            }
+            pdl_wait();
+            int it = 0;  // k-blocks issued so far by this CTA
             for (int work = work0; work < total_work; work += work_step) {
                 const TileCoord t = decode_work(p, work, cta_rank);
                 int kb0, kb1;
                 split_range(p, t.split, kb0, kb1);
-                for (int kb = kb0; kb < kb1; ++kb) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
-                    const int tap = kb / p.kc;
-                    const int j = kb - tap * p.kc;
-                    const bool src1 = j >= p.kc0;
-                    const int c = (src1 ? (j - p.kc0) : j) * kBK;
-                    const int wk = tap * p.Kpt + (src1 ? p.C0 : 0) + c;
-                    const CUtensorMap* tmA = src1 ? &p.tmA1 : &p.tmA0;
-                    void* dst_a = smem_a + stage * kAStage;
-                    void* dst_b = smem_b + stage * b_stage;
-                    const int brow = p.wgt_tiled ? (t.n_tile * p.kb_total + kb) * p.block_n + cta_rank * b_rows
-                                                 : t.n_tile * p.block_n + cta_rank * b_rows;
-                    if (kTwoCta) {
-                        // both CTAs' loads are credited to the leader's full barrier: it sees 2 x tx_bytes per stage
-                        if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * tx_bytes);
-                        const uint32_t fb = mapa_u32(smem_u32(&full_bar[stage]), 0);
-                        if (p.mode == 0) {
-                            tma_load_2d_pair(dst_a, tmA, fb, c, t.m_tile * kBM, kEvictNormal);
-                        } else {
-                            const int r = tap / 3, s3 = tap - 3 * r;
-                            tma_load_4d_pair(dst_a, tmA, fb, c, t.w0 * p.stride + s3 - p.pad_lo, t.h0 * p.stride + r - p.pad_lo, t.n0,
-                                             kEvictNormal);
-                        }
-                        tma_load_2d_pair(dst_b, &p.tmB, fb, p.wgt_tiled ? 0 : wk, brow,
-                                         p.wgt_tiled ? kEvictFirst : kEvictLast);
+                for (int kb = kb0; kb < kb1; ++kb, ++it) {
+                    if (it >= npre) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        arm(stage);
+                        load_a(t, kb, stage);
+                        load_b(t, kb, stage);
                     } else {
-                        mbar_expect_tx(&full_bar[stage], tx_bytes);
-                        if (p.mode == 0) {
-                            tma_load_2d(dst_a, tmA, &full_bar[stage], c, t.m_tile * kBM, kEvictNormal);
-                        } else {
-                            const int r = tap / 3, s3 = tap - 3 * r;
-                            tma_load_4d(dst_a, tmA, &full_bar[stage], c, t.w0 * p.stride + s3 - p.pad_lo,
-                                        t.h0 * p.stride + r - p.pad_lo, t.n0, kEvictNormal);
-                        }
-                        tma_load_2d(dst_b, &p.tmB, &full_bar[stage], p.wgt_tiled ? 0 : wk, brow,
-                                    p.wgt_tiled ? kEvictFirst : kEvictLast);
+                        load_a(t, kb, stage);  // its weights are already in flight
                     }
                     if (++stage == p.stages) {
                         stage = 0;
@@ -366,11 +677,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) umma_gemm_kernel(const __grid
                 const TileCoord t = decode_work(p, work, cta_rank);
                 int kb0, kb1;
                 split_range(p, t.split, kb0, kb1);
-                const int as = iter & 1;
-                const uint32_t aphase = (iter >> 1) & 1;
+                const int as = p.acc_bufs == 2 ? (iter & 1) : 0;
+                const uint32_t aphase = (p.acc_bufs == 2 ? (iter >> 1) : iter) & 1;
                 mbar_wait(&tmem_empty[as], aphase ^ 1);
                 tc_fence_after();
-                const uint32_t tmem_d = tmem_base + as * 256;
+                const uint32_t tmem_d = tmem_base + as * p.acc_stride;
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
@@ -408,10 +719,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) umma_gemm_kernel(const __grid
         const int row = lane_group * 32 + lane;
         const int tid_e = threadIdx.x - 64;  // 0..255 among the epilogue warps
         int iter = 0;
+        pdl_wait();  // bias / residual / output buffers belong to the stream order
         for (int work = work0; work < total_work; work += work_step, ++iter) {
             const TileCoord t = decode_work(p, work, cta_rank);
-            const int as = iter & 1;
-            const uint32_t aphase = (iter >> 1) & 1;
+            const int as = p.acc_bufs == 2 ? (iter & 1) : 0;
+            const uint32_t aphase = (p.acc_bufs == 2 ? (iter >> 1) : iter) & 1;
             const int ncol0 = t.n_tile * p.block_n;
             int out_row;
             const bool valid = tile_row(p, t, row, out_row);
@@ -434,6 +746,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) umma_gemm_kernel(const __grid
                 }
                 if (p.bias_rows > 0 && valid) bias_sel = min(1, max(0, out_row / p.bias_rows - img0));
             }
+            if (p.ln_parts != 0)
+                for (int c = tid_e; c < p.block_n; c += kEpiThreads) wg_s[c] = (ncol0 + c < p.N) ? p.ln_wg[ncol0 + c] : 0.f;
             if (p.res_smem) {
                 const int vpr = p.block_n >> 3;  // 16-byte vectors per tile row
                 for (int i = tid_e; i < kBM * vpr; i += kEpiThreads) {
@@ -448,8 +762,24 @@ __global__ void __launch_bounds__(kGemmThreads, 1) umma_gemm_kernel(const __grid
             tc_fence_after();
             if (p.res_smem) cp_async_wait_all();
             epi_bar_sync();  // staged bias / residual visible to all epilogue threads
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_group * 32) << 16) + as * 256;
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_group * 32) << 16) + as * p.acc_stride;
+            if (kStaged) {
+                // staging tile: over the drained pipeline stages when this CTA has no further tile, else dedicated
+                __half* tile_s = p.stage_dedicated ? res_s : reinterpret_cast<__half*>(smem);
+                float* scratch = reinterpret_cast<float*>(tile_s + kBM * (p.block_n + 8));
+                staged_epilogue(p, t, taddr, tile_s, scratch, flag_s,
+                                p.bias_mode == 1 ? bias_s + bias_sel * p.block_n : nullptr, wg_s, warp - 2, lane, row,
+                                out_row, valid);
+                tc_fence_before();
+                mbar_arrive(&tmem_empty[as]);
+                continue;
+            }
+            const float2 lnc = ln_row_coeffs(p, out_row, valid);
             auto process16 = [&](float (&acc)[16], int c) {  // c: column offset inside the tile
+                if (p.ln_parts != 0) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) acc[j] = fmaf(acc[j], lnc.x, lnc.y * wg_s[c + j]);
+                }
                 const float* bptr = nullptr;
                 if (p.bias_mode == 1) bptr = bias_s + bias_sel * p.block_n + c;
                 else if (kGeneric && p.bias_mode == 2) bptr = p.bias + bias_base + ncol0 + c;
@@ -523,6 +853,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) umma_gemm_kernel(const __grid
         // sums its 1/splits slice of the tile over all peers through DSMEM in rank order (deterministic), applies
         // bias / residual / conversion and stores it.  No workspace round trip, no second launch. ----
         __syncwarp();
+        pdl_wait();  // (warps 0 / 1: the reduction below reads bias / residual and writes the output)
         cluster_sync_all();
         const TileCoord t = decode_work(p, blockIdx.x);
         const int ncol0 = t.n_tile * p.block_n;
@@ -573,7 +904,296 @@ __global__ void __launch_bounds__(kGemmThreads, 1) umma_gemm_kernel(const __grid
     if (warp == 1) {
         tc_fence_after();
         if (kTwoCta) tmem_dealloc_pair(tmem_base, 512);
-        else tmem_dealloc(tmem_base, 512);
+        else tmem_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
+    }
+}
+
+
+// =====================================================================================================================
+// Halo-reuse 3x3 convolution (mode 2) with GroupNorm-apply + SiLU fused into the operand path
+// (reference unet.py:470-489: norm1 -> nonlinearity -> conv1, norm2 -> nonlinearity -> conv2; :1044-1046 conv_norm_out).
+//
+// The image is walked in padded-linear order q = y * (W + 1) + x (one shared zero column between image rows), so the
+// input of output position q for tap (dy, dx) is position q + dy * (W + 1) + dx: every tap of a 128-position tile is
+// the SAME shared-memory patch read from a row-shifted start address.  Per 64-channel chunk:
+//   warps 2..9  load the (rows + 2) x (W + 1) pixel patch ONCE with plain 16-byte loads, apply x * sc[n, c] + sh[n, c]
+//               (GroupNorm with the statistics its producer left behind) and SiLU in registers, and store it in the
+//               128-byte-swizzled K-major layout the tensor core reads (zero rows for the padding / pad column);
+//   warp 0      streams the nine [block_n x 64] weight tiles of the chunk with TMA;
+//   warp 1      issues 9 x 4 tcgen05.mma whose A descriptors start at patch + s_tap * 128 bytes.
+// One activation byte enters shared memory once per chunk instead of nine times, is normalised once, and the
+// standalone GroupNorm launch (and its round trip through L2) disappears.  Warps 2..9 then run the staged epilogue.
+// =====================================================================================================================
+__device__ __forceinline__ float silu_fast(float y) {
+    // y * sigmoid(y) with sigmoid(y) = 0.5 * tanh(0.5 y) + 0.5: one MUFU op per element (the patch transform is MUFU
+    // bound otherwise: ex2 + rcp); tanh.approx has 2^-11 relative error, half an fp16 ulp of the stored result
+    float th;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(0.5f * y));
+    const float hy = 0.5f * y;
+    return fmaf(hy, th, hy);
+}
+
+__device__ __forceinline__ void ldr_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+template <bool kFp32Direct>
+__global__ void __launch_bounds__(kGemmThreads, 1) halo_conv_kernel(const __grid_constant__ GemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int b_stage = p.block_n * (kBK * 2);
+    uint8_t* patch = smem;                                  // [2][patch_bytes]
+    uint8_t* smem_b = smem + 2 * p.patch_bytes;             // [stages][block_n * 128]
+    uint64_t* full_b = reinterpret_cast<uint64_t*>(smem_b + p.stages * b_stage);
+    uint64_t* empty_b = full_b + kMaxStages;
+    uint64_t* full_a = empty_b + kMaxStages;                // [2]
+    uint64_t* empty_a = full_a + 2;                         // [2]
+    uint64_t* tmem_full = empty_a + 2;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    float* bias_s = reinterpret_cast<float*>(tmem_ptr + 4);               // [256]
+    unsigned int* flag_s = reinterpret_cast<unsigned int*>(bias_s + 256);   // [8]
+    float2* stat_s = reinterpret_cast<float2*>(flag_s + 8);               // [64] (mean, rstd) per group
+    float2* scsh = stat_s + 64;                                           // [C0 + C1] (scale, shift) per channel
+    const int Cin = p.C0 + p.C1;
+    __half* stage_tile = reinterpret_cast<__half*>(scsh + ((Cin + 7) & ~7));  // dedicated staging tile (if any)
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&p.tmB);
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(&full_b[s], 1);
+            mbar_init(&empty_b[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&full_a[s], kEpiThreads);
+            mbar_init(&empty_a[s], 1);
+            mbar_init(&tmem_full[s], 1);
+            mbar_init(&tmem_empty[s], kEpiThreads);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_ptr, static_cast<uint32_t>(p.tmem_cols));
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+    pdl_trigger();
+
+    const int total_work = p.m_tiles * p.n_tiles;
+    const int work0 = blockIdx.x, work_step = gridDim.x;
+    const int kc = p.kc;
+
+    if (warp == 0) {
+        // ------------------------------- weight producer (TMA; constant data: no grid dependency) -------------------
+        if (lane == 0) {
+            int it = 0;
+            for (int work = work0; work < total_work; work += work_step) {
+                const TileCoord t = decode_work(p, work);
+                for (int kb = 0; kb < kc * p.taps; ++kb, ++it) {
+                    const int st = it % p.stages;
+                    const uint32_t ph = (it / p.stages) & 1;
+                    mbar_wait(&empty_b[st], ph ^ 1);
+                    mbar_expect_tx(&full_b[st], b_stage);
+                    tma_load_2d(smem_b + st * b_stage, &p.tmB, &full_b[st], 0, (t.n_tile * p.kb_total + kb) * p.block_n,
+                                kEvictFirst);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------- MMA issuer -------------------------------------------------------------------
+        const uint32_t idesc = make_idesc_f16(kBM, p.block_n, 0, 0);
+        int it = 0, ait = 0, iter = 0;
+        for (int work = work0; work < total_work; work += work_step, ++iter) {
+            const TileCoord t = decode_work(p, work);
+            const int y0 = t.w0 / p.Wp;
+            const int xp0 = t.w0 - y0 * p.Wp;
+            const int as = p.acc_bufs == 2 ? (iter & 1) : 0;
+            const uint32_t aphase = (p.acc_bufs == 2 ? (iter >> 1) : iter) & 1;
+            mbar_wait(&tmem_empty[as], aphase ^ 1);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + as * p.acc_stride;
+            for (int j = 0; j < kc; ++j, ++ait) {
+                const int pa = ait & 1;
+                mbar_wait(&full_a[pa], (ait >> 1) & 1);
+                tc_fence_after();
+                const uint32_t pbase = smem_u32(patch + pa * p.patch_bytes) + 1024;
+                for (int tap = 0; tap < p.taps; ++tap, ++it) {
+                    const int st = it % p.stages;
+                    mbar_wait(&full_b[st], (it / p.stages) & 1);
+                    tc_fence_after();
+                    if (lane == 0) {
+                        const int dy = p.taps == 9 ? tap / 3 - 1 : 0, dx = p.taps == 9 ? tap - (tap / 3) * 3 - 1 : 0;
+                        // patch pixel of output position q0 for this tap (>= -1); a 1x1 "convolution" has no halo row
+                        const int srow = xp0 + (p.taps == 9 ? p.Wp : 0) + dy * p.Wp + dx;
+                        const uint32_t a_addr = pbase + srow * 128;
+                        // start address shifted by whole 128-byte rows inside the 1024-byte swizzle atom (the patch was
+                        // written in the absolute-address swizzle pattern of a 1024-byte aligned buffer)
+                        const uint64_t adesc = make_smem_desc_sw128(a_addr, 1024, 0) |
+                                               (static_cast<uint64_t>(p.desc_bo ? ((a_addr >> 7) & 7) : 0) << 49);
+                        const uint64_t bdesc = make_smem_desc_sw128(smem_u32(smem_b + st * b_stage), 1024, 0);
+#pragma unroll
+                        for (int k = 0; k < kBK / 16; ++k)
+                            umma_f16_ss(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (j > 0 || tap > 0 || k > 0) ? 1u : 0u);
+                        umma_commit(&empty_b[st]);
+                        if (tap == p.taps - 1) {
+                            umma_commit(&empty_a[pa]);
+                            if (j == kc - 1) umma_commit(&tmem_full[as]);
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else {
+        // ------------------------------- loader / transform warps, then epilogue ---------------------------------------
+        const int ltid = threadIdx.x - 64;
+        const int ew = warp - 2;
+        const int lane_group = warp & 3;
+        const int row = lane_group * 32 + lane;
+        const bool gn = p.gn_gamma != nullptr;
+        const bool ups = p.upsample != 0;
+        const int Hs = ups ? (p.H >> 1) : p.H, Ws = ups ? (p.W >> 1) : p.W;
+        if (ltid < 16) {  // "pixel -1" of both patches: the zero pad column that precedes the patch
+            const int which = ltid >> 3;
+            *reinterpret_cast<uint4*>(patch + which * p.patch_bytes + 7 * 128 + (ltid & 7) * 16) = make_uint4(0, 0, 0, 0);
+        }
+        pdl_wait();
+        int cur_img = -1, ait = 0, iter = 0;
+        for (int work = work0; work < total_work; work += work_step, ++iter) {
+            const TileCoord t = decode_work(p, work);
+            const int img = t.n0;
+            const int y0 = t.w0 / p.Wp;
+            const int ya = y0 - (p.taps == 9 ? 1 : 0);
+            if (gn && img != cur_img) {
+                // ---- GroupNorm coefficients of this image: group statistics from the producers' per-channel sums ----
+                const int cpg = Cin / p.gn_groups;
+                const float inv_cnt = 1.0f / (static_cast<float>(cpg) * static_cast<float>(p.gn_hw));
+                ldr_bar_sync();  // previous tile's readers of the table are done
+                for (int g = ew; g < p.gn_groups; g += 8) {
+                    float s = 0.f, q = 0.f;
+                    for (int c = g * cpg + lane; c < (g + 1) * cpg; c += 32) {
+                        const float2 v = (c < p.C0)
+                            ? *reinterpret_cast<const float2*>(p.gn_chan0 + (static_cast<size_t>(img) * p.C0 + c) * 2)
+                            : *reinterpret_cast<const float2*>(p.gn_chan1 + (static_cast<size_t>(img) * p.C1 + c - p.C0) * 2);
+                        s += v.x, q += v.y;
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        s += __shfl_xor_sync(0xffffffffu, s, o);
+                        q += __shfl_xor_sync(0xffffffffu, q, o);
+                    }
+                    if (lane == 0) {
+                        const float mean = s * inv_cnt;
+                        stat_s[g] = make_float2(mean, rsqrtf(fmaxf(q * inv_cnt - mean * mean, 0.f) + p.gn_eps));
+                    }
+                }
+                ldr_bar_sync();
+                for (int c = ltid; c < Cin; c += kEpiThreads) {
+                    const float2 st = stat_s[c / cpg];
+                    const float sc = p.gn_gamma[c] * st.y;
+                    scsh[c] = make_float2(sc, fmaf(-st.x, sc, p.gn_beta[c]));
+                }
+                ldr_bar_sync();
+                cur_img = img;
+            }
+            // ---- operand patches: one per 64-channel chunk ----
+            const int nvec = p.patch_rows * p.Wp * 8;
+            for (int j = 0; j < kc; ++j, ++ait) {
+                const int pa = ait & 1;
+                mbar_wait(&empty_a[pa], ((ait >> 1) & 1) ^ 1);
+                const bool src1 = j >= p.kc0;
+                const int cbase = (src1 ? j - p.kc0 : j) * kBK;
+                const int Csrc = src1 ? p.C1 : p.C0;
+                const __half* src = (src1 ? p.a1 : p.a0) + static_cast<size_t>(img) * Hs * Ws * Csrc + cbase;
+                const float2* tab = scsh + (src1 ? p.C0 : 0) + cbase;
+                uint8_t* pbase = patch + pa * p.patch_bytes + 1024;
+                constexpr int NB = 6;
+                for (int v0 = 0; v0 < nvec; v0 += kEpiThreads * NB) {
+                    uint4 raw[NB];
+                    bool okv[NB];
+#pragma unroll
+                    for (int i = 0; i < NB; ++i) {
+                        const int v = v0 + ltid + kEpiThreads * i;
+                        const int pi = v >> 3, jj = v & 7;
+                        const int yy = ya + pi / p.Wp, xx = pi % p.Wp;
+                        okv[i] = v < nvec && yy >= 0 && yy < p.H && xx < p.W && (cbase + jj * 8) < Csrc;
+                        raw[i] = make_uint4(0, 0, 0, 0);
+                        if (okv[i]) {
+                            const int ys = ups ? (yy >> 1) : yy, xs = ups ? (xx >> 1) : xx;
+                            raw[i] = __ldg(reinterpret_cast<const uint4*>(src + (static_cast<size_t>(ys) * Ws + xs) * Csrc + jj * 8));
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < NB; ++i) {
+                        const int v = v0 + ltid + kEpiThreads * i;
+                        if (v >= nvec) continue;
+                        const int pi = v >> 3, jj = v & 7;
+                        uint4 val = raw[i];
+                        if (gn && okv[i]) {
+                            __half2* h2 = reinterpret_cast<__half2*>(&val);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const float2 f = __half22float2(h2[q]);
+                                const float4 cf = *reinterpret_cast<const float4*>(tab + jj * 8 + 2 * q);  // sc0 sh0 sc1 sh1
+                                float a = fmaf(f.x, cf.x, cf.y), b = fmaf(f.y, cf.z, cf.w);
+                                if (p.gn_silu) a = silu_fast(a), b = silu_fast(b);
+                                h2[q] = __floats2half2_rn(a, b);
+                            }
+                        }
+                        *reinterpret_cast<uint4*>(pbase + pi * 128 + ((jj ^ (pi & 7)) << 4)) = val;
+                    }
+                }
+                fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
+                mbar_arrive(&full_a[pa]);
+            }
+            // ---- epilogue ----
+            const int as = p.acc_bufs == 2 ? (iter & 1) : 0;
+            const uint32_t aphase = (p.acc_bufs == 2 ? (iter >> 1) : iter) & 1;
+            const int ncol0 = t.n_tile * p.block_n;
+            if (p.bias != nullptr) {
+                const float* bsrc = p.bias + (p.bias_rows > 0 ? static_cast<size_t>(img) * p.bias_stride : 0);
+                for (int c = ltid; c < p.block_n; c += kEpiThreads) bias_s[c] = (ncol0 + c < p.N) ? bsrc[ncol0 + c] : 0.f;
+            }
+            int out_row;
+            const bool valid = tile_row(p, t, row, out_row);
+            mbar_wait(&tmem_full[as], aphase);
+            tc_fence_after();
+            epi_bar_sync();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_group * 32) << 16) + as * p.acc_stride;
+            if (kFp32Direct) {
+                // tiny output width (conv_out: 4 channels, fp32): one thread per output pixel
+                if (ew < 4) {
+                    uint32_t v[16];
+                    tmem_ld16(taddr, v);
+                    tmem_ld_wait();
+                    if (valid) {
+                        for (int c = 0; c < 16 && ncol0 + c < p.N; ++c) {
+                            const float x = __uint_as_float(v[c]) + (p.bias != nullptr ? bias_s[c] : 0.f);
+                            if (p.out_f32) reinterpret_cast<float*>(p.out)[static_cast<size_t>(out_row) * p.N + ncol0 + c] = x;
+                            else reinterpret_cast<__half*>(p.out)[static_cast<size_t>(out_row) * p.N + ncol0 + c] = __float2half_rn(x);
+                        }
+                    }
+                }
+            } else {
+                __half* tile_s = p.stage_dedicated ? stage_tile : reinterpret_cast<__half*>(smem);
+                float* scratch = reinterpret_cast<float*>(tile_s + kBM * (p.block_n + 8));
+                staged_epilogue(p, t, taddr, tile_s, scratch, flag_s, p.bias != nullptr ? bias_s : nullptr, bias_s, ew, lane,
+                                row, out_row, valid);
+            }
+            tc_fence_before();
+            mbar_arrive(&tmem_empty[as]);
+            epi_bar_sync();  // staging buffers (and, when aliased, the pipeline memory) are free again
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
     }
 }
 
@@ -624,6 +1244,11 @@ struct GemmPlan {
     int bias_mode, res_smem, epi_smem;
     int cluster;  // split-K reduced inside a thread-block cluster of `splits` CTAs (DSMEM) instead of a second kernel
     int two_cta;  // CTA pairs (tcgen05.mma cta_group::2, M = 256): each CTA stages half of the B tile
+    int halo;     // mode 2: halo-reuse convolution
+    int Wp, tiles_per_img, patch_rows, patch_bytes;
+    int staged, stage_dedicated, acc_bufs;
+    int cs_slots;  // statistics slots per image this tiling produces (0: column statistics not available)
+    int smem_bytes;
 };
 
 static bool cluster_splitk_enabled() {
@@ -645,6 +1270,81 @@ static int ilog2(int v) {
     return l;
 }
 
+static bool staged_enabled() {
+    // B200SD_STAGED=0: residual-only GEMMs keep the register epilogue with the residual tile prefetched into shared
+    // memory (statistics outputs always take the staged epilogue)
+    const char* e = getenv("B200SD_STAGED");
+    return !(e && e[0] == '0');
+}
+
+static bool desc_base_offset_enabled() {
+    // how row-shifted SWIZZLE_128B descriptors are formed (tools/desc_probe.cu decides; read per call)
+    const char* e = getenv("B200SD_DESC_BO");
+    return e && e[0] == '1';
+}
+
+// Tiling of the halo-reuse convolution (mode 2).
+static int plan_halo(const b200sd_gemm_args& a, GemmPlan& pl) {
+    B200SD_REQUIRE((a.mode == 0 || a.stride == 1) && !a.pad_after_only, "b200sd_gemm: halo needs a stride-1 pad-1 convolution");
+    B200SD_REQUIRE(!a.geglu && a.act == 0 && a.split_k <= 1, "b200sd_gemm: halo kernel: no GEGLU / activation / split-K");
+    B200SD_REQUIRE(a.wgt_tiled && a.block_n > 0, "b200sd_gemm: halo kernel needs chunk-major pre-tiled weights (explicit block_n)");
+    B200SD_REQUIRE(a.n_img > 0 && a.h > 0 && a.w > 0 && a.w <= 255, "b200sd_gemm: bad image geometry for the halo kernel");
+    B200SD_REQUIRE(!a.upsample2x || (a.h % 2 == 0 && a.w % 2 == 0 && a.c1 == 0 && a.gn_groups == 0),
+                   "b200sd_gemm: upsample2x needs even output size, one source, no GroupNorm");
+    pl.halo = 1;
+    pl.Hout = a.h, pl.Wout = a.w;
+    pl.M = a.n_img * a.h * a.w;
+    pl.Wp = a.w + 1;
+    pl.tiles_per_img = (a.h * pl.Wp + kBM - 1) / kBM;
+    pl.m_tiles = a.n_img * pl.tiles_per_img;
+    const int span = (kBM - 1 + pl.Wp - 1) / pl.Wp + 1;  // image rows a 128-position tile can touch
+    const bool conv = a.mode == 1;  // mode 0 + halo: a 1x1 convolution over an image (one tap, no halo rows)
+    pl.patch_rows = span + (conv ? 2 : 0);
+    const int rows_needed = std::max(pl.patch_rows * pl.Wp, (conv ? 3 : 1) * pl.Wp + kBM) + 8 + 1;
+    pl.patch_bytes = ((rows_needed + 7) / 8) * 1024;
+    pl.block_n = a.block_n;
+    B200SD_REQUIRE(pl.block_n == 16 || (pl.block_n % 32 == 0 && pl.block_n <= 256), "b200sd_gemm: halo block_n %d", pl.block_n);
+    pl.n_tiles = (a.n + pl.block_n - 1) / pl.block_n;
+    pl.splits = 1, pl.kb_per_split = pl.kb_total, pl.cluster = 0, pl.two_cta = 0;
+    pl.bias_mode = a.bias != nullptr ? 1 : 0;
+    pl.res_smem = 0;
+    const long units = static_cast<long>(pl.m_tiles) * pl.n_tiles;
+    pl.acc_bufs = units > num_sms() ? 2 : 1;
+    const bool fp32_direct = a.out_f32 || pl.block_n == 16;
+    B200SD_REQUIRE(!fp32_direct || (pl.block_n == 16 && a.residual == nullptr && a.cs_partial == nullptr),
+                   "b200sd_gemm: halo fp32 / narrow output needs block_n 16, no residual, no statistics");
+    pl.staged = fp32_direct ? 0 : 1;
+    pl.stage_dedicated = (pl.staged && pl.acc_bufs == 2) ? 1 : 0;
+    const int cin = a.c0 + a.c1;
+    const int fixed = 2 * pl.patch_bytes + (2 * kMaxStages + 8) * 8 + 16 + 256 * 4 + 32 + 64 * 8 + ((cin + 7) & ~7) * 8 +
+                      (pl.stage_dedicated ? kBM * (pl.block_n + 8) * 2 + 8 * pl.block_n * 8 : 0) + 1024;
+    const int b_stage = pl.block_n * kBK * 2;
+    pl.stages = std::min(kMaxStages, (227 * 1024 - fixed) / b_stage);
+    B200SD_REQUIRE(pl.stages >= 3, "b200sd_gemm: halo kernel does not fit shared memory (w=%d c=%d block_n=%d)", a.w, cin, pl.block_n);
+    pl.smem_bytes = fixed + pl.stages * b_stage;
+    pl.epi_smem = 0;
+    pl.cs_slots = pl.tiles_per_img;
+    return 0;
+}
+
+// block_n the halo kernel would like for these arguments (smallest one-wave tile wins: the kernel is bound by
+// shared-memory bandwidth, reads (128 + bn) + writes (patch share + bn) rows of 32 bytes per MMA of bn / 2 cycles)
+static int halo_pick_block_n(const b200sd_gemm_args& a) {
+    if (a.n <= 16) return 16;
+    const int wp = a.w + 1;
+    const long m_tiles = static_cast<long>(a.n_img) * ((a.h * wp + kBM - 1) / kBM);
+    double best = 1e30;
+    int best_bn = 128;
+    for (int bn = 256; bn >= 32; bn -= 32) {
+        const int nt = (a.n + bn - 1) / bn;
+        if (nt * bn > a.n + a.n / 4 + 31) continue;
+        const double waves = std::ceil(static_cast<double>(m_tiles * nt) / num_sms());
+        const double t = waves * ((41.0 + bn / 2.0) * (a.mode == 1 ? 36.0 : 4.0) * ((a.c0 + a.c1 + 63) / 64) + 4000.0) + 2.0 * nt;
+        if (t < best) best = t, best_bn = bn;
+    }
+    return best_bn;
+}
+
 static int plan_gemm(const b200sd_gemm_args& a, GemmPlan& pl) {
     B200SD_REQUIRE(a.mode == 0 || a.mode == 1, "b200sd_gemm: bad mode %d", a.mode);
     B200SD_REQUIRE(!a.pad_after_only || (a.mode == 1 && a.stride == 2), "b200sd_gemm: pad_after_only is for stride-2 convolutions");
@@ -657,6 +1357,14 @@ static int plan_gemm(const b200sd_gemm_args& a, GemmPlan& pl) {
     pl.kc1 = (a.c1 + kBK - 1) / kBK;
     pl.taps = a.mode == 1 ? 9 : 1;
     pl.kb_total = pl.taps * (pl.kc0 + pl.kc1);
+    pl.halo = 0, pl.Wp = 0, pl.tiles_per_img = 0, pl.patch_rows = 0, pl.patch_bytes = 0;
+    pl.staged = 0, pl.stage_dedicated = 0, pl.acc_bufs = 1, pl.cs_slots = 0, pl.smem_bytes = 0;
+    const bool want_stats = a.cs_partial != nullptr || a.rs_out != nullptr;
+    B200SD_REQUIRE(!want_stats || (!a.geglu && !a.out_f32 && a.act == 0 && a.n % 8 == 0 && a.split_k <= 1),
+                   "b200sd_gemm: statistics outputs need a plain fp16 epilogue without split-K");
+    B200SD_REQUIRE(a.ln_parts == 0 || (a.mode == 0 && a.ln_stat && a.ln_wg && a.split_k <= 1),
+                   "b200sd_gemm: LayerNorm fold needs mode 0, statistics, the fold vector and no split-K");
+    if (a.halo) return plan_halo(a, pl);
     if (a.mode == 0) {
         B200SD_REQUIRE(a.m > 0, "b200sd_gemm: m=%d", a.m);
         pl.M = a.m;
@@ -691,7 +1399,7 @@ static int plan_gemm(const b200sd_gemm_args& a, GemmPlan& pl) {
     if (a.geglu) B200SD_REQUIRE(a.n % 16 == 0, "b200sd_gemm: GEGLU needs n %% 16 == 0");
     // ---- tile shape / split-K selection by a small cost model (cycles; constants fitted to B200 runs) ----
     const int sms = num_sms();
-    const bool can_split = !a.geglu && a.n % 4 == 0 && a.act == 0;
+    const bool can_split = !a.geglu && a.n % 4 == 0 && a.act == 0 && !want_stats && a.ln_parts == 0;
     auto epi_cycles = [&](int bn) { return 400.0 + (bn / 32.0) * (a.geglu ? 520.0 : 230.0); };
     auto kb_cycles = [&](int bn) { return std::max(2.0 * bn, (kAStage + 128.0 * bn) / 38.0); };
     double best_t = 1e30;
@@ -703,7 +1411,8 @@ static int plan_gemm(const b200sd_gemm_args& a, GemmPlan& pl) {
         if (a.block_n > 0 && bn != a.block_n) continue;
         const int nt = (a.n + bn - 1) / bn;
         if (a.block_n == 0 && bn > 16 && nt * bn > a.n + a.n / 4 + 15) continue;  // > 25 % padding
-        const int stages_bn = std::min(kMaxStages, (kSmemBudget - 2 * 256 * 4) / (kAStage + bn * kBK * 2));
+        if (want_stats && bn % 32 != 0) continue;
+        const int stages_bn = std::min(kMaxStages, (smem_budget() - kEpiFixed) / (kAStage + bn * kBK * 2));
         for (int sp : kSplits) {
             if (a.split_k > 0 && sp != a.split_k) continue;
             if (sp > 1 && (!can_split || sp * 2 > pl.kb_total) && a.split_k == 0) continue;
@@ -773,8 +1482,33 @@ static int plan_gemm(const b200sd_gemm_args& a, GemmPlan& pl) {
     pl.two_cta = (two_cta_enabled() && pl.splits == 1 && regular && pl.m_tiles >= 2 &&
                   static_cast<long>((pl.m_tiles + 1) / 2) * pl.n_tiles * 2 >= num_sms() / 2) ? 1 : 0;
     const int per_stage = kAStage + (pl.two_cta ? pl.block_n / 2 : pl.block_n) * kBK * 2;
-    pl.epi_smem = 2 * 256 * 4 + (pl.res_smem ? kBM * (pl.block_n + 8) * 2 : 0);
-    pl.stages = std::max(2, std::min(kMaxStages, (kSmemBudget - pl.epi_smem) / per_stage));
+    {
+        const long units = static_cast<long>(pl.m_tiles) * pl.n_tiles * pl.splits;
+        pl.acc_bufs = ((!pl.cluster && units > num_sms()) || pl.two_cta) ? 2 : 1;
+        // staged epilogue: fp16 tile in shared memory, row-contiguous residual reads / stores, statistics outputs
+        const bool eligible = regular && pl.splits == 1 && !pl.two_cta && !a.geglu && !a.out_f32 && a.n % 8 == 0;
+        pl.staged = (eligible && (want_stats || (a.residual != nullptr && staged_enabled()))) ? 1 : 0;
+        B200SD_REQUIRE(!want_stats || pl.staged, "b200sd_gemm: this shape cannot emit statistics (n=%d block_n=%d)", a.n, pl.block_n);
+        if (pl.staged) pl.res_smem = 0;
+        pl.stage_dedicated = (pl.staged && pl.acc_bufs == 2) ? 1 : 0;
+        if (a.cs_partial != nullptr) {
+            // every 16-row group of a tile must lie inside one image, and the tiles of an image must be countable
+            int slots = 0;
+            if (a.mode == 0) {
+                if (a.cs_hw >= kBM && a.cs_hw % kBM == 0) slots = a.cs_hw / kBM;
+                else if (a.cs_hw >= 16 && kBM % a.cs_hw == 0) slots = 1;
+            } else {
+                if (pl.bn_img == 1) slots = pl.tiles_w * pl.tiles_h;
+                else if (pl.bn_img <= 8 && pl.tiles_w * pl.tiles_h == 1) slots = 1;
+            }
+            B200SD_REQUIRE(slots > 0, "b200sd_gemm: column statistics are not available for this geometry (rows per image %d)", a.cs_hw);
+            pl.cs_slots = slots;
+        }
+    }
+    pl.epi_smem = kEpiFixed + (pl.res_smem ? kBM * (pl.block_n + 8) * 2 : 0) +
+                  (pl.stage_dedicated ? kBM * (pl.block_n + 8) * 2 + 8 * pl.block_n * 8 : 0);
+    pl.stages = std::max(2, std::min(kMaxStages, (smem_budget() - pl.epi_smem) / per_stage));
+    pl.smem_bytes = pl.stages * per_stage + (2 * kMaxStages + 4) * 8 + 16 + pl.epi_smem + 1024;
     return 0;
 }
 
@@ -797,7 +1531,9 @@ static int launch_gemm(const b200sd_gemm_args& a, cudaStream_t stream) {
     memset(&p, 0, sizeof(p));
     // ---- tensor maps ----
     const uint32_t es1[4] = {1, 1, 1, 1};
-    if (a.mode == 0) {
+    if (pl.halo) {
+        // activations are read by the loader warps with plain loads; only the weights go through TMA
+    } else if (a.mode == 0) {
         const uint32_t box[2] = {kBK, kBM};
         {
             const uint64_t dims[2] = {static_cast<uint64_t>(a.c0), static_cast<uint64_t>(a.m)};
@@ -844,7 +1580,7 @@ static int launch_gemm(const b200sd_gemm_args& a, cudaStream_t stream) {
         const uint32_t box[2] = {kBK, static_cast<uint32_t>(pl.two_cta ? pl.block_n / 2 : pl.block_n)};
         if (int rc = encode_tmap_f16(&p.tmB, a.wgt, 2, dims, str, box, es1)) return rc;
     }
-    p.mode = a.mode;
+    p.mode = pl.halo ? 2 : a.mode;
     p.M = pl.M;
     p.N = a.n;
     p.n_store = a.geglu ? a.n / 2 : a.n;
@@ -884,19 +1620,65 @@ static int launch_gemm(const b200sd_gemm_args& a, cudaStream_t stream) {
     p.cluster = pl.cluster;
     p.two_cta = pl.two_cta;
     p.m_pairs = (pl.m_tiles + 1) / 2;
+    p.H = a.h, p.W = a.w, p.Wp = pl.Wp, p.tiles_per_img = pl.tiles_per_img;
+    p.patch_rows = pl.patch_rows, p.patch_bytes = pl.patch_bytes;
+    p.upsample = a.upsample2x, p.desc_bo = desc_base_offset_enabled() ? 1 : 0;
+    p.a0 = reinterpret_cast<const __half*>(a.a0), p.a1 = reinterpret_cast<const __half*>(a.a1), p.C1 = a.c1;
+    if (pl.halo && a.gn_groups > 0) {
+        B200SD_REQUIRE(a.gn_chan0 && a.gn_gamma && a.gn_beta && (a.c1 == 0 || a.gn_chan1) && a.gn_groups <= 64 &&
+                           (a.c0 + a.c1) % a.gn_groups == 0,
+                       "b200sd_gemm: bad fused GroupNorm arguments");
+        p.gn_chan0 = a.gn_chan0, p.gn_chan1 = a.gn_chan1, p.gn_gamma = a.gn_gamma, p.gn_beta = a.gn_beta;
+        p.gn_groups = a.gn_groups, p.gn_silu = a.gn_silu, p.gn_eps = a.gn_eps, p.gn_hw = a.h * a.w;
+    }
+    p.cs_partial = a.cs_partial, p.cs_chan = a.cs_chan, p.cs_tickets = a.cs_tickets;
+    p.cs_slots = pl.cs_slots;
+    p.cs_hw = a.mode == 0 ? a.cs_hw : pl.Hout * pl.Wout;
+    if (p.cs_hw <= 0) p.cs_hw = 1;
+    B200SD_REQUIRE(a.cs_partial == nullptr || (a.cs_chan && a.cs_tickets), "b200sd_gemm: statistics outputs need cs_chan and cs_tickets");
+    p.rs_out = a.rs_out;
+    p.ln_stat = a.ln_stat, p.ln_wg = a.ln_wg, p.ln_parts = a.ln_parts, p.ln_eps = a.ln_eps, p.ln_k = a.c0 + a.c1;
+    p.staged = pl.staged, p.stage_dedicated = pl.stage_dedicated;
+    {
+        // one accumulator buffer when no CTA sees a second tile (nothing to overlap the epilogue with); the allocation
+        // is the smallest power of two that holds the buffers, so small tiles leave TMEM for a co-resident CTA
+        p.acc_bufs = pl.acc_bufs;
+        int stride = 32;
+        while (stride < pl.block_n) stride <<= 1;
+        if (pl.two_cta) stride = 256;
+        p.acc_stride = stride;
+        p.tmem_cols = pl.two_cta ? 512 : stride * p.acc_bufs;
+    }
+    if (pl.halo) {
+        using HaloFn = void (*)(GemmParams);
+        const bool direct = pl.staged == 0;
+        HaloFn hfn = direct ? halo_conv_kernel<true> : halo_conv_kernel<false>;
+        static bool hattr[2] = {false, false};
+        if (!hattr[direct ? 1 : 0]) {
+            B200SD_CHECK_CUDA(cudaFuncSetAttribute(hfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            hattr[direct ? 1 : 0] = true;
+        }
+        const int units = pl.m_tiles * pl.n_tiles;
+        B200SD_CHECK_CUDA(launch_kernel(hfn, dim3(std::min(units, num_sms())), dim3(kGemmThreads), pl.smem_bytes, stream, p));
+        B200SD_CHECK_CUDA(cudaGetLastError());
+        count_launch(1);
+        return 0;
+    }
 
-    const int smem_bytes = pl.stages * (kAStage + (pl.two_cta ? pl.block_n / 2 : pl.block_n) * kBK * 2) + (2 * kMaxStages + 4) * 8 + 16 + pl.epi_smem + 1024;
+    const int smem_bytes = pl.smem_bytes;
     const int total = pl.m_tiles * pl.n_tiles * pl.splits;
     const int grid = std::min(total, num_sms());
     // compile-time epilogue variants for the hot shapes; anything irregular takes the generic kernel
     B200SD_REQUIRE(a.act == 0 || (a.act >= 1 && a.act <= 3 && pl.splits == 1 && !a.geglu), "b200sd_gemm: act=%d unsupported here", a.act);
     const bool regular = (a.act == 0) && (a.n % 16 == 0) && (p.n_store % 8 == 0) && (pl.block_n % 32 == 0) && pl.bias_mode != 2 &&
-                         (a.residual == nullptr || pl.res_smem || pl.splits > 1);
+                         (a.residual == nullptr || pl.res_smem || pl.splits > 1 || pl.staged);
     using KernelFn = void (*)(GemmParams);
     KernelFn fn;
     int variant;
     if (!regular) {
         fn = umma_gemm_kernel<true, false, false, false>, variant = 0;
+    } else if (pl.staged) {
+        fn = umma_gemm_kernel<false, false, false, false, false, true>, variant = 8;
     } else if (pl.splits > 1) {
         fn = umma_gemm_kernel<false, false, false, true>, variant = 1;
     } else if (a.geglu) {
@@ -915,7 +1697,7 @@ static int launch_gemm(const b200sd_gemm_args& a, cudaStream_t stream) {
         p.bias = nullptr;
         p.residual = nullptr;
     }
-    static bool attr_set[8] = {false, false, false, false, false, false, false, false};
+    static bool attr_set[9] = {false, false, false, false, false, false, false, false, false};
     if (!attr_set[variant]) {
         B200SD_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set[variant] = true;
@@ -977,6 +1759,20 @@ extern "C" int b200sd_gemm_plan(const b200sd_gemm_args* args, int32_t* out4) {
     b200sd::GemmPlan pl;
     if (int rc = b200sd::plan_gemm(*args, pl)) return rc;
     out4[0] = pl.block_n, out4[1] = pl.splits, out4[2] = pl.kb_total, out4[3] = pl.n_tiles;
+    return 0;
+}
+
+extern "C" int b200sd_gemm_plan_ex(const b200sd_gemm_args* args, int32_t* out8) {
+    if (!args || !out8) return 2;
+    b200sd::GemmPlan pl;
+    b200sd_gemm_args a = *args;
+    if (a.halo && a.block_n == 0) {  // planning query before the weights are tiled
+        a.block_n = b200sd::halo_pick_block_n(a);
+        a.wgt_tiled = 1;
+    }
+    if (int rc = b200sd::plan_gemm(a, pl)) return rc;
+    out8[0] = pl.block_n, out8[1] = pl.splits, out8[2] = pl.kb_total, out8[3] = pl.n_tiles;
+    out8[4] = pl.cs_slots, out8[5] = pl.staged, out8[6] = pl.stages, out8[7] = pl.m_tiles;
     return 0;
 }
 

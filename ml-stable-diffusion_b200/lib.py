@@ -28,6 +28,14 @@ class GemmArgs(C.Structure):
         ("a0", C.c_void_p), ("a1", C.c_void_p), ("wgt", C.c_void_p), ("bias", C.c_void_p),
         ("residual", C.c_void_p), ("out", C.c_void_p), ("workspace", C.c_void_p),
         ("workspace_bytes", C.c_size_t),
+        # fused normalisation (include/b200sd.h): halo convolution + GroupNorm operand transform, statistics outputs,
+        # LayerNorm fold
+        ("halo", C.c_int32), ("upsample2x", C.c_int32), ("gn_groups", C.c_int32), ("gn_silu", C.c_int32),
+        ("gn_eps", C.c_float),
+        ("gn_chan0", C.c_void_p), ("gn_chan1", C.c_void_p), ("gn_gamma", C.c_void_p), ("gn_beta", C.c_void_p),
+        ("cs_partial", C.c_void_p), ("cs_chan", C.c_void_p), ("cs_tickets", C.c_void_p), ("cs_hw", C.c_int32),
+        ("rs_out", C.c_void_p),
+        ("ln_stat", C.c_void_p), ("ln_wg", C.c_void_p), ("ln_parts", C.c_int32), ("ln_eps", C.c_float),
     ]
 
 
@@ -47,6 +55,7 @@ _SIGNATURES = {
     "b200sd_gemm": (C.c_int, [C.POINTER(GemmArgs), C.c_void_p]),
     "b200sd_gemm_workspace_bytes": (C.c_size_t, [C.POINTER(GemmArgs)]),
     "b200sd_gemm_plan": (C.c_int, [C.POINTER(GemmArgs), C.POINTER(C.c_int32)]),
+    "b200sd_gemm_plan_ex": (C.c_int, [C.POINTER(GemmArgs), C.POINTER(C.c_int32)]),
     "b200sd_gemm_describe_plan": (C.c_int, [C.POINTER(GemmArgs), C.c_char_p, C.c_size_t]),
     "b200sd_linear_small": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                       C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
@@ -188,10 +197,11 @@ TILED_WEIGHTS = os.environ.get("B200SD_TILED_W", "1") != "0"
 _tiled_cache = {}
 
 
-def pack_tiled(w2d, c0, c1, taps, bn):
+def pack_tiled(w2d, c0, c1, taps, bn, chunk_major=False):
     """[N, taps*(c0+c1)] -> [n_tiles, k_blocks, bn, 64] fp16 in the exact k-block order of the kernel's main
     loop (tap-major; per tap the 64-channel chunks of source 0, then of source 1; ragged chunks zero padded), so
-    that each weight tile is one contiguous bn*128-byte burst in HBM."""
+    that each weight tile is one contiguous bn*128-byte burst in HBM.  chunk_major: k-block = chunk * taps + tap
+    (the halo convolution walks all nine taps of one 64-channel chunk before the next chunk)."""
     n, kpt = w2d.shape[0], c0 + c1
     kc0, kc1 = (c0 + 63) // 64, (c1 + 63) // 64
     kc = kc0 + kc1
@@ -203,15 +213,22 @@ def pack_tiled(w2d, c0, c1, taps, bn):
         lo = j * 64 if j < kc0 else c0 + (j - kc0) * 64
         hi = min(lo + 64, c0 if j < kc0 else kpt)
         out[:, :, j, :, : hi - lo] = wp[:, :, lo:hi].reshape(nt, bn, taps, hi - lo).permute(0, 2, 1, 3)
+    if chunk_major:
+        out = out.permute(0, 2, 1, 3, 4)
     return out.reshape(nt, taps * kc, bn, 64).contiguous()
+
+
+def plan_ex(args):
+    """(block_n, splits, kb_total, n_tiles, stat slots per image, staged, stages, m_tiles) of a call."""
+    plan = (C.c_int32 * 8)()
+    _check(load().b200sd_gemm_plan_ex(C.byref(args), plan), "b200sd_gemm_plan_ex")
+    return tuple(int(v) for v in plan)
 
 
 def _maybe_tile_weights(args, wgt, taps):
     """Static weight operands are re-laid out once per (weight, block_n) and cached."""
-    plan = (C.c_int32 * 4)()
-    _check(load().b200sd_gemm_plan(C.byref(args), plan), "b200sd_gemm_plan")
-    bn = int(plan[0])
-    key = (wgt.data_ptr(), bn, args.c0, args.c1, taps)
+    bn = plan_ex(args)[0]
+    key = (wgt.data_ptr(), bn, args.c0, args.c1, taps, bool(args.halo))
     hit = _tiled_cache.get(key)
     packed = None
     if hit is not None and hit[0]() is wgt and hit[1] == wgt._version:
@@ -219,7 +236,7 @@ def _maybe_tile_weights(args, wgt, taps):
     if packed is None:
         if torch.cuda.is_current_stream_capturing():
             return  # never pack during capture; the warm-up pass has populated the cache for these shapes
-        packed = pack_tiled(wgt, args.c0, args.c1, taps, bn)
+        packed = pack_tiled(wgt, args.c0, args.c1, taps, bn, chunk_major=bool(args.halo))
         if len(_tiled_cache) > 4096:  # drop entries whose source tensor is gone
             for k in [k for k, v in _tiled_cache.items() if v[0]() is None]:
                 del _tiled_cache[k]
@@ -238,27 +255,82 @@ def run_gemm(args):
 
 
 _ws_cache = {}
+_ws_retired = []   # superseded workspaces stay allocated: CUDA graphs captured earlier hold their addresses
+_ticket_cache = {}
 
 
 def _workspace(nbytes, device):
-    """Process-wide scratch (split-K partials, GroupNorm statistics).  Kernels that use it are
-    stream-ordered on the single compute stream of the process; it only ever grows (outside of
-    CUDA-graph capture: the warm-up pass sizes it), so captured pointers stay valid."""
+    """Process-wide scratch (split-K partials, GroupNorm / column-statistics partials).  Kernels that use it are
+    stream-ordered on the single compute stream of the process.  It only ever grows (outside of CUDA-graph
+    capture: the warm-up pass sizes it) and a superseded buffer is never freed, so pointers baked into
+    previously captured graphs stay valid."""
     key = device.index
     ws = _ws_cache.get(key)
     if ws is None or ws.numel() * 4 < nbytes:
         if torch.cuda.is_current_stream_capturing():
             raise B200SDError("workspace would have to grow during CUDA-graph capture; run one eager "
                               "warm-up call with the same shapes first")
+        if ws is not None:
+            _ws_retired.append(ws)
         ws = torch.empty(max(nbytes // 4 + 1, 1 << 24), dtype=torch.float32, device=device)
         _ws_cache[key] = ws
     return ws
 
 
+def _tickets(device):
+    """Arrival counters of the statistics epilogue ([n_img][n_tiles] per call): zero once, self-resetting, shared by
+    every call on the device (calls are stream ordered)."""
+    t = _ticket_cache.get(device.index)
+    if t is None:
+        t = torch.zeros(1 << 16, dtype=torch.int32, device=device)
+        _ticket_cache[device.index] = t
+    return t
+
+
+def _fused_args(args, x_dev, *, n_img, cout, gn=None, stats=None, cs_hw=0, ln=None, rowstats=None, m=0):
+    """Fill the fused-normalisation fields of a GemmArgs.  gn: dict(chan0, chan1, gamma, beta, groups, eps, silu);
+    stats: dict, receives 'chan' [n_img, cout, 2]; rowstats: dict, receives 'rows' [n_tiles, m, 2] and 'parts';
+    ln: dict(stat, parts, wg, eps)."""
+    keep = []
+    if gn is not None:
+        args.gn_groups, args.gn_silu, args.gn_eps = int(gn["groups"]), int(bool(gn["silu"])), float(gn["eps"])
+        args.gn_chan0 = gn["chan0"].data_ptr()
+        args.gn_chan1 = None if gn.get("chan1") is None else gn["chan1"].data_ptr()
+        args.gn_gamma, args.gn_beta = gn["gamma"].data_ptr(), gn["beta"].data_ptr()
+    if ln is not None:
+        args.ln_stat, args.ln_wg = ln["stat"].data_ptr(), ln["wg"].data_ptr()
+        args.ln_parts, args.ln_eps = int(ln["parts"]), float(ln.get("eps", 1e-5))
+    if stats is not None or rowstats is not None:
+        if stats is not None:
+            args.cs_partial = 1  # planning query: non-null
+            args.cs_hw = cs_hw
+        if rowstats is not None:
+            args.rs_out = 1
+        pl = plan_ex(args)
+        n_tiles, slots = pl[3], pl[4]
+        if stats is not None:
+            if n_img * n_tiles > (1 << 16):
+                raise B200SDError("statistics ticket table too small")
+            chan = torch.empty(n_img, cout, 2, dtype=torch.float32, device=x_dev)
+            part = _workspace(n_img * slots * cout * 2 * 4, x_dev)
+            args.cs_partial, args.cs_chan, args.cs_tickets = part.data_ptr(), chan.data_ptr(), _tickets(x_dev).data_ptr()
+            stats["chan"] = chan
+            keep.append(chan)
+        if rowstats is not None:
+            rows = torch.empty(n_tiles, m, 2, dtype=torch.float32, device=x_dev)
+            args.rs_out = rows.data_ptr()
+            rowstats["rows"], rowstats["parts"] = rows, n_tiles
+            keep.append(rows)
+    return keep
+
+
 def linear(x, wgt, bias=None, residual=None, *, x1=None, geglu=False, out_dtype=torch.float16, split_k=0,
-           block_n=0, bias_rows=0, bias_stride=0, out=None, static_w=False, act=0):
+           block_n=0, bias_rows=0, bias_stride=0, out=None, static_w=False, act=0, ln=None, stats=None, cs_hw=0,
+           rowstats=None):
     """out[M, N] = epilogue([x | x1] @ wgt^T).  x [M, C0] fp16, wgt [N, C0(+C1)] fp16, bias fp32 [N].
-    static_w: `wgt` is a model weight (constant address/content) and may be re-tiled + cached."""
+    static_w: `wgt` is a model weight (constant address/content) and may be re-tiled + cached.
+    ln: LayerNorm of x folded into this GEMM (wgt = gamma (.) W, bias = W beta + b; dict(stat, parts, wg, eps));
+    stats / rowstats: dicts that receive the per-channel / per-row sums of the output (see _fused_args)."""
     _req(x, torch.float16, "linear x")
     _req(wgt, torch.float16, "linear wgt")
     m, n = x.shape[0], wgt.shape[0]
@@ -267,6 +339,10 @@ def linear(x, wgt, bias=None, residual=None, *, x1=None, geglu=False, out_dtype=
         out = torch.empty(m, n_out, dtype=out_dtype, device=x.device)
     args = gemm_args(0, x, wgt, out, a1=x1, bias=bias, residual=residual, m=m, n=n, geglu=geglu,
                      bias_rows=bias_rows, bias_stride=bias_stride, split_k=split_k, block_n=block_n, act=act)
+    if ln is not None or stats is not None or rowstats is not None:
+        args.split_k = 1
+        _keep = _fused_args(args, x.device, n_img=(m // cs_hw if cs_hw else 0), cout=n, stats=stats, cs_hw=cs_hw, ln=ln,
+                            rowstats=rowstats, m=m)
     if static_w and TILED_WEIGHTS:
         _maybe_tile_weights(args, wgt, 1)
     need = gemm_workspace_bytes(args)
@@ -279,21 +355,38 @@ def linear(x, wgt, bias=None, residual=None, *, x1=None, geglu=False, out_dtype=
 
 
 def conv3x3(x, wgt, bias=None, residual=None, *, x1=None, stride=1, out_dtype=torch.float16, split_k=0,
-            block_n=0, bias_rows=0, bias_stride=0, out=None, act=0, static_w=True, pad_after_only=False):
+            block_n=0, bias_rows=0, bias_stride=0, out=None, act=0, static_w=True, pad_after_only=False,
+            halo=False, gn=None, upsample=False, stats=None, rowstats=None, taps=9):
     """3x3 pad-1 convolution.  x NHWC fp16 [N, H, W, C0]; wgt [Cout, 9*(C0+C1)] fp16 (OHWI);
-    bias fp32 [Cout] or [N_img, Cout] with bias_rows = Hout*Wout."""
+    bias fp32 [Cout] or [N_img, Cout] with bias_rows = Hout*Wout.
+    halo: the halo-reuse kernel (stride 1); gn: GroupNorm (+SiLU) of x ++ x1 applied while loading (dict(chan0, chan1,
+    gamma, beta, groups, eps, silu), needs halo); upsample: x is read nearest-x2 upsampled (halo); stats: dict that
+    receives 'chan', the per-channel (sum, sum of squares) of the output for the consumer's GroupNorm; taps=1 with
+    halo: a 1x1 convolution (wgt [Cout, C0+C1]) that shares the halo kernel's GroupNorm operand path."""
     _req(x, torch.float16, "conv3x3 x")
     _req(wgt, torch.float16, "conv3x3 wgt")
     nimg, h, w, _ = x.shape
+    if upsample:
+        h, w = 2 * h, 2 * w
     cout = wgt.shape[0]
     ho, wo = h // stride, w // stride
     if out is None:
         out = torch.empty(nimg, ho, wo, cout, dtype=out_dtype, device=x.device)
-    args = gemm_args(1, x, wgt, out, a1=x1, bias=bias, residual=residual, n=cout, n_img=nimg, h=h, w=w,
+    if (gn is not None or upsample or taps == 1) and not halo:
+        raise B200SDError("conv3x3: gn / upsample / taps=1 need halo=True")
+    args = gemm_args(1 if taps == 9 else 0, x, wgt, out, a1=x1, bias=bias, residual=residual, n=cout, n_img=nimg, h=h, w=w,
                      stride=stride, bias_rows=bias_rows, bias_stride=bias_stride, split_k=split_k, block_n=block_n, act=act,
-                     pad_after_only=pad_after_only)
+                     pad_after_only=pad_after_only, m=(nimg * h * w if taps == 1 else 0))
+    args.halo, args.upsample2x = int(halo), int(upsample)
+    _keep = None
+    if gn is not None or stats is not None or rowstats is not None:
+        args.split_k = 1
+        _keep = _fused_args(args, x.device, n_img=nimg, cout=cout, gn=gn, stats=stats, cs_hw=ho * wo, rowstats=rowstats,
+                            m=nimg * ho * wo)
+    if halo and not (static_w and TILED_WEIGHTS):
+        raise B200SDError("conv3x3: the halo kernel needs static pre-tiled weights")
     if static_w and TILED_WEIGHTS:
-        _maybe_tile_weights(args, wgt, 9)
+        _maybe_tile_weights(args, wgt, taps)
     need = gemm_workspace_bytes(args)
     if need:
         ws = _workspace(need, x.device)

@@ -20,6 +20,7 @@ Pre-packing (done once at load):
 from __future__ import annotations
 
 import enum
+import os
 
 import torch
 
@@ -97,6 +98,10 @@ class UNetEngine:
         self.in_pad = max(8, (self.in_ch + 7) // 8 * 8)
         self.xl = cfg.get("addition_embed_type") == "text_time"
         self.support_controlnet = bool(cfg.get("support_controlnet", False))
+        # fused normalisation (round 2): GroupNorm + SiLU in the halo convolution's operand path, LayerNorm folded
+        # into the consumer GEMM, statistics from the producers' epilogues.  B200SD_FUSED=0 keeps the round-1 graph
+        # (standalone GroupNorm / LayerNorm launches) for A/B measurements.
+        self.fused = os.environ.get("B200SD_FUSED", "1") != "0"
         for c, h in zip(boc, self.heads):
             if c % h or c // h != 64:
                 raise L.B200SDError(f"b200sd attention kernel needs head dim 64 (got {c}/{h})")
@@ -153,6 +158,18 @@ class UNetEngine:
                 blk["gg"] = P.f16(torch.stack([gw[:half], gw[half:]], 1).reshape(gw.shape))
                 blk["ggb"] = torch.stack([gb[:half], gb[half:]], 1).reshape(-1).to(self.dev).contiguous()
                 blk["f2"], blk["f2b"] = P.lin(f"{b}.ff.net.2"), P.bias(f"{b}.ff.net.2")
+                if self.fused:
+                    # LayerNorm folded into the consumer GEMM (layer_norm.py:66-78 followed by unet.py:74-82 / :613):
+                    # W' = gamma (.) W (fp16), wg = row sums of the ROUNDED W', bias' = W beta + bias
+                    for name, ln, bkey in (("qkv", 1, None), ("q2", 2, None), ("gg", 3, "ggb")):
+                        wf32 = blk[name].float()
+                        folded = (wf32 * blk[f"ln{ln}g"][None, :]).half().contiguous()
+                        blk[name + "_ln"] = folded
+                        blk[name + "_wg"] = folded.float().sum(1).contiguous()
+                        bias = wf32 @ blk[f"ln{ln}b"]
+                        if bkey is not None:
+                            bias = bias + blk[bkey]
+                        blk[name + "_lnb"] = bias.contiguous()
                 t["blocks"].append(blk)
             w[p] = t
 
@@ -247,6 +264,108 @@ class UNetEngine:
         out = L.linear(tok, t["po"], t["pob"], x.reshape(m, c), static_w=True)
         return out.reshape(n, h, wd, c)
 
+    # ------------------------------------------------------------------ fused blocks
+    # An activation travels as (tensor, chan): chan = per-channel (sum, sum of squares) [n, C, 2] left behind by the
+    # epilogue that produced the tensor, or None when the producer could not emit them (then the consumer falls back
+    # to the standalone GroupNorm kernel).
+    def _gn_conv(self, x, xs, x1, x1s, gamma, beta, eps, silu, wgt, bias, residual=None, stats=None, **kw):
+        if xs is not None and (x1 is None or x1s is not None):
+            gn = dict(chan0=xs, chan1=x1s, gamma=gamma, beta=beta, groups=self.groups, eps=eps, silu=silu)
+            return L.conv3x3(x, wgt, bias, residual, x1=x1, halo=True, gn=gn, stats=stats, **kw)
+        hh = L.group_norm(x, gamma, beta, self.groups, eps, silu=silu, x1=x1)
+        return L.conv3x3(hh, wgt, bias, residual, halo=True, stats=stats, **kw)
+
+    def _resnet_f(self, p, x, xs, x1, x1s, temb_all):
+        r = self.w[p]
+        n, h, wd, _ = x.shape
+        off, co = self.temb_slices[p]
+        st1, st2 = {}, {}
+        hh = self._gn_conv(x, xs, x1, x1s, r["n1g"], r["n1b"], self.eps, True, r["c1"], temb_all[:, off:], stats=st1,
+                           bias_rows=h * wd, bias_stride=self.temb_total)
+        if "sc" in r:
+            res = L.linear(x.reshape(n * h * wd, -1), r["sc"], r["scb"],
+                           x1=None if x1 is None else x1.reshape(n * h * wd, -1), static_w=True)
+        else:
+            res = x
+        out = self._gn_conv(hh, st1.get("chan"), None, None, r["n2g"], r["n2b"], self.eps, True, r["c2"], r["c2b"], res,
+                            stats=st2)
+        return out, st2.get("chan")
+
+    def _transformer_f(self, p, x, xs, kv_all, batch, heads, s_ctx):
+        t = self.w[p]
+        n, h, wd, c = x.shape
+        m, s = n * h * wd, h * wd
+        impl = _IMPL_CODE[ATTENTION_IMPLEMENTATION_IN_EFFECT]
+        rs = {}
+        if xs is not None:
+            gn = dict(chan0=xs, chan1=None, gamma=t["ng"], beta=t["nb"], groups=32, eps=1e-6, silu=False)
+            tok = L.conv3x3(x, t["pi"], t["pib"], halo=True, taps=1, gn=gn, rowstats=rs).reshape(m, c)
+        else:
+            hn = L.group_norm(x, t["ng"], t["nb"], 32, 1e-6, silu=False)
+            tok = L.linear(hn.reshape(m, c), t["pi"], t["pib"], static_w=True, rowstats=rs)
+
+        def ln_of(rs, blk, name):
+            return dict(stat=rs["rows"], parts=rs["parts"], wg=blk[name + "_wg"], eps=1e-5)
+
+        nblk = len(t["blocks"])
+        for bi, blk in enumerate(t["blocks"]):
+            qkv = L.linear(tok, blk["qkv_ln"], blk["qkv_lnb"], ln=ln_of(rs, blk, "qkv"), static_w=True)
+            a = L.attention(qkv[:, :c], qkv[:, c:2 * c], qkv[:, 2 * c:], batch, heads, s, s, impl=impl)
+            rs = {}
+            tok = L.linear(a, blk["o1"], blk["o1b"], tok, static_w=True, rowstats=rs)
+            q = L.linear(tok, blk["q2_ln"], blk["q2_lnb"], ln=ln_of(rs, blk, "q2"), static_w=True)
+            ko = blk["kv_off"]
+            a = L.attention(q, kv_all[:, ko:ko + c], kv_all[:, ko + c:ko + 2 * c], batch, heads, s, s_ctx, impl=impl)
+            rs = {}
+            tok = L.linear(a, blk["o2"], blk["o2b"], tok, static_w=True, rowstats=rs)
+            g = L.linear(tok, blk["gg_ln"], blk["gg_lnb"], geglu=True, ln=ln_of(rs, blk, "gg"), static_w=True)
+            rs = {}
+            tok = L.linear(g, blk["f2"], blk["f2b"], tok, static_w=True, rowstats=rs if bi + 1 < nblk else None)
+        st = {}
+        ok = s % 128 == 0 or (s >= 16 and 128 % s == 0)   # geometries whose tiles map onto whole images
+        out = L.linear(tok, t["po"], t["pob"], x.reshape(m, c), static_w=True, stats=st if ok else None, cs_hw=s)
+        return out.reshape(n, h, wd, c), st.get("chan")
+
+    def _forward_fused(self, sample, temb_all, kv_all, batch, s_ctx, additional_residuals):
+        st = {}
+        x = L.conv3x3(sample, self.w["conv_in"]["w"], self.w["conv_in"]["b"], stats=st)
+        xs = st.get("chan")
+        skips = [(x, xs)]
+        for i, typ in enumerate(self.down_types):
+            for j in range(self.lpb):
+                x, xs = self._resnet_f(f"down_blocks.{i}.resnets.{j}", x, xs, None, None, temb_all)
+                if typ == "CrossAttnDownBlock2D":
+                    x, xs = self._transformer_f(f"down_blocks.{i}.attentions.{j}", x, xs, kv_all, batch, self.heads[i], s_ctx)
+                skips.append((x, xs))
+            if i != self.nb - 1:
+                d = self.w[f"down_blocks.{i}.downsamplers.0.conv"]
+                st = {}
+                x = L.conv3x3(x, d["w"], d["b"], stride=2, stats=st)
+                xs = st.get("chan")
+                skips.append((x, xs))
+        if additional_residuals is not None:  # the sums have no producer-side statistics: standalone GroupNorm there
+            skips = [(L.add(s, r), None) for (s, _), r in zip(skips, additional_residuals[:-1])]
+            x, xs = skips[-1]
+        x, xs = self._resnet_f("mid_block.resnets.0", x, xs, None, None, temb_all)
+        x, xs = self._transformer_f("mid_block.attentions.0", x, xs, kv_all, batch, self.heads[-1], s_ctx)
+        x, xs = self._resnet_f("mid_block.resnets.1", x, xs, None, None, temb_all)
+        if additional_residuals is not None:
+            x, xs = L.add(x, additional_residuals[-1]), None
+        rheads = self.heads[::-1]
+        for i, typ in enumerate(self.up_types):
+            for j in range(self.lpb + 1):
+                sk, sks = skips.pop()
+                x, xs = self._resnet_f(f"up_blocks.{i}.resnets.{j}", x, xs, sk, sks, temb_all)
+                if typ == "CrossAttnUpBlock2D":
+                    x, xs = self._transformer_f(f"up_blocks.{i}.attentions.{j}", x, xs, kv_all, batch, rheads[i], s_ctx)
+            if i != self.nb - 1:
+                u = self.w[f"up_blocks.{i}.upsamplers.0.conv"]
+                st = {}
+                x = L.conv3x3(x, u["w"], u["b"], halo=True, upsample=True, stats=st)
+                xs = st.get("chan")
+        o = self.w["out"]
+        return self._gn_conv(x, xs, None, None, o["g"], o["b"], self.eps, True, o["w"], o["cb"], out_dtype=torch.float32)
+
     # ------------------------------------------------------------------ forward
     def time_embedding(self, timesteps, time_ids=None, text_embeds=None):
         """fp32 [B] -> per-image bias vectors of every ResNet block: fp32 [B, sum Cout]."""
@@ -272,6 +391,8 @@ class UNetEngine:
         batch = sample.shape[0]
         temb_all = self.time_embedding(timesteps, time_ids, text_embeds)
         kv_all = L.linear(ctx_tokens, self.kv_w, static_w=True) if self.kv_w is not None else None
+        if self.fused:
+            return self._forward_fused(sample, temb_all, kv_all, batch, s_ctx, additional_residuals)
         x = L.conv3x3(sample, self.w["conv_in"]["w"], self.w["conv_in"]["b"])
         skips = [x]
         for i, typ in enumerate(self.down_types):
