@@ -31,6 +31,14 @@ PUBLISHED_ITER_S = 3.07     # best published SD-2.1-base 
 WORKLOAD = "SD-2.1-base txt2img 512x512, 20 DDIM steps, CFG 7.5, fp16 (BASELINE configs[1])"
 
 
+def CONFIG(world):
+    """The `config` object of the JSON line: identical for the b200sd arm and the reference arm."""
+    return {"workload": WORKLOAD, "unet_batch": 2, "latent": "4x64x64", "text_tokens": 77,
+            "weights": "random-init SD-2.1-base (865.9 M params)",
+            "parallelism": f"replicas x{world}, independent prompts per rank, no data-path collective",
+            "cache": "inputs larger than L2: every step streams 1.73 GB of fp16 weights through the 126 MB L2"}
+
+
 def _peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -131,32 +139,32 @@ def time_cpu(budget_s=25.0, max_steps=3, warmup=1):
 
 
 def run_reference_arm(args, rank, world):
+    """`--impl reference`: the reference's own CPU implementation of the path (its unmodified PyTorch-CPU UNet modules
+    when /root/reference is present, else the oracle restatement of them) on the box's host cores, same `config`,
+    metric and unit as the b200sd arm, EXACTLY --steps timed UNet forwards after --warmup untimed ones (a CPU
+    forward takes seconds: the default 40 + 3 finish within a few minutes).  Rank 0 only."""
     if rank != 0:
         return
     kind, fn = cpu_unet_runner()
-    t0 = time.perf_counter()
-    fn()
-    first = time.perf_counter() - t0
-    warm = max(0, min(args.warmup, 1) - 1)  # the probe above already is one warm-up
+    warm = max(0, args.warmup)
     for _ in range(warm):
         fn()
-    k = max(1, min(args.steps, int(100.0 / max(first, 1e-3))))
     t0 = time.perf_counter()
-    for _ in range(k):
+    for _ in range(args.steps):
         fn()
     dt = time.perf_counter() - t0
-    val = k / dt
+    val = args.steps / dt
     line = {
         "impl": "reference", "metric": "diffusion_iter_per_s", "value": round(val, 4), "unit": "iter/s",
-        "n_gpus": args.gpus, "steps": k, "warmup": 1 + warm, "ms_per_step": round(1e3 * dt / k, 2),
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": warm, "ms_per_step": round(1e3 * dt / args.steps, 2),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": round(val / PUBLISHED_ITER_S, 4),
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "unet_batch": 2, "latent": "64x64", "note": "CPU arm runs the UNet forward "
-                   "only (the reference does CFG + scheduler math on the host as well; negligible)"},
+        "config": CONFIG(max(1, args.gpus)),
         "cpu_baseline": {"value": round(val, 4), "unit": "iter/s", "cores": torch.get_num_threads(), "kind": kind,
-                         "sample": f"{k} fp32 UNet forwards of the reference's PyTorch-CPU path "
-                                   f"({'unmodified reference modules' if kind == 'reference' else 'oracle restatement'})"
-                                   f", requested steps={args.steps}"},
+                         "sample": f"{args.steps} fp32 UNet forwards (SD-2.1-base, bs=2, 64x64 latents) of the reference's "
+                                   f"PyTorch-CPU path ({'unmodified reference modules' if kind == 'reference' else 'oracle restatement (port)'}); "
+                                   "the CPU arm runs the UNet forward only (the reference does CFG + scheduler math on "
+                                   "the host as well; negligible)"},
         "e2e": {"value": round(val, 4), "unit": "iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -165,55 +173,167 @@ def run_reference_arm(args, rank, world):
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
-def gemm_roofline(pipe, peaks):
-    """Per-kernel roofline of the dominant kernel (umma_gemm_kernel = every conv / linear of the UNet):
-    algorithmic FLOPs of each launch (2*M*N*K) / its CUDA-event duration, summed over one eager forward."""
-    from b200sd import lib as L
+N_STEPS_IMG, GUIDANCE = 20, 7.5
 
+
+class LoopBench:
+    """K denoising iterations of a pipeline's device loop as ONE CUDA graph.  Every 20 iterations (one image) the
+    graph re-runs the per-prompt prologue (cross-attention K/V, time-embedding table, first UNet input), exactly
+    what ``B200StableDiffusionPipeline.denoise`` captures; optional ControlNets run inside every step."""
+
+    def __init__(self, pipe, lat0, cond=None):
+        from b200sd import lib as L
+        from b200sd import scheduler as S
+        self.L, self.pipe, self.lat0 = L, pipe, lat0
+        self.plan = S.DDIMScheduler(N_STEPS_IMG).plan()
+        self.cond = cond
+        self.graphs = {}
+
+    def body(self, k_steps):
+        L, pipe = self.L, self.pipe
+        u, n = pipe.unet, pipe.images_per_call
+        for i in range(k_steps):
+            j = i % N_STEPS_IMG
+            if j == 0:
+                pipe._latents.copy_(self.lat0)
+                pipe._hist.zero_()
+                u.prepare_prompt()
+                table = u.time_table(self.ts_rows)
+                L.nchw_to_nhwc(pipe._latents, c_pad=u.engine.in_pad, out=u._x_nhwc[:n])
+                L.nchw_to_nhwc(pipe._latents, c_pad=u.engine.in_pad, out=u._x_nhwc[n:])
+                if self.cond is not None:
+                    pipe.prepare_controlnets(self.ts_rows)
+            st = self.plan[j]
+            res = pipe.controlnet_residuals(j, table[j]) if self.cond is not None else None
+            u._run_core(table[j], res)
+            k = pipe._coeffs(st, GUIDANCE)
+            k.noise_pred_nhwc = 1
+            k.n_hist, k.push_eps_slot, k.push_x0_slot, k.push_x_slot = 0, -1, -1, -1
+            L.cfg_scheduler_step(u._out_nhwc, pipe._latents, k, unet_in=u._x_nhwc)
+
+    def capture(self, k_steps, classes=0xF):
+        key = (k_steps, classes)
+        if key in self.graphs:
+            return self.graphs[key]
+        L, pipe = self.L, self.pipe
+        self.ts_rows = pipe._ts_rows(self.plan)
+        if self.cond is not None:
+            pipe.set_control_conditions(self.cond)
+        s = torch.cuda.Stream(device=pipe.device)
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            n0 = L.launch_count()
+            self.body(min(k_steps, 2))   # eager warm-up: workspaces, weight tiling, kernel attributes
+            torch.cuda.synchronize()
+            n1 = L.launch_count()
+            self.body(N_STEPS_IMG)       # launch census of one whole image
+            self.launches_per_image = L.launch_count() - n1
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        L.load().b200sd_set_launch_classes(classes)
+        try:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.body(k_steps)
+        finally:
+            L.load().b200sd_set_launch_classes(0xF)
+        self.graphs[key] = g
+        return g
+
+
+def timed_replays(graph, reps, barrier):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(2):
+        graph.replay()
+    barrier()
+    e0.record()
+    for _ in range(reps):
+        graph.replay()
+    e1.record()
+    barrier()
+    return e0.elapsed_time(e1) / reps
+
+
+def gemm_census(pipe):
+    """Algorithmic FLOPs (2 M N K) of every tensor-core GEMM / convolution launch of one UNet forward."""
+    from b200sd import lib as L
     recs = []
     orig = L.run_gemm
 
-    def timed(args):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        m = args.m if args.mode == 0 else args.n_img * (args.h // max(1, args.stride)) * (args.w // max(1, args.stride))
+    def rec(args):
+        m = args.m if (args.mode == 0 and not args.halo) else args.n_img * (args.h // max(1, args.stride)) * (args.w // max(1, args.stride))
         k = (args.c0 + args.c1) * (9 if args.mode == 1 else 1)
-        e0.record()
+        recs.append(2.0 * m * args.n * k)
         orig(args)
-        e1.record()
-        recs.append((2.0 * m * args.n * k, e0, e1))
 
-    unet = pipe.unet
-    L.run_gemm = timed
+    L.run_gemm = rec
     try:
-        # park the GPU behind a ~40 ms spin kernel so the host enqueues the whole eager forward ahead of it:
-        # the events then bracket back-to-back device execution instead of host launch latency
-        torch.cuda.synchronize()
-        torch.cuda._sleep(int(80e6))
-        unet._run()  # eager (not the captured graph), same launch sequence
+        u = pipe.unet
+        u._run_core(torch.zeros(u.batch, u.engine.temb_total, device=pipe.device))
     finally:
         L.run_gemm = orig
     torch.cuda.synchronize()
-    flops = sum(r[0] for r in recs)
-    ms = sum(r[1].elapsed_time(r[2]) for r in recs)
-    achieved = flops / (ms * 1e-3) / 1e12
+    return sum(recs), len(recs)
+
+
+def class_breakdown(loop, barrier, peaks, pipe):
+    """Device time of one image's loop (20 steps + prologue) with only ONE kernel class launching, per class: the
+    same launch sequence on the same buffers, each class captured as its own CUDA graph.  No event gaps, no profiler
+    serialisation: the four numbers add up to the full loop when the classes do not overlap."""
+    out = {}
+    for name, bit in (("gemm_conv", 1), ("attention", 2), ("normalisation", 4), ("elementwise", 8)):
+        g = loop.capture(N_STEPS_IMG, classes=bit)
+        out[name] = round(timed_replays(g, 3, barrier) / N_STEPS_IMG, 4)
+    flops, launches = gemm_census(pipe)
     burst, sustained, _, how = peaks
-    traffic = None  # DRAM bytes per launch of the same kernel from the committed ncu pass (profiles/traffic_r1.json)
+    ms = out["gemm_conv"]
+    achieved = flops / (ms * 1e-3) / 1e12
+    traffic = None
     try:
-        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic_r1.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "traffic_r2.json")) as f:
             traffic = round(json.load(f)["dram_bytes_per_launch"])
     except (OSError, KeyError, ValueError):
         pass
-    return {"bound": "tensor", "kernel": "umma_gemm_kernel (all conv3x3 / 1x1 / linear launches of one UNet forward)",
+    roof = {"bound": "tensor", "kernel": "umma_gemm_kernel + halo_conv_kernel (every conv3x3 / 1x1 / linear launch of one UNet forward)",
             "achieved": round(achieved, 1), "peak": sustained, "unit": "TFLOP/s", "frac": round(achieved / sustained, 4),
-            "peak_kind": f"{how} sustained bf16 dense (kernel timed inside a long step)", "traffic": traffic,
-            "traffic_unit": "DRAM bytes per launch (ncu, L2 flushed per kernel; algorithmic = weights 1.73e9 B / forward)",
-            "launches": len(recs), "algorithmic_tflop": round(flops / 1e12, 4), "kernel_ms_sum": round(ms, 3)}
+            "peak_kind": f"{how} sustained bf16 dense (kernels timed inside a long step)", "traffic": traffic,
+            "traffic_unit": "DRAM bytes per launch (ncu; algorithmic = weights 1.73e9 B / forward)",
+            "launches": launches, "algorithmic_tflop": round(flops / 1e12, 4), "kernel_ms_sum": ms,
+            "how": "CUDA-graph replay of the loop with only the GEMM / convolution class launching (same buffers, no "
+                   "event gaps), divided by the steps"}
+    return out, roof
+
+
+def extra_config(name, dev, barrier, peaks, steps=N_STEPS_IMG):
+    """BASELINE configs[3] (SDXL-base 768x768) and configs[4] (SD-2.1 + ControlNet): iter/s of the device loop."""
+    from b200sd import config as C
+    from b200sd.pipeline import B200StableDiffusionPipeline
+    g = torch.Generator().manual_seed(7)
+    if name == "sdxl_768":
+        pipe = B200StableDiffusionPipeline.from_random_init("sdxl-base", images_per_call=1, device=dev, seed=1,
+                                                            scheduler="DDIM", height=768, width=768)
+        tflop, hw, d_ctx, cond = 7.282, 96, 2048, None
+        pipe.unet._time_ids.copy_(torch.tensor([[768, 768, 0, 0, 768, 768]] * 2, dtype=torch.float32))
+        pipe.unet._text_embeds.copy_(torch.randn(2, 1280, generator=g))
+    else:
+        pipe = B200StableDiffusionPipeline.from_random_init("sd21-base", images_per_call=1, device=dev, seed=1,
+                                                            scheduler="DDIM", controlnet_cfgs=[C.SD21_CONTROLNET])
+        tflop, hw, d_ctx = 1.609 + 0.567, 64, 1024
+        cond = [torch.rand(2, 3, 512, 512, generator=g).half().to(dev)]
+    pipe.unet._ctx.copy_(torch.cat([torch.zeros(1, d_ctx, 1, 77), torch.randn(1, d_ctx, 1, 77, generator=g)]).half())
+    lat0 = torch.randn(1, 4, hw, hw, generator=g).half().float().to(dev)
+    loop = LoopBench(pipe, lat0, cond)
+    ms = timed_replays(loop.capture(steps), 2, barrier) / steps
+    _, sustained, _, _ = peaks
+    return {"iter_per_s": round(1e3 / ms, 2), "ms_per_step": round(ms, 4),
+            "launches_per_step": round(loop.launches_per_image / N_STEPS_IMG, 1),
+            "step_roofline": {"algorithmic_tflop": tflop, "achieved": round(tflop / (ms * 1e-3), 1), "peak": sustained,
+                              "unit": "TFLOP/s", "frac": round(tflop / (ms * 1e-3) / sustained, 4)}}
 
 
 def run_gpu_arm(args, rank, local_rank, world):
     import torch.distributed as dist
     from b200sd import lib as L
-    from b200sd import scheduler as S
     from b200sd.pipeline import B200StableDiffusionPipeline
 
     torch.cuda.set_device(local_rank)
@@ -222,60 +342,40 @@ def run_gpu_arm(args, rank, local_rank, world):
         dist.init_process_group("nccl", device_id=dev)
     L.load()
     peaks = _peaks()
-    n_steps_img, guidance = 20, 7.5
     pipe = B200StableDiffusionPipeline.from_random_init("sd21-base", images_per_call=1, device=dev, seed=1,
                                                         scheduler="DDIM")
     unet = pipe.unet
-    plan = S.DDIMScheduler(n_steps_img).plan()
     g = torch.Generator().manual_seed(93 + rank)  # each rank = an independent prompt / seed
     emb_cond = torch.randn(1, 1024, 1, 77, generator=g)
     emb = torch.cat([torch.zeros_like(emb_cond), emb_cond]).half()
-    lat0 = torch.randn(1, 4, 64, 64, generator=g).half().float()
-    pipe._ctx.copy_(emb)
-    pipe._latents.copy_(lat0)
-    pipe._hist.zero_()
-    coeffs = []
-    for st in plan:
-        k = L.StepCoeffs()
-        k.guidance, k.cx, k.ce, k.x0_cx, k.x0_ce = guidance, st.cx, st.ce, st.x0_cx, st.x0_ce
-        k.n_hist, k.push_eps_slot, k.push_x0_slot, k.push_x_slot = 0, -1, -1, -1
-        coeffs.append((float(st.timestep), k))
-
-    def device_step(i):
-        t, k = coeffs[i % n_steps_img]
-        if i % n_steps_img == 0:
-            pipe._latents.copy_(lat0)
-        pipe._t.fill_(t)
-        sample = torch.cat([pipe._latents, pipe._latents], 0)
-        npred = unet.forward_device(sample, pipe._t, pipe._ctx)
-        L.cfg_scheduler_step(npred, pipe._latents, k)
-
-    # ---- warm-up (also captures the CUDA graph) ----
-    for i in range(max(3, args.warmup)):
-        device_step(i)
-    torch.cuda.synchronize()
-    launches_per_step = (unet.launches_per_call or 0) + 1
+    lat0 = torch.randn(1, 4, 64, 64, generator=g).half().float().to(dev)
+    unet._ctx.copy_(emb)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    # ---- value: K iterations of the pipeline's device loop (UNet forward bs=2 + fused CFG/DDIM step), one graph ----
+    loop = LoopBench(pipe, lat0)
+    graph = loop.capture(args.steps)
+    launches_per_step = loop.launches_per_image / N_STEPS_IMG
+    for _ in range(max(1, (max(3, args.warmup) + args.steps - 1) // args.steps)):  # >= W warm-up steps
+        graph.replay()
     sampler = ClockSampler(local_rank)
     sampler.start()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(args.steps):
-        device_step(i)
+    graph.replay()                      # EXACTLY args.steps iterations
     e1.record()
     barrier()
     ms_dev = e0.elapsed_time(e1)
     if args.quick:
         if rank == 0:
             print(json.dumps({"quick": True, "iter_per_s": round(world * args.steps / (ms_dev * 1e-3), 2),
-                              "ms_per_step": round(ms_dev / args.steps, 4), "launches_per_step": int(launches_per_step),
-                              "pdl": os.environ.get("B200SD_PDL", "0"), "smem_kb": os.environ.get("B200SD_SMEM_KB", "")}),
+                              "ms_per_step": round(ms_dev / args.steps, 4), "launches_per_step": round(launches_per_step, 1),
+                              "fused": os.environ.get("B200SD_FUSED", "1"), "pdl": os.environ.get("B200SD_PDL", "0")}),
                   flush=True)
         sampler.stop()
         if world > 1:
@@ -283,21 +383,23 @@ def run_gpu_arm(args, rank, local_rank, world):
         return
 
     # ---- e2e: the reference-facing boundary call with pinned host buffers, copies inside the timed region ----
+    from b200sd import scheduler as S
+    plan = S.DDIMScheduler(N_STEPS_IMG).plan()
     h_sample = torch.empty(2, 4, 64, 64, dtype=torch.float16).pin_memory()
     h_t = torch.empty(2, dtype=torch.float16).pin_memory()
     h_ctx = emb.clone().pin_memory()
-    h_lat = lat0.clone()
+    h_lat = lat0.cpu().clone()
     np_sample, np_t, np_ctx = h_sample.numpy(), h_t.numpy(), h_ctx.numpy()
 
     def e2e_step(i):
-        t, k = coeffs[i % n_steps_img]
+        st = plan[i % N_STEPS_IMG]
         np_sample[:] = np.concatenate([h_lat.numpy()] * 2).astype(np.float16)
-        np_t[:] = t
+        np_t[:] = float(st.timestep)
         out = unet(sample=np_sample, timestep=np_t, encoder_hidden_states=np_ctx)["noise_pred"]  # H2D + D2H inside
-        eps = out[:1] + guidance * (out[1:] - out[:1])          # host CFG + DDIM exactly like pipeline.py:559-569
-        h_lat.copy_(torch.from_numpy(k.cx * h_lat.numpy() + k.ce * eps))
-        if (i + 1) % n_steps_img == 0:
-            h_lat.copy_(lat0)
+        eps = out[:1] + GUIDANCE * (out[1:] - out[:1])          # host CFG + DDIM exactly like pipeline.py:559-569
+        h_lat.copy_(torch.from_numpy(st.cx * h_lat.numpy() + st.ce * eps))
+        if (i + 1) % N_STEPS_IMG == 0:
+            h_lat.copy_(lat0.cpu())
 
     for i in range(3):
         e2e_step(i)
@@ -311,14 +413,14 @@ def run_gpu_arm(args, rank, local_rank, world):
     ms_e2e = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
     clocks = sampler.stop()
 
-    # ---- images/s: 20 steps + VAE decode through the device-resident pipeline loop ----
+    # ---- images/s: 20 steps + VAE decode through the public device-resident pipeline loop, >= 5 images ----
     def one_image():
-        final = pipe.denoise(emb, lat0, n_steps_img, guidance)
+        final = pipe.denoise(emb, lat0, N_STEPS_IMG, GUIDANCE)
         return pipe.decode_latents(final)
 
     one_image()
     barrier()
-    n_img = max(1, min(3, args.steps // n_steps_img + 1))
+    n_img = 5
     e0.record()
     for _ in range(n_img):
         img = one_image()
@@ -330,23 +432,25 @@ def run_gpu_arm(args, rank, local_rank, world):
     # ---- BASELINE configs[2] shape: 8 prompts per GPU (UNet batch 16), 20 steps + VAE decode of all 8 ----
     ms_b8 = float("nan")
     if not args.no_batched:
-        del one_image
         pipe8 = B200StableDiffusionPipeline.from_random_init("sd21-base", images_per_call=8, device=dev, seed=1,
                                                              scheduler="DDIM")
         emb8 = torch.cat([torch.zeros(8, 1024, 1, 77), torch.randn(8, 1024, 1, 77, generator=g)]).half()
         lat8 = torch.randn(8, 4, 64, 64, generator=g).half().float()
 
         def eight_images():
-            return pipe8.decode_latents(pipe8.denoise(emb8, lat8, n_steps_img, guidance))
+            return pipe8.decode_latents(pipe8.denoise(emb8, lat8, N_STEPS_IMG, GUIDANCE))
 
         eight_images()
         barrier()
         e0.record()
-        img8 = eight_images()
+        for _ in range(2):
+            img8 = eight_images()
         img8_host = img8.cpu()
         e1.record()
         barrier()
-        ms_b8 = e0.elapsed_time(e1)
+        ms_b8 = e0.elapsed_time(e1) / 2
+        del pipe8, eight_images, img8, img8_host
+        torch.cuda.empty_cache()
 
     # max over ranks
     stats = torch.tensor([ms_dev, ms_e2e, ms_img, ms_b8], dtype=torch.float64, device=dev)
@@ -354,9 +458,23 @@ def run_gpu_arm(args, rank, local_rank, world):
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
     ms_dev, ms_e2e, ms_img, ms_b8 = [float(v) for v in stats.tolist()]
 
+    # ---- rank 0 at N = 1: per-class attribution, the other BASELINE configs, the CPU arm ----
+    classes = roof = None
+    extra = {}
     if rank == 0:
-        roof = gemm_roofline(pipe, peaks)
-        cpu, _ = time_cpu() if world >= 1 else (None, None)
+        classes, roof = class_breakdown(loop, torch.cuda.synchronize, peaks, pipe)
+    if world == 1 and not args.no_extra:
+        del loop, graph
+        torch.cuda.empty_cache()
+        for name in ("sd21_controlnet", "sdxl_768"):
+            try:
+                extra[name] = extra_config(name, dev, torch.cuda.synchronize, peaks)
+            except Exception as exc:  # reported, never hidden
+                extra[name] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+            torch.cuda.empty_cache()
+
+    if rank == 0:
+        cpu, _ = time_cpu() if world == 1 else (None, None)
         value = world * args.steps / (ms_dev * 1e-3)
         e2e_val = world * args.steps / (ms_e2e * 1e-3)
         burst, sustained, hbm, how = peaks
@@ -365,19 +483,16 @@ def run_gpu_arm(args, rank, local_rank, world):
             "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": round(ms_dev / args.steps, 4),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": round(value / PUBLISHED_ITER_S, 2),
             "dtype": "f16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "unet_batch": 2, "latent": "4x64x64", "text_tokens": 77,
-                       "weights": "random-init SD-2.1-base (865.9 M params)", "parallelism": f"replicas x{world}, "
-                       "independent prompts per rank, no data-path collective",
-                       "cache": "inputs larger than L2: every step streams 1.73 GB of fp16 weights through the 126 MB L2",
-                       "cuda_graph": True},
+            "config": CONFIG(world),
             "e2e": {"value": round(e2e_val, 2), "unit": "iter/s", "h2d_bytes_per_step": int(np_sample.nbytes +
                     np_t.nbytes + np_ctx.nbytes), "d2h_bytes_per_step": int(2 * 4 * 64 * 64 * 4),
                     "ms_per_step": round(ms_e2e / args.steps, 4), "api": "UNetModel.__call__(**np.ndarray) boundary + "
                     "host CFG/DDIM, as in the reference loop (pipeline.py:499-573)"},
-            "gpu_launches": int(launches_per_step * args.steps),
-            "launches_per_step": int(launches_per_step),
+            "gpu_launches": int(round(launches_per_step * args.steps)),
+            "launches_per_step": round(launches_per_step, 1),
             "images_per_s": round(world * 1e3 / ms_img, 3),
             "ms_per_image": round(ms_img, 2),
+            "images_timed": n_img,
             "batched_images_per_s": None if ms_b8 != ms_b8 else round(world * 8 * 1e3 / ms_b8, 3),
             "batched_note": "BASELINE configs[2] shape: 8 prompts per GPU (UNet batch 16), 20 DDIM steps + VAE decode",
             "step_roofline": {"bound": "tensor", "achieved": round(UNET_TFLOP / (ms_dev / args.steps * 1e-3), 1),
@@ -385,6 +500,8 @@ def run_gpu_arm(args, rank, local_rank, world):
                               "frac": round(UNET_TFLOP / (ms_dev / args.steps * 1e-3) / sustained, 4),
                               "note": "whole UNet forward (1.609 TFLOP algorithmic) / device time per step; per GPU"},
             "roofline": roof,
+            "kernel_class_ms_per_step": classes,
+            "configs": extra or None,
             "cpu_baseline": cpu,
             "clocks": clocks,
             "image_checksum": float(host_img.double().sum()),
@@ -402,6 +519,7 @@ def main():
     ap.add_argument("--impl", default="b200sd", choices=["b200sd", "reference"])
     ap.add_argument("--no-batched", action="store_true", help="skip the 8-prompts-per-GPU images/s measurement")
     ap.add_argument("--quick", action="store_true", help="device-resident iter/s only (tuning runs; not a bench line)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the SDXL-768 / ControlNet configs (N = 1 only)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -33,6 +33,10 @@ int b200sd_version(void);
 /* Programmatic dependent launch on/off (default off; env B200SD_PDL=1 enables): lets each kernel's
  * prologue overlap the previous kernel's tail inside the captured CUDA graph. */
 void b200sd_set_pdl(int enabled);
+/* Measurement aid: only entry points whose class bit is set launch (others return 0 at once): 1 GEMM / convolution,
+ * 2 attention, 4 normalisation, 8 elementwise; default 0xF.  bench.py captures one CUDA graph per class over the same
+ * buffers to attribute the step time per kernel class. */
+void b200sd_set_launch_classes(uint32_t mask);
 /* number of kernels launched by this library since load (bench.py's gpu_launches) */
 uint64_t b200sd_launch_count(void);
 
@@ -223,6 +227,8 @@ typedef struct {
     int32_t push_eps_slot;   /* >= 0: hist[slot] = eps'  */
     int32_t push_x0_slot;    /* >= 0: hist[slot] = x0    */
     int32_t push_x_slot;     /* >= 0: hist[slot] = x (sample before this update) */
+    int32_t noise_pred_nhwc; /* 1: noise_pred is NHWC fp32 [2*n, h, w, c] (the UNet's conv_out epilogue output, no
+                                layout kernel in between); 0: NCHW */
 } b200sd_step_coeffs;
 
 int b200sd_cfg_scheduler_step(const float* noise_pred, float* latents, float* hist /* [4][numel] */,

@@ -59,27 +59,52 @@ class ControlNetEngine(UNetEngine):
             x = L.conv3x3(x, e["w"], e["b"], stride=e["stride"], act=e["act"])
         return x
 
-    def forward(self, sample, timesteps, ctx_tokens, s_ctx, cond_nhwc):
-        """Returns the list of NHWC fp16 residuals: 12 (or fewer) down residuals + the mid residual."""
+    def forward(self, sample, timesteps, ctx_tokens, s_ctx, cond_nhwc, temb_all=None, kv_all=None, emb=None):
+        """Returns the list of NHWC fp16 residuals: 12 (or fewer) down residuals + the mid residual.
+        temb_all / kv_all / emb: precomputed time-embedding biases, cross-attention K/V and conditioning embedding
+        (constant over a denoising loop: the pipeline's per-prompt prologue)."""
         batch = sample.shape[0]
-        temb_all = self.time_embedding(timesteps)
-        kv_all = L.linear(ctx_tokens, self.kv_w, static_w=True) if self.kv_w is not None else None
-        e = self.embed_condition(cond_nhwc)
-        x = L.conv3x3(sample, self.w["conv_in"]["w"], self.w["conv_in"]["b"], e)   # conv_in(sample) + embedding
-        skips = [x]
-        for i, typ in enumerate(self.down_types):
-            for j in range(self.lpb):
-                x = self._resnet(f"down_blocks.{i}.resnets.{j}", x, None, temb_all)
-                if typ == "CrossAttnDownBlock2D":
-                    x = self._transformer(f"down_blocks.{i}.attentions.{j}", x, kv_all, batch, self.heads[i], s_ctx)
-                skips.append(x)
-            if i != self.nb - 1:
-                d = self.w[f"down_blocks.{i}.downsamplers.0.conv"]
-                x = L.conv3x3(x, d["w"], d["b"], stride=2)
-                skips.append(x)
-        x = self._resnet("mid_block.resnets.0", x, None, temb_all)
-        x = self._transformer("mid_block.attentions.0", x, kv_all, batch, self.heads[-1], s_ctx)
-        x = self._resnet("mid_block.resnets.1", x, None, temb_all)
+        if temb_all is None:
+            temb_all = self.time_embedding(timesteps)
+        if kv_all is None:
+            kv_all = self.kv_project(ctx_tokens)
+        e = self.embed_condition(cond_nhwc) if emb is None else emb
+        if self.fused:
+            st = {}
+            x = L.conv3x3(sample, self.w["conv_in"]["w"], self.w["conv_in"]["b"], e, stats=st)
+            xs = st.get("chan")
+            skips = [x]
+            for i, typ in enumerate(self.down_types):
+                for j in range(self.lpb):
+                    x, xs = self._resnet_f(f"down_blocks.{i}.resnets.{j}", x, xs, None, None, temb_all)
+                    if typ == "CrossAttnDownBlock2D":
+                        x, xs = self._transformer_f(f"down_blocks.{i}.attentions.{j}", x, xs, kv_all, batch, self.heads[i], s_ctx)
+                    skips.append(x)
+                if i != self.nb - 1:
+                    d = self.w[f"down_blocks.{i}.downsamplers.0.conv"]
+                    st = {}
+                    x = L.conv3x3(x, d["w"], d["b"], stride=2, stats=st)
+                    xs = st.get("chan")
+                    skips.append(x)
+            x, xs = self._resnet_f("mid_block.resnets.0", x, xs, None, None, temb_all)
+            x, xs = self._transformer_f("mid_block.attentions.0", x, xs, kv_all, batch, self.heads[-1], s_ctx)
+            x, xs = self._resnet_f("mid_block.resnets.1", x, xs, None, None, temb_all)
+        else:
+            x = L.conv3x3(sample, self.w["conv_in"]["w"], self.w["conv_in"]["b"], e)   # conv_in(sample) + embedding
+            skips = [x]
+            for i, typ in enumerate(self.down_types):
+                for j in range(self.lpb):
+                    x = self._resnet(f"down_blocks.{i}.resnets.{j}", x, None, temb_all)
+                    if typ == "CrossAttnDownBlock2D":
+                        x = self._transformer(f"down_blocks.{i}.attentions.{j}", x, kv_all, batch, self.heads[i], s_ctx)
+                    skips.append(x)
+                if i != self.nb - 1:
+                    d = self.w[f"down_blocks.{i}.downsamplers.0.conv"]
+                    x = L.conv3x3(x, d["w"], d["b"], stride=2)
+                    skips.append(x)
+            x = self._resnet("mid_block.resnets.0", x, None, temb_all)
+            x = self._transformer("mid_block.attentions.0", x, kv_all, batch, self.heads[-1], s_ctx)
+            x = self._resnet("mid_block.resnets.1", x, None, temb_all)
         outs = []
         for s, (w, b) in zip(skips, self.zero_convs):
             n, h, wd, c = s.shape
@@ -114,6 +139,30 @@ class ControlNetModel(B200Model):
         self._t = torch.zeros(batch, dtype=torch.float32, device=dev)
         self._ctx = torch.zeros(spec["encoder_hidden_states"]["shape"], dtype=torch.float16, device=dev)
         self._cond = torch.zeros(spec["controlnet_cond"]["shape"], dtype=torch.float16, device=dev)
+        self._kv_all = (torch.zeros(batch * seq_len, e.kv_total, dtype=torch.float16, device=dev)
+                        if e.kv_w is not None else None)
+        self._emb = None     # conditioning embedding of `_cond` (device loop prologue)
+        self._table = None   # time-embedding biases of all steps (device loop prologue)
+
+    # -- per-prompt prologue + per-step core of the device loop (pipeline.denoise) ------------------------------
+    def prepare_prompt(self, ts_rows):
+        """Everything that does not change over a denoising loop: cross-attention K/V from `_ctx`, the embedding of
+        the conditioning image `_cond` (the reference recomputes it every step, pipeline.py:516-522), the
+        time-embedding biases of all steps."""
+        e, b = self.engine, self.batch
+        if self._kv_all is not None:
+            e.kv_project(L.ctx_to_tokens(self._ctx), out=self._kv_all)
+        self._emb = e.embed_condition(L.nchw_to_nhwc(self._cond, c_pad=8))
+        n_steps = ts_rows.shape[0] // b
+        per = max(1, 32 // b)
+        parts = [e.time_embedding(ts_rows[s0 * b:(s0 + min(per, n_steps - s0)) * b].contiguous())
+                 for s0 in range(0, n_steps, per)]
+        self._table = torch.cat(parts, 0).reshape(n_steps, b, -1)
+
+    def run_core(self, x_nhwc, step):
+        """Residuals (NHWC fp16) for the UNet input `x_nhwc` at loop step `step` (after prepare_prompt)."""
+        return self.engine.forward(x_nhwc, None, None, self.seq, None, temb_all=self._table[step], kv_all=self._kv_all,
+                                   emb=self._emb)
 
     def _run(self):
         e = self.engine

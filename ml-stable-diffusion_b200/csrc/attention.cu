@@ -387,6 +387,7 @@ using namespace b200sd;
 extern "C" int b200sd_attention(const void* q, const void* k, const void* v, void* out, const float* mask,
                                 int32_t batch, int32_t heads, int32_t sq, int32_t sk, int32_t d, int32_t ldq,
                                 int32_t ldk, int32_t ldv, int32_t ldo, float scale, int32_t impl, void* stream_) {
+    if (!b200sd::launch_class_enabled(2)) return 0;  // bench.py's per-class timing graphs
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     B200SD_REQUIRE(q && k && v && out, "b200sd_attention: null pointer");
     B200SD_REQUIRE(d == kD, "b200sd_attention: head dim %d not supported by this kernel (needs 64)", d);

@@ -47,6 +47,10 @@ int num_sms();
 // executes griddepcontrol.wait before it reads or writes global memory.
 bool pdl_enabled();
 
+// Launch classes (1 GEMM / convolution, 2 attention, 4 normalisation, 8 elementwise): bench.py captures graphs with only
+// one class enabled to attribute the step time per kernel class without event gaps or profiler serialisation.
+bool launch_class_enabled(int cls);
+
 #ifdef __CUDACC__
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,

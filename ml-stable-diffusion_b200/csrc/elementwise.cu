@@ -194,8 +194,15 @@ __global__ void cfg_step_kernel(const float* __restrict__ noise_pred, float* __r
     const int numel = n * c * hw;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= numel) return;
-    const float eu = noise_pred[i];
-    const float ec = noise_pred[numel + i];
+    int ni = i;  // index of this element inside one CFG half of noise_pred
+    if (k.noise_pred_nhwc) {  // the UNet's conv_out output as it leaves the epilogue: [2n, h*w, c]
+        const int p = i % hw;
+        const int ch = (i / hw) % c;
+        const int b = i / (hw * c);
+        ni = (b * hw + p) * c + ch;
+    }
+    const float eu = noise_pred[ni];
+    const float ec = noise_pred[numel + ni];
     const float eps = eu + k.guidance * (ec - eu);
     const float x = latents[i];
     float xp = k.cx * x + k.ce * eps;
@@ -269,6 +276,7 @@ using namespace b200sd;
 
 extern "C" int b200sd_nchw_to_nhwc(const void* in, int32_t in_f32, void* out, int32_t n, int32_t c, int32_t h,
                                    int32_t w, int32_t c_pad, void* stream_) {
+    if (!b200sd::launch_class_enabled(8)) return 0;  // bench.py's per-class timing graphs
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     B200SD_REQUIRE(in && out && c_pad >= c, "b200sd_nchw_to_nhwc: bad arguments");
     const size_t total = static_cast<size_t>(n) * h * w * c_pad;
@@ -287,6 +295,7 @@ extern "C" int b200sd_nchw_to_nhwc(const void* in, int32_t in_f32, void* out, in
 
 extern "C" int b200sd_nhwc_to_nchw_f32(const void* in, int32_t in_f32, float* out, int32_t n, int32_t c, int32_t h,
                                        int32_t w, int32_t c_pad, void* stream_) {
+    if (!b200sd::launch_class_enabled(8)) return 0;  // bench.py's per-class timing graphs
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     B200SD_REQUIRE(in && out && c_pad >= c, "b200sd_nhwc_to_nchw_f32: bad arguments");
     const size_t total = static_cast<size_t>(n) * c * h * w;
@@ -303,6 +312,7 @@ extern "C" int b200sd_nhwc_to_nchw_f32(const void* in, int32_t in_f32, float* ou
 
 extern "C" int b200sd_ctx_to_tokens(const void* in, int32_t in_f32, void* out, int32_t b, int32_t d, int32_t s,
                                     void* stream_) {
+    if (!b200sd::launch_class_enabled(8)) return 0;  // bench.py's per-class timing graphs
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     B200SD_REQUIRE(in && out, "b200sd_ctx_to_tokens: null pointer");
     dim3 grid((s + 31) / 32, (d + 31) / 32, b), block(32, 8);
@@ -319,6 +329,7 @@ extern "C" int b200sd_ctx_to_tokens(const void* in, int32_t in_f32, void* out, i
 
 extern "C" int b200sd_embed_tokens(const float* ids, const void* token_embedding, const void* position_embedding,
                                    void* out, int32_t batch, int32_t s, int32_t d, int32_t vocab, void* stream_) {
+    if (!b200sd::launch_class_enabled(8)) return 0;  // bench.py's per-class timing graphs
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     B200SD_REQUIRE(ids && token_embedding && position_embedding && out && d % 8 == 0 && vocab > 0,
                    "b200sd_embed_tokens: bad arguments (d=%d must be a multiple of 8)", d);
@@ -334,6 +345,7 @@ extern "C" int b200sd_embed_tokens(const float* ids, const void* token_embedding
 
 extern "C" int b200sd_upsample2x(const void* in, void* out, int32_t n, int32_t h, int32_t w, int32_t c,
                                  void* stream_) {
+    if (!b200sd::launch_class_enabled(8)) return 0;  // bench.py's per-class timing graphs
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     B200SD_REQUIRE(in && out && c % 8 == 0, "b200sd_upsample2x: c=%d must be a multiple of 8", c);
     const size_t total = static_cast<size_t>(n) * 4 * h * w * (c / 8);
@@ -345,6 +357,7 @@ extern "C" int b200sd_upsample2x(const void* in, void* out, int32_t n, int32_t h
 }
 
 extern "C" int b200sd_add(const void* a, const void* b, void* out, size_t numel, void* stream_) {
+    if (!b200sd::launch_class_enabled(8)) return 0;  // bench.py's per-class timing graphs
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     B200SD_REQUIRE(a && b && out && numel % 2 == 0, "b200sd_add: bad arguments");
     B200SD_CHECK_CUDA(launch_kernel(add_kernel, dim3(grid_for(numel / 2, 256)), dim3(256), 0, stream, reinterpret_cast<const __half2*>(a),
@@ -357,6 +370,7 @@ extern "C" int b200sd_add(const void* a, const void* b, void* out, size_t numel,
 
 extern "C" int b200sd_linear_small(const float* x, const void* wgt, const float* bias, const float* add, float* out,
                                    int32_t m, int32_t n, int32_t k, int32_t act_in, int32_t act_out, void* stream_) {
+    if (!b200sd::launch_class_enabled(8)) return 0;  // bench.py's per-class timing graphs
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     B200SD_REQUIRE(x && wgt && out, "b200sd_linear_small: null pointer");
     B200SD_REQUIRE(m >= 1 && m <= 32 && k % 8 == 0, "b200sd_linear_small: need 1 <= m <= 32 and k %% 8 == 0 (m=%d k=%d)",
@@ -379,6 +393,7 @@ extern "C" int b200sd_linear_small(const float* x, const void* wgt, const float*
 
 extern "C" int b200sd_timestep_embedding(const float* timesteps, float* out, int32_t m, int32_t dim,
                                          int32_t flip_sin_to_cos, float freq_shift, void* stream_) {
+    if (!b200sd::launch_class_enabled(8)) return 0;  // bench.py's per-class timing graphs
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     B200SD_REQUIRE(timesteps && out && dim % 2 == 0, "b200sd_timestep_embedding: bad arguments");
     const int total = m * (dim / 2);
@@ -392,6 +407,7 @@ extern "C" int b200sd_timestep_embedding(const float* timesteps, float* out, int
 extern "C" int b200sd_cfg_scheduler_step(const float* noise_pred, float* latents, float* hist, float* denoised,
                                          void* unet_in, int32_t c_pad, int32_t n, int32_t c, int32_t h, int32_t w,
                                          const b200sd_step_coeffs* coeffs, void* stream_) {
+    if (!b200sd::launch_class_enabled(8)) return 0;  // bench.py's per-class timing graphs
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     B200SD_REQUIRE(noise_pred && latents && coeffs, "b200sd_cfg_scheduler_step: null pointer");
     B200SD_REQUIRE(coeffs->n_hist >= 0 && coeffs->n_hist <= 4 && (coeffs->n_hist == 0 || hist),
@@ -410,6 +426,7 @@ extern "C" int b200sd_cfg_scheduler_step(const float* noise_pred, float* latents
 
 extern "C" int b200sd_image_postprocess(const void* in, int32_t in_f32, int32_t c_pad, float* out_f32,
                                         uint8_t* out_u8, int32_t n, int32_t h, int32_t w, int32_t c, void* stream_) {
+    if (!b200sd::launch_class_enabled(8)) return 0;  // bench.py's per-class timing graphs
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     B200SD_REQUIRE(in && (out_f32 || out_u8), "b200sd_image_postprocess: null pointer");
     const size_t pixels = static_cast<size_t>(n) * h * w;
@@ -426,6 +443,7 @@ extern "C" int b200sd_image_postprocess(const void* in, int32_t in_f32, int32_t 
 
 extern "C" int b200sd_latent_prep(const float* z, const float* w, const float* b, float inv_scale, void* out,
                                   int32_t n, int32_t c, int32_t h, int32_t wd, int32_t c_pad, void* stream_) {
+    if (!b200sd::launch_class_enabled(8)) return 0;  // bench.py's per-class timing graphs
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     B200SD_REQUIRE(z && w && out && c >= 1 && c <= 8 && c_pad >= c, "b200sd_latent_prep: bad arguments");
     const int total = n * h * wd;

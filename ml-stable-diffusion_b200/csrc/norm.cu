@@ -501,6 +501,7 @@ extern "C" size_t b200sd_group_norm_workspace_bytes(int32_t n_img, int32_t hw, i
 extern "C" int b200sd_group_norm(const void* x0, const void* x1, int32_t c0, int32_t c1, int32_t n_img, int32_t hw,
                                  int32_t groups, float eps, const float* gamma, const float* beta, int32_t silu,
                                  void* out, float* stats_ws, size_t stats_ws_bytes, void* stream_) {
+    if (!b200sd::launch_class_enabled(4)) return 0;  // bench.py's per-class timing graphs
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     const int C = c0 + c1;
     B200SD_REQUIRE(x0 && out && gamma && beta && stats_ws, "b200sd_group_norm: null pointer");
@@ -601,6 +602,7 @@ extern "C" int b200sd_group_norm(const void* x0, const void* x1, int32_t c0, int
 
 extern "C" int b200sd_layer_norm(const void* x, const float* gamma, const float* beta, void* out, int32_t rows,
                                  int32_t c, float eps, void* stream_) {
+    if (!b200sd::launch_class_enabled(4)) return 0;  // bench.py's per-class timing graphs
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     B200SD_REQUIRE(x && gamma && beta && out, "b200sd_layer_norm: null pointer");
     B200SD_REQUIRE(c % 8 == 0 && c > 0 && c <= 2048, "b200sd_layer_norm: c=%d must be a multiple of 8, <= 2048", c);
@@ -622,6 +624,7 @@ extern "C" int b200sd_layer_norm(const void* x, const float* gamma, const float*
 
 extern "C" int b200sd_softmax_rows(const float* in, void* out, int32_t rows, int32_t cols, float scale,
                                    void* stream_) {
+    if (!b200sd::launch_class_enabled(4)) return 0;  // bench.py's per-class timing graphs
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     B200SD_REQUIRE(in && out && rows > 0 && cols > 0, "b200sd_softmax_rows: bad arguments");
     B200SD_CHECK_CUDA(launch_kernel(softmax_rows_kernel, dim3(rows), dim3(256), 0, stream, in, reinterpret_cast<__half*>(out), cols,

@@ -22,6 +22,10 @@ void set_error(const char* fmt, ...) {
 void count_launch(int n) { g_launches.fetch_add(static_cast<uint64_t>(n), std::memory_order_relaxed); }
 
 static int g_pdl = -1;
+static std::atomic<uint32_t> g_class_mask{0xFu};
+
+bool launch_class_enabled(int cls) { return (g_class_mask.load(std::memory_order_relaxed) & static_cast<uint32_t>(cls)) != 0; }
+
 
 bool pdl_enabled() {
     if (g_pdl < 0) {
@@ -97,3 +101,4 @@ extern "C" const char* b200sd_last_error(void) { return b200sd::g_error; }
 extern "C" int b200sd_version(void) { return 1; }
 extern "C" uint64_t b200sd_launch_count(void) { return b200sd::g_launches.load(); }
 extern "C" void b200sd_set_pdl(int enabled) { b200sd::g_pdl = enabled ? 1 : 0; }
+extern "C" void b200sd_set_launch_classes(uint32_t mask) { b200sd::g_class_mask.store(mask & 0xFu); }

@@ -44,6 +44,7 @@ class StepCoeffs(C.Structure):
         ("guidance", C.c_float), ("cx", C.c_float), ("ce", C.c_float), ("ch", C.c_float * 4),
         ("x0_cx", C.c_float), ("x0_ce", C.c_float), ("x0_ch", C.c_float * 4), ("n_hist", C.c_int32),
         ("push_eps_slot", C.c_int32), ("push_x0_slot", C.c_int32), ("push_x_slot", C.c_int32),
+        ("noise_pred_nhwc", C.c_int32),
     ]
 
 
@@ -52,6 +53,7 @@ _SIGNATURES = {
     "b200sd_version": (C.c_int, []),
     "b200sd_launch_count": (C.c_uint64, []),
     "b200sd_set_pdl": (None, [C.c_int]),
+    "b200sd_set_launch_classes": (None, [C.c_uint32]),
     "b200sd_gemm": (C.c_int, [C.POINTER(GemmArgs), C.c_void_p]),
     "b200sd_gemm_workspace_bytes": (C.c_size_t, [C.POINTER(GemmArgs)]),
     "b200sd_gemm_plan": (C.c_int, [C.POINTER(GemmArgs), C.POINTER(C.c_int32)]),
@@ -306,7 +308,17 @@ def _fused_args(args, x_dev, *, n_img, cout, gn=None, stats=None, cs_hw=0, ln=No
             args.cs_hw = cs_hw
         if rowstats is not None:
             args.rs_out = 1
-        pl = plan_ex(args)
+        try:
+            pl = plan_ex(args)
+        except B200SDError:
+            if stats is None:
+                raise
+            # this geometry cannot emit column statistics (e.g. images smaller than 16 pixels): the caller sees no
+            # 'chan' entry and its consumer falls back to the standalone GroupNorm kernel
+            args.cs_partial, args.cs_hw, stats = None, 0, None
+            if rowstats is None:
+                return keep
+            pl = plan_ex(args)
         n_tiles, slots = pl[3], pl[4]
         if stats is not None:
             if n_img * n_tiles > (1 << 16):
@@ -456,12 +468,15 @@ def attention(q, k, v, batch, heads, sq, sk, d=64, mask=None, impl=0, out=None, 
     return out
 
 
-def nchw_to_nhwc(x, c_pad=None):
+def nchw_to_nhwc(x, c_pad=None, out=None):
     n, c, h, w = x.shape
     c_pad = c if c_pad is None else c_pad
     if x.dtype not in (torch.float16, torch.float32) or not x.is_contiguous():
         raise B200SDError("nchw_to_nhwc: expected contiguous fp16/fp32")
-    out = torch.empty(n, h, w, c_pad, dtype=torch.float16, device=x.device)
+    if out is None:
+        out = torch.empty(n, h, w, c_pad, dtype=torch.float16, device=x.device)
+    elif out.dtype != torch.float16 or not out.is_contiguous() or tuple(out.shape) != (n, h, w, c_pad):
+        raise B200SDError("nchw_to_nhwc: bad output buffer")
     _check(load().b200sd_nchw_to_nhwc(_ptr(x), int(x.dtype == torch.float32), _ptr(out), n, c, h, w, c_pad,
                                       _stream()), "b200sd_nchw_to_nhwc")
     return out

@@ -85,6 +85,12 @@ class UNetModel(B200Model):
                              if e.xl else None)
         self._res = [torch.zeros(s, dtype=torch.float16, device=dev) for s in self.res_shapes]
         self._out = torch.zeros(batch, e.out_ch, height, width, dtype=torch.float32, device=dev)
+        # device-resident loop (pipeline.denoise): the UNet input as the kernels read it (NHWC fp16, written by the
+        # fused CFG + scheduler kernel), the per-prompt cross-attention K/V, the conv_out epilogue's NHWC output
+        self._x_nhwc = torch.zeros(batch, height, width, e.in_pad, dtype=torch.float16, device=dev)
+        self._kv_all = (torch.zeros(batch * seq_len, e.kv_total, dtype=torch.float16, device=dev)
+                        if e.kv_w is not None else None)
+        self._out_nhwc = torch.zeros(batch, height, width, e.out_ch, dtype=torch.float32, device=dev)
         self._graph = None
         self.use_cuda_graph = use_cuda_graph
         self.launches_per_call = None
@@ -111,6 +117,33 @@ class UNetModel(B200Model):
         res = [L.nchw_to_nhwc(r) for r in self._res] if self._res else None
         out = e.forward(x, self._t, ctx, self.seq, self._time_ids, self._text_embeds, res)
         L.nhwc_to_nchw_f32(out, c=e.out_ch, out=self._out)
+
+    # -- per-prompt prologue + per-step core of the device loop (pipeline.denoise) ------------------------------
+    def prepare_prompt(self):
+        """Cross-attention keys / values of every block from ``_ctx`` (constant over the denoising loop)."""
+        if self._kv_all is not None:
+            self.engine.kv_project(L.ctx_to_tokens(self._ctx), out=self._kv_all)
+
+    def time_table(self, ts_rows):
+        """ts_rows: fp32 device tensor [n_steps * batch] (each step's timestep repeated per batch row) ->
+        [n_steps, batch, sum Cout] time-embedding biases of every ResNet block for ALL steps (unet.py:442,476-478
+        depend on t only): one small-M pass per 32 rows instead of three launches inside every step."""
+        e, b = self.engine, self.batch
+        n_steps = ts_rows.shape[0] // b
+        per = max(1, 32 // b)
+        parts = []
+        for s0 in range(0, n_steps, per):
+            k = min(per, n_steps - s0)
+            tid = self._time_ids.repeat(k, 1) if e.xl else None
+            te = self._text_embeds.repeat(k, 1) if e.xl else None
+            parts.append(e.time_embedding(ts_rows[s0 * b:(s0 + k) * b].contiguous(), tid, te))
+        return torch.cat(parts, 0).reshape(n_steps, b, -1)
+
+    def _run_core(self, temb, residuals=None):
+        """One UNet forward on ``_x_nhwc`` with precomputed time-embedding biases ``temb`` [batch, sum Cout] and the
+        prologue's K/V; the conv_out epilogue writes ``_out_nhwc``."""
+        self.engine.forward(self._x_nhwc, None, None, self.seq, additional_residuals=residuals, temb_all=temb,
+                            kv_all=self._kv_all, out=self._out_nhwc)
 
     def _launch(self):
         if not self.use_cuda_graph:

@@ -143,7 +143,7 @@ class B200StableDiffusionPipeline:
             esd = C.random_state_dict(C.vae_encoder_param_shapes(vae_cfg), seed=seed + 50, dtype=torch.float16)
             venc = VAEEncoderModel(vae_cfg, esd, batch=images_per_call, height=height, width=width, device=device)
         return cls(unet, vae, scheduler=scheduler, xl=unet.engine.xl, controlnet=nets, text_encoder=enc,
-                   tokenizer=tokenizer, vae_encoder=venc)
+                   tokenizer=tokenizer, vae_encoder=venc, force_zeros_for_empty_prompt=unet.engine.xl)
 
     # ---------------------------------------------------------------- reference-named helpers
     def check_inputs(self, prompt, height, width, callback_steps):
@@ -163,15 +163,23 @@ class B200StableDiffusionPipeline:
     def _encode_prompt(self, prompts, do_cfg, negative_prompt):
         """-> (2B, D, 1, S) fp16 array, uncond half first (pipeline.py:123-257: concat [neg, pos], :252 transpose)."""
         conds = [self._encode_one(p) for p in prompts]
-        negs = negative_prompt if isinstance(negative_prompt, list) else [negative_prompt or ""] * len(prompts)
+        if isinstance(negative_prompt, list):
+            if len(negative_prompt) != len(prompts):
+                raise ValueError(f"`negative_prompt` has batch size {len(negative_prompt)}, but `prompt` has batch size "
+                                 f"{len(prompts)}")
+            negs = list(negative_prompt)
+        else:
+            negs = [negative_prompt] * len(prompts)
         unconds = []
         for ng, cnd in zip(negs, conds):
             if not do_cfg:
                 unconds.append(cnd)
-            elif ng == "" and self.force_zeros_for_empty_prompt:
-                unconds.append(np.zeros_like(cnd))  # pipeline.py:183-184
+            elif ng is None and self.force_zeros_for_empty_prompt:
+                # pipeline.py:183-184: zeros only when NO negative prompt was given and the flag is set (the
+                # reference's CLI sets it for SDXL only, pipeline.py:744-755); an explicit "" is encoded
+                unconds.append(np.zeros_like(cnd))
             else:
-                unconds.append(self._encode_one(ng))
+                unconds.append(self._encode_one(ng or ""))
         emb = np.stack(unconds + conds, 0)  # (2B, S, D)
         return np.ascontiguousarray(emb.transpose(0, 2, 1)[:, :, None, :]).astype(np.float16)
 
@@ -213,10 +221,18 @@ class B200StableDiffusionPipeline:
             emb, pooled = np.concatenate([neg, emb], 0), np.concatenate([neg_pooled, pooled], 0)
         return np.ascontiguousarray(emb.transpose(0, 2, 1)[:, :, None, :]).astype(np.float16), pooled
 
-    def prepare_latents(self, batch, channels, height, width, latents=None):
-        """pipeline.py:322-344: np.random.randn(...).astype(fp16) * init_noise_sigma."""
+    def prepare_latents(self, batch, channels, height, width, latents=None, seed=None, rng="numpy"):
+        """pipeline.py:322-344: np.random.randn(...).astype(fp16) * init_noise_sigma (the global numpy stream, seeded by
+        the caller like pipeline.py:725-726).  With ``seed``: the Swift pipeline's ``generateLatentSamples``
+        (StableDiffusionPipeline.swift:361-379): one draw of C*h*w normals per image from the chosen
+        ``StableDiffusionRNG`` source (numpy / torch / nvidia, rng.py), so a seed reproduces the reference CLIs' latents."""
         shape = (batch, channels, height // self.vae_scale_factor, width // self.vae_scale_factor)
-        if latents is None:
+        if latents is None and seed is not None:
+            from .rng import random_source
+            src = random_source(rng, seed)
+            per = int(np.prod(shape[1:]))
+            latents = np.stack([src.normal_array(per).reshape(shape[1:]) for _ in range(batch)]).astype(np.float32)
+        elif latents is None:
             latents = np.random.randn(*shape).astype(np.float16)
         elif tuple(latents.shape) != shape:
             raise ValueError(f"Unexpected latents shape, got {latents.shape}, expected {shape}")
@@ -270,34 +286,72 @@ class B200StableDiffusionPipeline:
                                                                     st.push_x0_slot, st.push_x_slot)
         return k
 
-    def _loop_on_static_buffers(self, plan, guidance_scale):
-        """The whole N-step loop on the UNet's static input buffers (no host-side tensor arguments): what the
-        loop graph captures.  Per step: timestep fill, latents -> both CFG halves of `sample`, the UNet launch
-        sequence, one fused CFG + scheduler kernel (its coefficients are baked into the launch)."""
+    def _loop_on_static_buffers(self, plan, guidance_scale, ts_rows, use_controlnet=False):
+        """The whole N-step loop on static device buffers (no host-side tensor arguments): what the loop graph
+        captures.  Prologue, once per prompt: cross-attention K/V of all blocks from the text states, the
+        time-embedding biases of all ResNet blocks for ALL timesteps (`ts_rows`: each step's timestep repeated per
+        batch row, a device tensor made outside the capture), the first UNet input.  Per step: the UNet launch
+        sequence and ONE fused kernel for guidance + scheduler update, which also writes the next step's UNet
+        input (fp16 NHWC, both CFG halves: pipeline.py:502 np.concatenate([latents] * 2)) -- no fill / copy /
+        layout kernels in between."""
         u, n = self.unet, self.images_per_call
         self._hist.zero_()
-        for st in plan:
-            u._t.fill_(float(st.timestep))
-            u._sample[:n].copy_(self._latents)   # pipeline.py:502 np.concatenate([latents] * 2)
-            u._sample[n:].copy_(self._latents)
-            u._run()
-            L.cfg_scheduler_step(u._out, self._latents, self._coeffs(st, guidance_scale), hist=self._hist,
-                                 denoised=self._denoised)
+        u.prepare_prompt()
+        table = u.time_table(ts_rows)
+        L.nchw_to_nhwc(self._latents, c_pad=u.engine.in_pad, out=u._x_nhwc[:n])
+        L.nchw_to_nhwc(self._latents, c_pad=u.engine.in_pad, out=u._x_nhwc[n:])
+        if use_controlnet:
+            self.prepare_controlnets(ts_rows)
+        for i, st in enumerate(plan):
+            u._run_core(table[i], self.controlnet_residuals(i) if use_controlnet else None)
+            k = self._coeffs(st, guidance_scale)
+            k.noise_pred_nhwc = 1
+            L.cfg_scheduler_step(u._out_nhwc, self._latents, k, hist=self._hist, denoised=self._denoised,
+                                 unet_in=u._x_nhwc)
 
-    def _loop_graph_for(self, key, plan, guidance_scale):
+    def set_control_conditions(self, controlnet_cond):
+        """Copy the conditioning images (each (2B, 3, H, W)) into the ControlNets' static input buffers."""
+        for module, cond in zip(self.controlnet, controlnet_cond):
+            module._cond.copy_(torch.as_tensor(cond))
+
+    def prepare_controlnets(self, ts_rows):
+        """Device-loop prologue of every ControlNet: text states, the embedding of its conditioning image (static
+        buffer `_cond`), time-embedding table."""
+        for module in self.controlnet:
+            module._ctx.copy_(self.unet._ctx)
+            module.prepare_prompt(ts_rows)
+
+    def controlnet_residuals(self, step, _temb=None):
+        """pipeline.py:259-284 inside the device loop: every ControlNet sees the UNet's input; residuals are summed."""
+        total = None
+        for module in self.controlnet:
+            outs = module.run_core(self.unet._x_nhwc, step)
+            if total is None:
+                total = list(outs)
+            else:
+                total = [L.add(acc, o) for acc, o in zip(total, outs)]
+        return total
+
+    def _ts_rows(self, plan):
+        return torch.tensor([float(st.timestep) for st in plan for _ in range(self.unet.batch)], dtype=torch.float32,
+                            device=self.device)
+
+    def _loop_graph_for(self, key, plan, guidance_scale, use_controlnet=False):
         g = self._loop_graphs.get(key)
         if g is None:
             keep = self._latents.clone()
+            ts_rows = self._ts_rows(plan)
             s = torch.cuda.Stream(device=self.device)  # eager warm-up off the capture: workspaces, weight tiling
             s.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(s):
-                self._loop_on_static_buffers(plan[:1], guidance_scale)
+                self._loop_on_static_buffers(plan[:1], guidance_scale, ts_rows[: self.unet.batch], use_controlnet)
             torch.cuda.current_stream().wait_stream(s)
             torch.cuda.synchronize()
             self._latents.copy_(keep)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                self._loop_on_static_buffers(plan, guidance_scale)
+                self._loop_on_static_buffers(plan, guidance_scale, ts_rows, use_controlnet)
+            g._b200sd_keep = ts_rows
             self._latents.copy_(keep)  # capture does not execute, but keep the contract obvious
             if len(self._loop_graphs) >= 4:
                 self._loop_graphs.pop(next(iter(self._loop_graphs)))
@@ -319,14 +373,17 @@ class B200StableDiffusionPipeline:
         self._latents.copy_(torch.as_tensor(latents), non_blocking=True)
         if controlnet_cond:
             controlnet_cond = [torch.as_tensor(c).to(self.device, torch.float16) for c in controlnet_cond]
-        if self.loop_graph and callback is None and record is None and not controlnet_cond:
+        if self.loop_graph and callback is None and record is None:
             u = self.unet
             u._ctx.copy_(self._ctx)
             if u.engine.xl:
                 u._time_ids.copy_(torch.as_tensor(time_ids).reshape(u._time_ids.shape))
                 u._text_embeds.copy_(torch.as_tensor(text_embeds))
-            key = (self.scheduler_name, int(num_inference_steps), float(guidance_scale), int(start_step))
-            self._loop_graph_for(key, plan, guidance_scale).replay()
+            if controlnet_cond:
+                self.set_control_conditions(controlnet_cond)
+            key = (self.scheduler_name, int(num_inference_steps), float(guidance_scale), int(start_step),
+                   bool(controlnet_cond))
+            self._loop_graph_for(key, plan, guidance_scale, bool(controlnet_cond)).replay()
             return self._denoised if return_denoised else self._latents
         self._hist.zero_()
         k = L.StepCoeffs()
@@ -361,7 +418,7 @@ class B200StableDiffusionPipeline:
                  return_dict=True, callback=None, callback_steps=1, controlnet_cond=None,
                  original_size: Optional[Tuple[int, int]] = None, crops_coords_top_left: Tuple[int, int] = (0, 0),
                  target_size: Optional[Tuple[int, int]] = None, unet_batch_one=False, prompt_embeds=None,
-                 starting_image=None, strength=0.5, **kwargs):
+                 starting_image=None, strength=0.5, seed=None, rng="numpy", **kwargs):
         """``starting_image`` ((B, 3, H, W) in [-1, 1], the vae_encoder input) + ``strength`` select the Swift
         pipeline's image-to-image mode (StableDiffusionPipeline.swift:250-262, 361-378): the encoded image is noised
         to timestep ``timeSteps[startStep]`` and only the remaining steps run."""
@@ -399,7 +456,7 @@ class B200StableDiffusionPipeline:
                 text_embeds = torch.as_tensor(xl_pooled, dtype=torch.float32, device=self.device)
             if text_embeds is None:
                 text_embeds = torch.zeros(2 * self.images_per_call, 1280, device=self.device)
-        lat = self.prepare_latents(len(prompts), self.unet.in_channels, height, width, latents)
+        lat = self.prepare_latents(len(prompts), self.unet.in_channels, height, width, latents, seed=seed, rng=rng)
         start_step = 0
         if starting_image is not None:
             if self.vae_encoder is None:

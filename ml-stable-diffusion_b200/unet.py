@@ -326,7 +326,7 @@ class UNetEngine:
         out = L.linear(tok, t["po"], t["pob"], x.reshape(m, c), static_w=True, stats=st if ok else None, cs_hw=s)
         return out.reshape(n, h, wd, c), st.get("chan")
 
-    def _forward_fused(self, sample, temb_all, kv_all, batch, s_ctx, additional_residuals):
+    def _forward_fused(self, sample, temb_all, kv_all, batch, s_ctx, additional_residuals, out=None):
         st = {}
         x = L.conv3x3(sample, self.w["conv_in"]["w"], self.w["conv_in"]["b"], stats=st)
         xs = st.get("chan")
@@ -364,7 +364,8 @@ class UNetEngine:
                 x = L.conv3x3(x, u["w"], u["b"], halo=True, upsample=True, stats=st)
                 xs = st.get("chan")
         o = self.w["out"]
-        return self._gn_conv(x, xs, None, None, o["g"], o["b"], self.eps, True, o["w"], o["cb"], out_dtype=torch.float32)
+        return self._gn_conv(x, xs, None, None, o["g"], o["b"], self.eps, True, o["w"], o["cb"], out_dtype=torch.float32,
+                             out=out)
 
     # ------------------------------------------------------------------ forward
     def time_embedding(self, timesteps, time_ids=None, text_embeds=None):
@@ -383,16 +384,25 @@ class UNetEngine:
             emb = emb + aug
         return L.linear_small(emb, self.temb_w, self.temb_b, act_in=True)
 
+    def kv_project(self, ctx_tokens, out=None):
+        """to_k | to_v of every cross-attention block on the text states (unet.py:79-82): one GEMM.  The text states
+        do not change during a denoising loop, so the pipeline calls this once per prompt, not once per step."""
+        return L.linear(ctx_tokens, self.kv_w, static_w=True, out=out) if self.kv_w is not None else None
+
     def forward(self, sample, timesteps, ctx_tokens, s_ctx, time_ids=None, text_embeds=None,
-                additional_residuals=None):
+                additional_residuals=None, temb_all=None, kv_all=None, out=None):
         """sample: NHWC fp16 [B, H, W, in_pad]; timesteps fp32 [B]; ctx_tokens fp16 [B*s_ctx, D].
         additional_residuals: list of NHWC fp16 tensors (ControlNet, unet.py:1009-1022).
+        temb_all / kv_all: precomputed time-embedding biases [B, sum Cout] / cross-attention keys and values (the
+        per-prompt prologue of the pipeline's loop); out: optional fp32 NHWC output buffer.
         Returns noise_pred NHWC fp32 [B, H, W, out_ch]."""
         batch = sample.shape[0]
-        temb_all = self.time_embedding(timesteps, time_ids, text_embeds)
-        kv_all = L.linear(ctx_tokens, self.kv_w, static_w=True) if self.kv_w is not None else None
+        if temb_all is None:
+            temb_all = self.time_embedding(timesteps, time_ids, text_embeds)
+        if kv_all is None:
+            kv_all = self.kv_project(ctx_tokens)
         if self.fused:
-            return self._forward_fused(sample, temb_all, kv_all, batch, s_ctx, additional_residuals)
+            return self._forward_fused(sample, temb_all, kv_all, batch, s_ctx, additional_residuals, out)
         x = L.conv3x3(sample, self.w["conv_in"]["w"], self.w["conv_in"]["b"])
         skips = [x]
         for i, typ in enumerate(self.down_types):
@@ -423,4 +433,4 @@ class UNetEngine:
                 x = L.conv3x3(L.upsample2x(x), u["w"], u["b"])
         o = self.w["out"]
         x = L.group_norm(x, o["g"], o["b"], self.groups, self.eps, silu=True)
-        return L.conv3x3(x, o["w"], o["cb"], out_dtype=torch.float32)
+        return L.conv3x3(x, o["w"], o["cb"], out_dtype=torch.float32, out=out)
