@@ -70,7 +70,7 @@ class B200StableDiffusionPipeline:
 
     def __init__(self, unet: UNetModel, vae_decoder: VAEDecoderModel, scheduler="DDIM", text_encoder=None,
                  tokenizer=None, force_zeros_for_empty_prompt=True, xl=False, controlnet=None, loop_graph=True,
-                 vae_encoder=None, text_encoder_2=None, tokenizer_2=None):
+                 vae_encoder=None, text_encoder_2=None, tokenizer_2=None, scheduler_kwargs=None):
         self.unet = unet
         self.text_encoder_2 = text_encoder_2  # SDXL: CLIPTextModelWithProjection slot (pipeline.py:64-65, 136-141)
         self.tokenizer_2 = tokenizer_2
@@ -82,6 +82,11 @@ class B200StableDiffusionPipeline:
             raise ValueError("the UNet was not built with support_controlnet=True (no additional_residual inputs)")
         self.vae_decoder = vae_decoder
         self.scheduler_name = scheduler
+        # this class mirrors the reference's PYTHON pipeline, whose DPM-Solver++ is diffusers 0.30.2
+        # (final_sigmas_type="zero"); pass scheduler_kwargs={"final_sigmas_type": "sigma_min"} for the Swift CLI's ending
+        self.scheduler_kwargs = dict(scheduler_kwargs or {})
+        if scheduler == "DPMSolverMultistep":
+            self.scheduler_kwargs.setdefault("final_sigmas_type", "zero")
         self.device = unet.device
         self.xl = xl
         d_ctx = unet.engine.cfg["cross_attention_dim"]
@@ -366,7 +371,7 @@ class B200StableDiffusionPipeline:
         (timestep, noise_pred, latents_after_step) clones per step -- a debugging / testing aid.  Without
         callback / record / ControlNet the whole loop replays as ONE CUDA graph: the scheduler
         history lives on the device and no host synchronisation happens between the first and the last step."""
-        sched = S.make_scheduler(self.scheduler_name, num_inference_steps)
+        sched = S.make_scheduler(self.scheduler_name, num_inference_steps, **self.scheduler_kwargs)
         plan = list(sched.plan(start=start_step)) if start_step else list(sched.plan())
         n = self.images_per_call
         self._ctx.copy_(torch.as_tensor(text_embeddings), non_blocking=True)
@@ -382,7 +387,7 @@ class B200StableDiffusionPipeline:
             if controlnet_cond:
                 self.set_control_conditions(controlnet_cond)
             key = (self.scheduler_name, int(num_inference_steps), float(guidance_scale), int(start_step),
-                   bool(controlnet_cond))
+                   bool(controlnet_cond), tuple(sorted(self.scheduler_kwargs.items())))
             self._loop_graph_for(key, plan, guidance_scale, bool(controlnet_cond)).replay()
             return self._denoised if return_denoised else self._latents
         self._hist.zero_()
@@ -461,7 +466,7 @@ class B200StableDiffusionPipeline:
         if starting_image is not None:
             if self.vae_encoder is None:
                 raise ValueError("a starting image was provided but the pipeline has no vae_encoder")
-            sched = S.make_scheduler(self.scheduler_name, num_inference_steps)
+            sched = S.make_scheduler(self.scheduler_name, num_inference_steps, **self.scheduler_kwargs)
             start_step = sched.start_step(strength)
             if start_step >= num_inference_steps:
                 raise ValueError(f"strength {strength} leaves no denoising steps")

@@ -116,7 +116,19 @@ class DDIMScheduler(_Base):
 class DPMSolverMultistepScheduler(_Base):
     """DPM-Solver++(2M) midpoint, epsilon prediction, 'linspace' spacing; first step and (for < 15
     steps) the last two steps are first order (DPMSolverMultistepScheduler.swift:216-244).
-    History ring: x0 of the previous step in slots 0/1."""
+    History ring: x0 of the previous step in slots 0/1.
+
+    ``final_sigmas_type``: how the LAST step ends.  ``"sigma_min"``: at the first training timestep's (alpha, sigma),
+    what the in-tree Swift scheduler does (``alpha_t[0] / sigma_t[0]``, DPMSolverMultistepScheduler.swift:214-222).
+    ``"zero"``: diffusers 0.30.2's default, which the reference's PYTHON pipeline runs (pipeline.py:565-569 ->
+    ``scheduler.step``): the final sigma is 0, the last step is always first order and lands exactly on the
+    denoised estimate x0."""
+
+    def __init__(self, num_inference_steps, final_sigmas_type="sigma_min", **kw):
+        super().__init__(num_inference_steps, **kw)
+        if final_sigmas_type not in ("sigma_min", "zero"):
+            raise ValueError(f"final_sigmas_type must be 'sigma_min' or 'zero', got {final_sigmas_type!r}")
+        self.final_sigmas_type = final_sigmas_type
 
     def plan(self, start=0):
         n = self.n
@@ -139,7 +151,9 @@ class DPMSolverMultistepScheduler(_Base):
             A = -alpha[p] * (math.exp(-h) - 1.0)
             ch = [0.0] * 4
             slot, prev_slot = i % 2, (i - 1) % 2
-            if first:
+            if i == n - 1 and self.final_sigmas_type == "zero":
+                cx, ce, n_hist = x0_cx, x0_ce, 0      # sigma_next = 0, alpha_next = 1: x_prev = x0 (first order)
+            elif first:
                 cx = sigma[p] / sigma[t] + A * x0_cx
                 ce = A * x0_ce
                 n_hist = 0

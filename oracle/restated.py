@@ -339,9 +339,10 @@ class DPMSolverPP2M:
     """DPM-Solver++(2M), midpoint, epsilon prediction, linspace spacing, lower_order_final
     when < 15 steps (DPMSolverMultistepScheduler.swift:61-126, :135-151, :156-244)."""
 
-    def __init__(self, num_steps, abar=None, n_train=1000):
+    def __init__(self, num_steps, abar=None, n_train=1000, final_sigmas_type="sigma_min"):
         self.abar = alphas_cumprod() if abar is None else abar
         self.n = num_steps
+        self.final_sigmas_type = final_sigmas_type  # "zero": diffusers 0.30.2 default (last step -> x0)
         ts = torch.linspace(0, n_train - 1, num_steps + 1).round().long().flip(0)[:-1]
         self.timesteps = [int(t) for t in ts]
         self.alpha = self.abar.sqrt()
@@ -364,7 +365,9 @@ class DPMSolverPP2M:
         lower_second = (i == self.n - 2) and self.lower_order_final  # Swift :221-222
         order1 = self.lower_order_nums < 1 or lower_final or lower_second
         h = self.lam[p] - self.lam[t]
-        if order1:
+        if i == self.n - 1 and self.final_sigmas_type == "zero":
+            out = x0
+        elif order1:
             out = (self.sigma[p] / self.sigma[t]) * x - self.alpha[p] * (torch.exp(-h) - 1.0) * x0
         else:
             t1 = self.timesteps[i - 1]

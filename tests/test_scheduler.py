@@ -185,3 +185,28 @@ def test_truncated_dpm_and_pndm_plans_match_fresh_oracle_schedulers(n, start):
         eu, ec = f(xr.numpy(), t)
         xr = refp.step(torch.from_numpy(R.cfg_combine(eu, ec, 7.5)), t, xr)
         assert np.allclose(xs[j], xr.numpy(), rtol=1e-8, atol=1e-8), ("pndm", n, start, j)
+
+
+@pytest.mark.parametrize("n", [5, 14, 20])
+def test_dpm_final_sigmas_zero_lands_on_the_denoised_estimate(n):
+    """diffusers 0.30.2 (final_sigmas_type="zero", what the reference's Python pipeline runs, pipeline.py:565-569): the
+    last step is first order with sigma_next = 0, i.e. x_prev = x0; every earlier step equals the Swift-ending plan."""
+    from b200sd import scheduler as S
+    zero = S.DPMSolverMultistepScheduler(n, final_sigmas_type="zero").plan()
+    swift = S.DPMSolverMultistepScheduler(n).plan()
+    for a, b in zip(zero[:-1], swift[:-1]):
+        assert a == b
+    last = zero[-1]
+    assert last.cx == last.x0_cx and last.ce == last.x0_ce and last.n_hist == 0
+    rng = np.random.RandomState(0)
+    x, eu, ec = (rng.randn(4, 8, 8).astype(np.float32) for _ in range(3))
+    hist = [np.zeros_like(x) for _ in range(4)]
+    xp, x0 = S.apply_plan_host(last, 7.5, eu, ec, x, hist)
+    np.testing.assert_array_equal(xp, x0)
+    with pytest.raises(ValueError):
+        S.DPMSolverMultistepScheduler(n, final_sigmas_type="bogus")
+
+
+def test_pipeline_uses_the_diffusers_ending_for_dpm():
+    from b200sd import scheduler as S
+    assert S.make_scheduler("DPMSolverMultistep", 20, final_sigmas_type="zero").final_sigmas_type == "zero"
