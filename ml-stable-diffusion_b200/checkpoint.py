@@ -19,8 +19,12 @@ _SCHEMAS = {
     "unet": C.unet_param_shapes,
     "controlnet": C.controlnet_param_shapes,
     "vae_decoder": C.vae_decoder_param_shapes,
+    "vae_encoder": C.vae_encoder_param_shapes,
     "text_encoder": C.clip_text_param_shapes,
 }
+# AutoencoderKL checkpoints written before diffusers 0.18 name the mid-block attention projections query / key / value /
+# proj_attn (diffusers remaps them when it loads the file); the engines use the current names
+_VAE_ATTN_RENAMES = {".query.": ".to_q.", ".key.": ".to_k.", ".value.": ".to_v.", ".proj_attn.": ".to_out.0."}
 _FILES = ("diffusion_pytorch_model.safetensors", "model.safetensors", "diffusion_pytorch_model.fp16.safetensors",
           "model.fp16.safetensors", "diffusion_pytorch_model.bin", "pytorch_model.bin")
 
@@ -54,10 +58,26 @@ def _canonical(shape):
     return shape[:2] if len(shape) == 4 and shape[2:] == (1, 1) else shape
 
 
+def remap_legacy_vae_keys(sd: dict) -> dict:
+    """Deprecated AutoencoderKL attention names -> current ones (values untouched; [C, C, 1, 1] vs [C, C] is accepted
+    by the shape check below)."""
+    out = {}
+    for k, v in sd.items():
+        if ".attentions." in k:
+            for old, new in _VAE_ATTN_RENAMES.items():
+                if old in k:
+                    k = k.replace(old, new)
+                    break
+        out[k] = v
+    return out
+
+
 def check_state_dict(component: str, cfg: dict, sd: dict, allow_extra=True) -> dict:
     """Validates names and shapes against the architecture schema; returns the subset the engine consumes.
-    ``vae_decoder`` accepts a full AutoencoderKL state dict (encoder / quant_conv entries are dropped)."""
+    ``vae_decoder`` / ``vae_encoder`` accept a full AutoencoderKL state dict (the other half is dropped)."""
     want = _SCHEMAS[component](cfg)
+    if component.startswith("vae"):
+        sd = remap_legacy_vae_keys(sd)
     missing = [k for k in want if k not in sd]
     if missing:
         raise KeyError(f"{component}: {len(missing)} parameters missing from the checkpoint, e.g. {missing[:3]}")
@@ -72,5 +92,16 @@ def check_state_dict(component: str, cfg: dict, sd: dict, allow_extra=True) -> d
 
 def load_component(model_dir: str, component: str, cfg: dict) -> dict:
     """``model_dir`` is a diffusers pipeline directory (``unet/``, ``vae/``, ``text_encoder/``, ...)."""
-    sub = {"unet": "unet", "controlnet": "", "vae_decoder": "vae", "text_encoder": "text_encoder"}[component]
-    return check_state_dict(component, cfg, read_state_dict(os.path.join(model_dir, sub) if sub else model_dir))
+    sub = {"unet": "unet", "controlnet": "", "vae_decoder": "vae", "vae_encoder": "vae", "text_encoder": "text_encoder",
+           "text_encoder_2": "text_encoder_2", "unet_refiner": "unet"}.get(component, component)
+    schema = "text_encoder" if component == "text_encoder_2" else ("unet" if component == "unet_refiner" else component)
+    return check_state_dict(schema, cfg, read_state_dict(os.path.join(model_dir, sub) if sub else model_dir))
+
+
+def read_config(model_dir: str, component: str) -> dict:
+    """``<model_dir>/<component>/config.json`` (scheduler: ``scheduler_config.json``) of a diffusers pipeline directory,
+    reduced to the keys the engines read (private ``_class_name`` / ``_diffusers_version`` entries dropped)."""
+    name = "scheduler_config.json" if component == "scheduler" else "config.json"
+    with open(os.path.join(model_dir, component, name)) as f:
+        cfg = json.load(f)
+    return {k: (tuple(v) if isinstance(v, list) else v) for k, v in cfg.items() if not k.startswith("_")}

@@ -33,7 +33,6 @@ struct __align__(64) AttnParams {
     int sq, sk, ldo;
     int causal;  // 1: key j is visible to query i only if j <= i (CLIP text encoder)
     float scale_log2;  // scale * log2(e)
-    int* error_flag;
 };
 
 // smem layout (1024-aligned): Q | P (2 x 16K, K-chunks of 64 keys) | K[2] | V[2] | barriers
@@ -68,7 +67,9 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
     const int n_half = (sk_eff + kHalf - 1) / kHalf;
 
     if (threadIdx.x == 0) {
-        if ((smem_u32(smem) & 1023u) != 0) atomicExch(p.error_flag, 1);  // swizzle needs 1024 B alignment
+        // SWIZZLE_128B tiles need a 1024-byte aligned base; a padded buffer would cost the second CTA per SM, so a
+        // misaligned launch (never observed: the kernel has no static shared memory) fails loudly instead
+        if ((smem_u32(smem) & 1023u) != 0) __trap();
         prefetch_tmap(&p.tmQ);
         prefetch_tmap(&p.tmK);
         prefetch_tmap(&p.tmV);
@@ -371,15 +372,6 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
     }
 }
 
-static int* attn_error_flag() {
-    static int* flag = nullptr;
-    if (!flag) {
-        if (cudaMalloc(&flag, sizeof(int)) != cudaSuccess) return nullptr;
-        cudaMemset(flag, 0, sizeof(int));
-    }
-    return flag;
-}
-
 }  // namespace b200sd
 
 using namespace b200sd;
@@ -416,8 +408,6 @@ extern "C" int b200sd_attention(const void* q, const void* k, const void* v, voi
     p.ldo = ldo;
     p.causal = (impl & 0x100) ? 1 : 0;
     p.scale_log2 = scale * 1.4426950408889634f;
-    p.error_flag = attn_error_flag();
-    B200SD_REQUIRE(p.error_flag != nullptr, "b200sd_attention: could not allocate the error flag");
     static bool attr_set = false;
     if (!attr_set) {
         B200SD_CHECK_CUDA(

@@ -26,6 +26,7 @@ static constexpr int kAStage = kBM * kBK * 2;  // 16 KiB
 static constexpr int kGemmThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
 static constexpr int kEpiThreads = 256;
 static constexpr int kMaxStages = 8;
+static constexpr int kHaloMaxStages = 24;  // weight ring of the halo kernel (narrow tiles need many stages in flight)
 static constexpr int kSmemBudget = 220 * 1024;
 static constexpr int kEpiFixed = 2 * 256 * 4 + 256 * 4 + 32;  // bias vectors, LayerNorm fold vector, flags
 
@@ -67,6 +68,7 @@ struct __align__(64) GemmParams {
     float* partial;
     // ---- mode 2 (halo-reuse 3x3 convolution): the image is walked in padded-linear order q = y * (W + 1) + x ----
     int H, W, Wp, tiles_per_img, patch_rows, patch_bytes, upsample;
+    int win, tw, th, tiles_x;  // mode 2 windowed tiling (wide images): tiles of th rows x tw columns, pitch Wp = tw + halo
     int desc_bo;            // 1: row-shifted A descriptors carry (address >> 7) & 7 in the matrix-base-offset field
     const __half* a0;       // raw NHWC sources (loader warps read them with plain loads)
     const __half* a1;
@@ -96,6 +98,9 @@ struct __align__(64) GemmParams {
 struct TileCoord {
     int m_tile, n_tile, split;
     int n0, h0, w0;  // conv: output-space origin of the 128-pixel box
+    // mode 2: output row r of the tile is patch pixel c0 + r; patch pixel i is image pixel (ya + i / P, xa + i % P);
+    // rows whose pixel falls outside [ylo, yhi) x [xlo, xhi) are junk (pad columns, tile tail)
+    int ya, xa, c0, xlo, xhi, ylo, yhi;
 };
 
 __device__ __forceinline__ TileCoord decode_work(const GemmParams& p, int work, int cta_rank = 0) {
@@ -116,9 +121,23 @@ __device__ __forceinline__ TileCoord decode_work(const GemmParams& p, int work, 
         t.split = r / p.n_tiles;
     }
     t.n0 = t.h0 = t.w0 = 0;
-    if (p.mode == 2) {  // n0 = image, w0 = first padded-linear position of the tile inside the image
+    if (p.mode == 2) {
         t.n0 = t.m_tile / p.tiles_per_img;
-        t.w0 = (t.m_tile - t.n0 * p.tiles_per_img) * kBM;
+        const int tt = t.m_tile - t.n0 * p.tiles_per_img;
+        const int halo = p.taps == 9 ? 1 : 0;
+        if (p.win) {  // a th x tw window of the image; the patch adds the halo ring, pitch Wp = tw + 2 * halo
+            const int ty = tt / p.tiles_x, tx = tt - ty * p.tiles_x;
+            const int y0 = ty * p.th, x0 = tx * p.tw;
+            t.w0 = tt;
+            t.ya = y0 - halo, t.xa = x0 - halo, t.c0 = halo * (p.Wp + 1);
+            t.xlo = x0, t.xhi = min(x0 + p.tw, p.W), t.ylo = y0, t.yhi = min(y0 + p.th, p.H);
+        } else {      // 128 consecutive positions of the padded-linear walk q = y * (W + 1) + x (pad column x == W)
+            const int q0 = tt * kBM;
+            const int y0 = q0 / p.Wp;
+            t.w0 = tt;
+            t.ya = y0 - halo, t.xa = 0, t.c0 = (q0 - y0 * p.Wp) + halo * p.Wp;
+            t.xlo = 0, t.xhi = p.W, t.ylo = 0, t.yhi = p.H;
+        }
     }
     if (p.mode == 1) {
         int tw = t.m_tile % p.tiles_w;
@@ -259,11 +278,12 @@ __device__ __forceinline__ bool tile_row(const GemmParams& p, const TileCoord& t
         out_row = t.m_tile * kBM + row;
         return out_row < p.M;
     }
-    if (p.mode == 2) {  // padded-linear position -> pixel; the pad column (x == W) and the tail are junk rows
-        const int q = t.w0 + row;
-        const int y = q / p.Wp, x = q - y * p.Wp;
+    if (p.mode == 2) {  // patch pixel -> image pixel; pad columns and the tile tail are junk rows
+        const int pi = t.c0 + row;
+        const int r = pi / p.Wp;
+        const int y = t.ya + r, x = t.xa + (pi - r * p.Wp);
         out_row = (t.n0 * p.H + y) * p.W + x;
-        return y < p.H && x < p.W;
+        return x >= t.xlo && x < t.xhi && y >= t.ylo && y < t.yhi;
     }
     const int dw = row & ((1 << p.bw_log2) - 1);
     const int dh = (row >> p.bw_log2) & ((1 << p.bh_log2) - 1);
@@ -322,6 +342,31 @@ __device__ __forceinline__ float2 ln_row_coeffs(const GemmParams& p, int out_row
     return make_float2(rstd, -mu * rstd);
 }
 
+// Residual rows of this warp's 16 tile rows, requested while the main loop (or its tail) still runs: the staged
+// epilogue's store pass would otherwise pay one L2 round trip per row.  Same lane <-> (row, vector) mapping as phase B.
+__device__ __forceinline__ void staged_prefetch_residual(const GemmParams& p, const TileCoord& t, int ew, int lane,
+                                                         uint4 (&res)[8], int it0 = 0) {
+    const int bn = p.block_n;
+    const int vpr = bn >> 3;
+    int L = 8;
+    while (L < vpr) L <<= 1;
+    const int rpi = 32 / L;
+    const int lr = lane / L, lcv = lane - lr * L;
+    const int ncol0 = t.n_tile * bn;
+    const bool col_ok = lcv < vpr && (ncol0 + lcv * 8) < p.N;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int it = it0 + i;
+        res[i] = make_uint4(0, 0, 0, 0);
+        if (it < 16 / rpi && p.residual != nullptr) {
+            const int r = ew * 16 + it * rpi + lr;
+            int orow;
+            if (tile_row(p, t, r, orow) && col_ok)
+                res[i] = *reinterpret_cast<const uint4*>(p.residual + static_cast<size_t>(orow) * p.N + ncol0 + lcv * 8);
+        }
+    }
+}
+
 // ---- staged epilogue (fp16 outputs) ------------------------------------------------------------------------------
 // Phase A: every epilogue thread owns one accumulator row (TMEM lane): TMEM -> registers -> (+LN fold) + bias -> fp16
 //          -> staging tile in shared memory [128][block_n + 8].
@@ -332,7 +377,8 @@ __device__ __forceinline__ float2 ln_row_coeffs(const GemmParams& p, int out_row
 //          arrive for an (image, n_tile) adds the partials of all tiles in slot order: deterministic, no float atomics.
 __device__ __forceinline__ void staged_epilogue(const GemmParams& p, const TileCoord& t, uint32_t taddr, __half* tile_s,
                                                 float* scratch, unsigned int* flag_s, const float* bias_row,
-                                                const float* wg_s, int ew, int lane, int row, int out_row, bool valid) {
+                                                const float* wg_s, int ew, int lane, int row, int out_row, bool valid,
+                                                const uint4 (&res_pre)[8]) {
     const int bn = p.block_n;
     const int ldt = bn + 8;
     const int half = ew >> 2;
@@ -361,20 +407,13 @@ __device__ __forceinline__ void staged_epilogue(const GemmParams& p, const TileC
                 *reinterpret_cast<uint4*>(trow + c + j) = pk;
             }
         };
-        uint32_t va[32], vb[32];
-        int c = 32 * half;
-        if (c < bn) tmem_ld32(taddr + c, va);
-        while (c < bn) {
+        // (single TMEM buffer: the kernel runs at the 168-register cap of three warps per scheduler, and the TMEM read
+        // is a small part of this epilogue)
+        uint32_t va[32];
+        for (int c = 32 * half; c < bn; c += 64) {
+            tmem_ld32(taddr + c, va);
             tmem_ld_wait();
-            const int c2 = c + 64;
-            if (c2 < bn) tmem_ld32(taddr + c2, vb);
             convert32(va, c);
-            if (c2 >= bn) break;
-            tmem_ld_wait();
-            const int c3 = c2 + 64;
-            if (c3 < bn) tmem_ld32(taddr + c3, va);
-            convert32(vb, c2);
-            c = c3;
         }
     }
     epi_bar_sync();
@@ -388,7 +427,13 @@ __device__ __forceinline__ void staged_epilogue(const GemmParams& p, const TileC
     float cs[8], cq[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) cs[e] = cq[e] = 0.f;
-    for (int it = 0; it < 16 / rpi; ++it) {
+    // residual rows: the first eight iterations were requested before the accumulator wait; the second eight are
+    // requested now and land while the first eight are processed
+    uint4 res_late[8];
+    staged_prefetch_residual(p, t, ew, lane, res_late, 8);
+#pragma unroll
+    for (int it = 0; it < 16; ++it) {
+        if (it >= 16 / rpi) break;
         const int r = ew * 16 + it * rpi + lr;
         int orow;
         const bool rv = tile_row(p, t, r, orow);
@@ -404,7 +449,7 @@ __device__ __forceinline__ void staged_epilogue(const GemmParams& p, const TileC
             }
             const size_t off = static_cast<size_t>(orow) * p.N + ncol0 + lcv * 8;
             if (p.residual != nullptr) {
-                const uint4 rr = *reinterpret_cast<const uint4*>(p.residual + off);
+                const uint4 rr = it < 8 ? res_pre[it] : res_late[it - 8];
                 const __half2* r2 = reinterpret_cast<const __half2*>(&rr);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
@@ -458,7 +503,7 @@ __device__ __forceinline__ void staged_epilogue(const GemmParams& p, const TileC
 #pragma unroll
     for (int w = 0; w < 8; ++w) img_of[w] = row_image(p, t, w * 16);
     int slot = 0;
-    if (p.mode == 2) slot = t.w0 / kBM;
+    if (p.mode == 2) slot = t.w0;
     else if (p.mode == 0) slot = p.cs_hw >= kBM ? (t.m_tile % (p.cs_hw / kBM)) : 0;
     else slot = (p.cs_slots > 1) ? ((t.h0 >> p.bh_log2) * p.tiles_w + (t.w0 >> p.bw_log2)) : 0;
     const float2* sc2 = reinterpret_cast<const float2*>(scratch);
@@ -748,6 +793,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) umma_gemm_kernel(const __grid
             }
             if (p.ln_parts != 0)
                 for (int c = tid_e; c < p.block_n; c += kEpiThreads) wg_s[c] = (ncol0 + c < p.N) ? p.ln_wg[ncol0 + c] : 0.f;
+            uint4 res_pre[8];
+            if (kStaged) staged_prefetch_residual(p, t, warp - 2, lane, res_pre);
             if (p.res_smem) {
                 const int vpr = p.block_n >> 3;  // 16-byte vectors per tile row
                 for (int i = tid_e; i < kBM * vpr; i += kEpiThreads) {
@@ -769,7 +816,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) umma_gemm_kernel(const __grid
                 float* scratch = reinterpret_cast<float*>(tile_s + kBM * (p.block_n + 8));
                 staged_epilogue(p, t, taddr, tile_s, scratch, flag_s,
                                 p.bias_mode == 1 ? bias_s + bias_sel * p.block_n : nullptr, wg_s, warp - 2, lane, row,
-                                out_row, valid);
+                                out_row, valid, res_pre);
                 tc_fence_before();
                 mbar_arrive(&tmem_empty[as]);
                 continue;
@@ -943,8 +990,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) halo_conv_kernel(const __grid
     uint8_t* patch = smem;                                  // [2][patch_bytes]
     uint8_t* smem_b = smem + 2 * p.patch_bytes;             // [stages][block_n * 128]
     uint64_t* full_b = reinterpret_cast<uint64_t*>(smem_b + p.stages * b_stage);
-    uint64_t* empty_b = full_b + kMaxStages;
-    uint64_t* full_a = empty_b + kMaxStages;                // [2]
+    uint64_t* empty_b = full_b + kHaloMaxStages;
+    uint64_t* full_a = empty_b + kHaloMaxStages;            // [2]
     uint64_t* empty_a = full_a + 2;                         // [2]
     uint64_t* tmem_full = empty_a + 2;
     uint64_t* tmem_empty = tmem_full + 2;
@@ -1008,8 +1055,6 @@ __global__ void __launch_bounds__(kGemmThreads, 1) halo_conv_kernel(const __grid
         int it = 0, ait = 0, iter = 0;
         for (int work = work0; work < total_work; work += work_step, ++iter) {
             const TileCoord t = decode_work(p, work);
-            const int y0 = t.w0 / p.Wp;
-            const int xp0 = t.w0 - y0 * p.Wp;
             const int as = p.acc_bufs == 2 ? (iter & 1) : 0;
             const uint32_t aphase = (p.acc_bufs == 2 ? (iter >> 1) : iter) & 1;
             mbar_wait(&tmem_empty[as], aphase ^ 1);
@@ -1026,8 +1071,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) halo_conv_kernel(const __grid
                     tc_fence_after();
                     if (lane == 0) {
                         const int dy = p.taps == 9 ? tap / 3 - 1 : 0, dx = p.taps == 9 ? tap - (tap / 3) * 3 - 1 : 0;
-                        // patch pixel of output position q0 for this tap (>= -1); a 1x1 "convolution" has no halo row
-                        const int srow = xp0 + (p.taps == 9 ? p.Wp : 0) + dy * p.Wp + dx;
+                        // patch pixel of the tile's first output position for this tap (>= -1)
+                        const int srow = t.c0 + dy * p.Wp + dx;
                         const uint32_t a_addr = pbase + srow * 128;
                         // start address shifted by whole 128-byte rows inside the 1024-byte swizzle atom (the patch was
                         // written in the absolute-address swizzle pattern of a 1024-byte aligned buffer)
@@ -1065,8 +1110,47 @@ __global__ void __launch_bounds__(kGemmThreads, 1) halo_conv_kernel(const __grid
         for (int work = work0; work < total_work; work += work_step, ++iter) {
             const TileCoord t = decode_work(p, work);
             const int img = t.n0;
-            const int y0 = t.w0 / p.Wp;
-            const int ya = y0 - (p.taps == 9 ? 1 : 0);
+            const int ya = t.ya, xa = t.xa;
+            // ---- operand patches: one per 64-channel chunk ----
+            // Thread t always handles vector (t & 7) of the patch pixels t / 8, t / 8 + 32, ...: pixel offsets and
+            // shared-memory destinations are computed once per tile, the eight (scale, shift) pairs once per chunk, and
+            // the raw vectors of chunk j + 1 are requested while chunk j is being normalised (one register set: a slot is
+            // refilled as soon as its vector has been consumed), so the L2 latency hides behind the transform.
+            constexpr int NBMAX = 12;
+            const int nvec = p.patch_rows * p.Wp * 8;
+            const int nb = (nvec + kEpiThreads - 1) / kEpiThreads;
+            const int jj = ltid & 7;
+            int soff[NBMAX], doff[NBMAX];
+#pragma unroll
+            for (int i = 0; i < NBMAX; ++i) {
+                const int v = ltid + kEpiThreads * i;
+                const int pi = v >> 3;
+                const int yy = ya + pi / p.Wp, xx = xa + pi % p.Wp;
+                const bool in_patch = i < nb && v < nvec;
+                const bool ok = in_patch && yy >= 0 && yy < p.H && xx >= 0 && xx < p.W;
+                const int ys = ups ? (yy >> 1) : yy, xs = ups ? (xx >> 1) : xx;
+                soff[i] = ok ? (ys * Ws + xs) : -1;
+                doff[i] = in_patch ? pi * 128 + ((jj ^ (pi & 7)) << 4) : -1;
+            }
+            auto chunk_src = [&](int j, int& csrc) -> const __half* {
+                const bool src1 = j >= p.kc0;
+                const int cbase = (src1 ? j - p.kc0 : j) * kBK + jj * 8;
+                csrc = src1 ? p.C1 : p.C0;
+                if (cbase >= csrc) return nullptr;  // ragged last chunk: channels beyond the source are zeros
+                return (src1 ? p.a1 : p.a0) + static_cast<size_t>(img) * Hs * Ws * csrc + cbase;
+            };
+            uint4 regs[NBMAX];
+            {
+                int csrc;
+                const __half* src = chunk_src(0, csrc);
+#pragma unroll
+                for (int i = 0; i < NBMAX; ++i) {
+                    regs[i] = make_uint4(0, 0, 0, 0);
+                    if (src != nullptr && soff[i] >= 0)
+                        regs[i] = __ldg(reinterpret_cast<const uint4*>(src + static_cast<size_t>(soff[i]) * csrc));
+                }
+            }
+            // (the first chunk's vectors are already in flight while the coefficient table is built)
             if (gn && img != cur_img) {
                 // ---- GroupNorm coefficients of this image: group statistics from the producers' per-channel sums ----
                 const int cpg = Cin / p.gn_groups;
@@ -1099,52 +1183,40 @@ __global__ void __launch_bounds__(kGemmThreads, 1) halo_conv_kernel(const __grid
                 ldr_bar_sync();
                 cur_img = img;
             }
-            // ---- operand patches: one per 64-channel chunk ----
-            const int nvec = p.patch_rows * p.Wp * 8;
             for (int j = 0; j < kc; ++j, ++ait) {
                 const int pa = ait & 1;
-                mbar_wait(&empty_a[pa], ((ait >> 1) & 1) ^ 1);
                 const bool src1 = j >= p.kc0;
-                const int cbase = (src1 ? j - p.kc0 : j) * kBK;
-                const int Csrc = src1 ? p.C1 : p.C0;
-                const __half* src = (src1 ? p.a1 : p.a0) + static_cast<size_t>(img) * Hs * Ws * Csrc + cbase;
-                const float2* tab = scsh + (src1 ? p.C0 : 0) + cbase;
+                int csrc_cur;
+                const bool chan_ok = chunk_src(j, csrc_cur) != nullptr;
+                int csrc_nxt = 0;
+                const __half* nsrc = (j + 1 < kc) ? chunk_src(j + 1, csrc_nxt) : nullptr;
+                float4 cf[4];  // (scale, shift) of this thread's eight channels
+                if (gn) {
+                    const float2* tab = scsh + (src1 ? p.C0 : 0) + (src1 ? j - p.kc0 : j) * kBK + jj * 8;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) cf[q] = chan_ok ? *reinterpret_cast<const float4*>(tab + 2 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                mbar_wait(&empty_a[pa], ((ait >> 1) & 1) ^ 1);
                 uint8_t* pbase = patch + pa * p.patch_bytes + 1024;
-                constexpr int NB = 6;
-                for (int v0 = 0; v0 < nvec; v0 += kEpiThreads * NB) {
-                    uint4 raw[NB];
-                    bool okv[NB];
 #pragma unroll
-                    for (int i = 0; i < NB; ++i) {
-                        const int v = v0 + ltid + kEpiThreads * i;
-                        const int pi = v >> 3, jj = v & 7;
-                        const int yy = ya + pi / p.Wp, xx = pi % p.Wp;
-                        okv[i] = v < nvec && yy >= 0 && yy < p.H && xx < p.W && (cbase + jj * 8) < Csrc;
-                        raw[i] = make_uint4(0, 0, 0, 0);
-                        if (okv[i]) {
-                            const int ys = ups ? (yy >> 1) : yy, xs = ups ? (xx >> 1) : xx;
-                            raw[i] = __ldg(reinterpret_cast<const uint4*>(src + (static_cast<size_t>(ys) * Ws + xs) * Csrc + jj * 8));
+                for (int i = 0; i < NBMAX; ++i) {
+                    if (doff[i] < 0) continue;
+                    uint4 val = regs[i];
+                    const bool live = soff[i] >= 0;
+                    regs[i] = make_uint4(0, 0, 0, 0);
+                    if (nsrc != nullptr && live)
+                        regs[i] = __ldg(reinterpret_cast<const uint4*>(nsrc + static_cast<size_t>(soff[i]) * csrc_nxt));
+                    if (gn && live && chan_ok) {
+                        __half2* h2 = reinterpret_cast<__half2*>(&val);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float2 f = __half22float2(h2[q]);
+                            float a = fmaf(f.x, cf[q].x, cf[q].y), b = fmaf(f.y, cf[q].z, cf[q].w);
+                            if (p.gn_silu) a = silu_fast(a), b = silu_fast(b);
+                            h2[q] = __floats2half2_rn(a, b);
                         }
                     }
-#pragma unroll
-                    for (int i = 0; i < NB; ++i) {
-                        const int v = v0 + ltid + kEpiThreads * i;
-                        if (v >= nvec) continue;
-                        const int pi = v >> 3, jj = v & 7;
-                        uint4 val = raw[i];
-                        if (gn && okv[i]) {
-                            __half2* h2 = reinterpret_cast<__half2*>(&val);
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                const float2 f = __half22float2(h2[q]);
-                                const float4 cf = *reinterpret_cast<const float4*>(tab + jj * 8 + 2 * q);  // sc0 sh0 sc1 sh1
-                                float a = fmaf(f.x, cf.x, cf.y), b = fmaf(f.y, cf.z, cf.w);
-                                if (p.gn_silu) a = silu_fast(a), b = silu_fast(b);
-                                h2[q] = __floats2half2_rn(a, b);
-                            }
-                        }
-                        *reinterpret_cast<uint4*>(pbase + pi * 128 + ((jj ^ (pi & 7)) << 4)) = val;
-                    }
+                    *reinterpret_cast<uint4*>(pbase + doff[i]) = val;
                 }
                 fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
                 mbar_arrive(&full_a[pa]);
@@ -1159,6 +1231,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) halo_conv_kernel(const __grid
             }
             int out_row;
             const bool valid = tile_row(p, t, row, out_row);
+            uint4 res_pre[8];
+            if (!kFp32Direct) staged_prefetch_residual(p, t, ew, lane, res_pre);  // hides behind the last chunk's MMAs
             mbar_wait(&tmem_full[as], aphase);
             tc_fence_after();
             epi_bar_sync();
@@ -1181,7 +1255,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) halo_conv_kernel(const __grid
                 __half* tile_s = p.stage_dedicated ? stage_tile : reinterpret_cast<__half*>(smem);
                 float* scratch = reinterpret_cast<float*>(tile_s + kBM * (p.block_n + 8));
                 staged_epilogue(p, t, taddr, tile_s, scratch, flag_s, p.bias != nullptr ? bias_s : nullptr, bias_s, ew, lane,
-                                row, out_row, valid);
+                                row, out_row, valid, res_pre);
             }
             tc_fence_before();
             mbar_arrive(&tmem_empty[as]);
@@ -1246,6 +1320,7 @@ struct GemmPlan {
     int two_cta;  // CTA pairs (tcgen05.mma cta_group::2, M = 256): each CTA stages half of the B tile
     int halo;     // mode 2: halo-reuse convolution
     int Wp, tiles_per_img, patch_rows, patch_bytes;
+    int win, tw, th, tiles_x;
     int staged, stage_dedicated, acc_bufs;
     int cs_slots;  // statistics slots per image this tiling produces (0: column statistics not available)
     int smem_bytes;
@@ -1288,21 +1363,39 @@ static int plan_halo(const b200sd_gemm_args& a, GemmPlan& pl) {
     B200SD_REQUIRE((a.mode == 0 || a.stride == 1) && !a.pad_after_only, "b200sd_gemm: halo needs a stride-1 pad-1 convolution");
     B200SD_REQUIRE(!a.geglu && a.act == 0 && a.split_k <= 1, "b200sd_gemm: halo kernel: no GEGLU / activation / split-K");
     B200SD_REQUIRE(a.wgt_tiled && a.block_n > 0, "b200sd_gemm: halo kernel needs chunk-major pre-tiled weights (explicit block_n)");
-    B200SD_REQUIRE(a.n_img > 0 && a.h > 0 && a.w > 0 && a.w <= 255, "b200sd_gemm: bad image geometry for the halo kernel");
+    B200SD_REQUIRE(a.n_img > 0 && a.h > 0 && a.w > 0, "b200sd_gemm: bad image geometry for the halo kernel");
     B200SD_REQUIRE(!a.upsample2x || (a.h % 2 == 0 && a.w % 2 == 0 && a.c1 == 0 && a.gn_groups == 0),
                    "b200sd_gemm: upsample2x needs even output size, one source, no GroupNorm");
     pl.halo = 1;
     pl.bw = pl.bh = pl.bn_img = pl.tiles_w = pl.tiles_h = pl.tiles_n = 1;
     pl.Hout = a.h, pl.Wout = a.w;
     pl.M = a.n_img * a.h * a.w;
-    pl.Wp = a.w + 1;
-    pl.tiles_per_img = (a.h * pl.Wp + kBM - 1) / kBM;
+    const bool conv = a.mode == 1;  // mode 0 + halo: a 1x1 convolution over an image (one tap, no halo ring)
+    const int halo = conv ? 1 : 0;
+    pl.win = 0, pl.tw = pl.th = pl.tiles_x = 0;
+    if (a.w + 1 <= 80) {
+        // narrow images: padded-linear walk, full-width patches
+        pl.Wp = a.w + 1;
+        pl.tiles_per_img = (a.h * pl.Wp + kBM - 1) / kBM;
+        const int span = (kBM - 1 + pl.Wp - 1) / pl.Wp + 1;  // image rows a 128-position tile can touch
+        pl.patch_rows = span + 2 * halo;
+    } else {
+        // wide images: th x tw windows with th * (tw + 2 halo) <= 128 positions; pick the shape that wastes least
+        double best = -1.0;
+        for (int th = 1; th <= 8; th *= 2) {
+            const int pitch = kBM / th, tw = pitch - 2 * halo;
+            const int tx = (a.w + tw - 1) / tw, ty = (a.h + th - 1) / th;
+            const double eff = static_cast<double>(a.w) * a.h / (static_cast<double>(tx) * ty * kBM);
+            if (eff > best) best = eff, pl.th = th, pl.tw = tw, pl.tiles_x = tx, pl.tiles_per_img = tx * ty;
+        }
+        pl.win = 1;
+        pl.Wp = pl.tw + 2 * halo;
+        pl.patch_rows = pl.th + 2 * halo;
+    }
     pl.m_tiles = a.n_img * pl.tiles_per_img;
-    const int span = (kBM - 1 + pl.Wp - 1) / pl.Wp + 1;  // image rows a 128-position tile can touch
-    const bool conv = a.mode == 1;  // mode 0 + halo: a 1x1 convolution over an image (one tap, no halo rows)
-    pl.patch_rows = span + (conv ? 2 : 0);
-    const int rows_needed = std::max(pl.patch_rows * pl.Wp, (conv ? 3 : 1) * pl.Wp + kBM) + 8 + 1;
+    const int rows_needed = std::max(pl.patch_rows * pl.Wp, (2 * halo + 1) * pl.Wp + kBM) + 8 + 1;
     pl.patch_bytes = ((rows_needed + 7) / 8) * 1024;
+    B200SD_REQUIRE(pl.patch_rows * pl.Wp * 8 <= 12 * kEpiThreads, "b200sd_gemm: image too wide for the halo kernel's patch (w=%d)", a.w);
     pl.block_n = a.block_n;
     B200SD_REQUIRE(pl.block_n == 16 || (pl.block_n % 32 == 0 && pl.block_n <= 256), "b200sd_gemm: halo block_n %d", pl.block_n);
     pl.n_tiles = (a.n + pl.block_n - 1) / pl.block_n;
@@ -1317,10 +1410,10 @@ static int plan_halo(const b200sd_gemm_args& a, GemmPlan& pl) {
     pl.staged = fp32_direct ? 0 : 1;
     pl.stage_dedicated = (pl.staged && pl.acc_bufs == 2) ? 1 : 0;
     const int cin = a.c0 + a.c1;
-    const int fixed = 2 * pl.patch_bytes + (2 * kMaxStages + 8) * 8 + 16 + 256 * 4 + 32 + 64 * 8 + ((cin + 7) & ~7) * 8 +
+    const int fixed = 2 * pl.patch_bytes + (2 * kHaloMaxStages + 8) * 8 + 16 + 256 * 4 + 32 + 64 * 8 + ((cin + 7) & ~7) * 8 +
                       (pl.stage_dedicated ? kBM * (pl.block_n + 8) * 2 + 8 * pl.block_n * 8 : 0) + 1024;
     const int b_stage = pl.block_n * kBK * 2;
-    pl.stages = std::min(kMaxStages, (227 * 1024 - fixed) / b_stage);
+    pl.stages = std::min(kHaloMaxStages, (227 * 1024 - fixed) / b_stage);
     B200SD_REQUIRE(pl.stages >= 3, "b200sd_gemm: halo kernel does not fit shared memory (w=%d c=%d block_n=%d)", a.w, cin, pl.block_n);
     pl.smem_bytes = fixed + pl.stages * b_stage;
     pl.epi_smem = 0;
@@ -1333,7 +1426,8 @@ static int plan_halo(const b200sd_gemm_args& a, GemmPlan& pl) {
 static int halo_pick_block_n(const b200sd_gemm_args& a) {
     if (a.n <= 16) return 16;
     const int wp = a.w + 1;
-    const long m_tiles = static_cast<long>(a.n_img) * ((a.h * wp + kBM - 1) / kBM);
+    long m_tiles = static_cast<long>(a.n_img) * ((a.h * wp + kBM - 1) / kBM);
+    if (wp > 80) m_tiles = static_cast<long>(a.n_img) * ((static_cast<long>(a.h) * a.w + 101) / 102);  // windows: ~80 % useful rows
     double best = 1e30;
     int best_bn = 128;
     for (int bn = 256; bn >= 32; bn -= 32) {
@@ -1622,6 +1716,7 @@ static int launch_gemm(const b200sd_gemm_args& a, cudaStream_t stream) {
     p.two_cta = pl.two_cta;
     p.m_pairs = (pl.m_tiles + 1) / 2;
     p.H = a.h, p.W = a.w, p.Wp = pl.Wp, p.tiles_per_img = pl.tiles_per_img;
+    p.win = pl.win, p.tw = pl.tw, p.th = pl.th, p.tiles_x = pl.tiles_x;
     p.patch_rows = pl.patch_rows, p.patch_bytes = pl.patch_bytes;
     p.upsample = a.upsample2x, p.desc_bo = desc_base_offset_enabled() ? 1 : 0;
     p.a0 = reinterpret_cast<const __half*>(a.a0), p.a1 = reinterpret_cast<const __half*>(a.a1), p.C1 = a.c1;

@@ -67,9 +67,12 @@ class UNetModel(B200Model):
             "encoder_hidden_states": {"shape": (batch, d_ctx, 1, seq_len), "dtype": dt},
         }
         if e.xl:
-            spec["time_ids"] = {"shape": (batch, 6), "dtype": dt}
+            # SDXL base: six geometry scalars (original size, crop, target size); the refiner: five (aesthetic score in
+            # place of the target size, StableDiffusionXLPipeline.swift:327-345) -> cfg["num_time_ids"] = 5
+            nid = int(cfg.get("num_time_ids", 6))
+            spec["time_ids"] = {"shape": (batch, nid), "dtype": dt}
             spec["text_embeds"] = {"shape": (batch, cfg["projection_class_embeddings_input_dim"]
-                                             - 6 * cfg["addition_time_embed_dim"]), "dtype": dt}
+                                             - nid * cfg["addition_time_embed_dim"]), "dtype": dt}
         self.res_shapes = []
         if e.support_controlnet:
             for i, shp in enumerate(self.residual_shapes()):
@@ -80,7 +83,7 @@ class UNetModel(B200Model):
         self._sample = torch.zeros(batch, e.in_ch, height, width, dtype=torch.float32, device=dev)
         self._t = torch.zeros(batch, dtype=torch.float32, device=dev)
         self._ctx = torch.zeros(batch, d_ctx, 1, seq_len, dtype=torch.float16, device=dev)
-        self._time_ids = torch.zeros(batch, 6, dtype=torch.float32, device=dev) if e.xl else None
+        self._time_ids = (torch.zeros(spec["time_ids"]["shape"], dtype=torch.float32, device=dev) if e.xl else None)
         self._text_embeds = (torch.zeros(spec["text_embeds"]["shape"], dtype=torch.float32, device=dev)
                              if e.xl else None)
         self._res = [torch.zeros(s, dtype=torch.float16, device=dev) for s in self.res_shapes]

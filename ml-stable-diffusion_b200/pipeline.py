@@ -70,8 +70,11 @@ class B200StableDiffusionPipeline:
 
     def __init__(self, unet: UNetModel, vae_decoder: VAEDecoderModel, scheduler="DDIM", text_encoder=None,
                  tokenizer=None, force_zeros_for_empty_prompt=True, xl=False, controlnet=None, loop_graph=True,
-                 vae_encoder=None, text_encoder_2=None, tokenizer_2=None, scheduler_kwargs=None):
+                 vae_encoder=None, text_encoder_2=None, tokenizer_2=None, scheduler_kwargs=None, unet_refiner=None):
         self.unet = unet
+        # SDXL refiner UNet (StableDiffusionXLPipeline.swift:205-225): takes over the loop at step
+        # int(len(timesteps) * refiner_start) with its own conditioning (set_refiner_inputs)
+        self.unet_refiner = unet_refiner
         self.text_encoder_2 = text_encoder_2  # SDXL: CLIPTextModelWithProjection slot (pipeline.py:64-65, 136-141)
         self.tokenizer_2 = tokenizer_2
         self.vae_encoder = vae_encoder  # VAEEncoderModel or None (image-to-image, StableDiffusionPipeline.swift:371-376)
@@ -150,6 +153,85 @@ class B200StableDiffusionPipeline:
         return cls(unet, vae, scheduler=scheduler, xl=unet.engine.xl, controlnet=nets, text_encoder=enc,
                    tokenizer=tokenizer, vae_encoder=venc, force_zeros_for_empty_prompt=unet.engine.xl)
 
+    _SCHEDULER_CLASS = {"PNDMScheduler": "PNDM", "DDIMScheduler": "DDIM", "DPMSolverMultistepScheduler": "DPMSolverMultistep"}
+
+    @classmethod
+    def from_pretrained(cls, model_dir, images_per_call=1, device="cuda", height=None, width=None,
+                        scheduler_override=None, controlnet_dirs=None, force_zeros_for_empty_prompt=None,
+                        with_vae_encoder=False, refiner_dir=None):
+        """Build the pipeline from a diffusers-layout model directory (``unet/``, ``vae/``, ``text_encoder[_2]/``,
+        ``tokenizer[_2]/``, ``scheduler/``): the counterpart of ``get_coreml_pipe(pytorch_pipe, mlpackages_dir,
+        model_version, compute_unit, scheduler_override, controlnet_models, force_zeros_for_empty_prompt)``
+        (pipeline.py:607-697), which wires converted .mlpackage files to the same slots.  Weights are read with
+        ``checkpoint.load_component`` (schema-checked), configs with ``checkpoint.read_config``.
+        ``refiner_dir``: an SDXL refiner directory whose UNet takes over at ``refiner_start`` (``__call__``)."""
+        import json
+        import os
+        from . import checkpoint as K
+        from .text_encoder import TextEncoderModel
+        from .tokenizer import BPETokenizer
+
+        ucfg = K.read_config(model_dir, "unet")
+        vcfg = K.read_config(model_dir, "vae")
+        if controlnet_dirs:
+            ucfg = dict(ucfg, support_controlnet=True)
+        f = 2 ** (len(vcfg["block_out_channels"]) - 1)
+        size = ucfg.get("sample_size", 64)
+        h = (height // f) if height else size
+        w = (width // f) if width else size
+        xl = ucfg.get("addition_embed_type") == "text_time"
+        unet = UNetModel(ucfg, K.load_component(model_dir, "unet", ucfg), batch=2 * images_per_call, height=h, width=w,
+                         device=device)
+        vsd = K.read_state_dict(os.path.join(model_dir, "vae"))
+        vae = VAEDecoderModel(vcfg, K.check_state_dict("vae_decoder", vcfg, vsd), batch=images_per_call, height=h,
+                              width=w, device=device)
+        venc = None
+        if with_vae_encoder:
+            from .vae import VAEEncoderModel
+            venc = VAEEncoderModel(vcfg, K.check_state_dict("vae_encoder", vcfg, vsd), batch=images_per_call,
+                                   height=h * f, width=w * f, device=device)
+
+        def text_pair(enc_dir, tok_dir):
+            if not os.path.isdir(os.path.join(model_dir, enc_dir)):
+                return None, None
+            tcfg = K.read_config(model_dir, enc_dir)
+            enc = TextEncoderModel(tcfg, K.load_component(model_dir, enc_dir, tcfg), batch=1, device=device)
+            tok = None
+            tdir = os.path.join(model_dir, tok_dir)
+            if os.path.exists(os.path.join(tdir, "merges.txt")):
+                tok = BPETokenizer.from_files(os.path.join(tdir, "merges.txt"), os.path.join(tdir, "vocab.json"))
+            return enc, tok
+
+        enc1, tok1 = text_pair("text_encoder", "tokenizer")
+        enc2, tok2 = text_pair("text_encoder_2", "tokenizer_2")
+        sched = scheduler_override
+        if sched is None:
+            with open(os.path.join(model_dir, "scheduler", "scheduler_config.json")) as fh:
+                name = json.load(fh).get("_class_name", "PNDMScheduler")
+            if name not in cls._SCHEDULER_CLASS:
+                raise ValueError(f"scheduler {name} of the checkpoint is not implemented; pass scheduler_override "
+                                 f"(one of {sorted(S.SCHEDULER_MAP)})")
+            sched = cls._SCHEDULER_CLASS[name]
+        nets = None
+        if controlnet_dirs:
+            from .controlnet import ControlNetModel
+            nets = []
+            for d in controlnet_dirs:
+                with open(os.path.join(d, "config.json")) as fh:
+                    ccfg = {k: (tuple(v) if isinstance(v, list) else v) for k, v in json.load(fh).items() if not k.startswith("_")}
+                nets.append(ControlNetModel(ccfg, K.load_component(d, "controlnet", ccfg), batch=2 * images_per_call,
+                                            height=h, width=w, device=device))
+        refiner = None
+        if refiner_dir:
+            rcfg = K.read_config(refiner_dir, "unet")
+            refiner = UNetModel(rcfg, K.load_component(refiner_dir, "unet", rcfg), batch=2 * images_per_call, height=h,
+                                width=w, device=device)
+        if force_zeros_for_empty_prompt is None:
+            force_zeros_for_empty_prompt = xl   # the reference's CLI sets it for SDXL only (pipeline.py:744-755)
+        return cls(unet, vae, scheduler=sched, text_encoder=enc1, tokenizer=tok1, text_encoder_2=enc2, tokenizer_2=tok2,
+                   xl=xl, controlnet=nets, vae_encoder=venc, force_zeros_for_empty_prompt=force_zeros_for_empty_prompt,
+                   unet_refiner=refiner)
+
     # ---------------------------------------------------------------- reference-named helpers
     def check_inputs(self, prompt, height, width, callback_steps):
         """pipeline.py:359-382."""
@@ -188,13 +270,14 @@ class B200StableDiffusionPipeline:
         emb = np.stack(unconds + conds, 0)  # (2B, S, D)
         return np.ascontiguousarray(emb.transpose(0, 2, 1)[:, :, None, :]).astype(np.float16)
 
-    def _encode_prompt_xl(self, prompts, do_cfg, negative_prompt=None, prompts_2=None, negative_prompt_2=None):
+    def _encode_prompt_xl(self, prompts, do_cfg, negative_prompt=None, prompts_2=None, negative_prompt_2=None,
+                          only_second=False):
         """SDXL branch of pipeline.py:123-257: both encoders' ``hidden_embeds`` concatenated along the feature axis
         (encoder 1 first), the pooled output of the LAST encoder, zeros for the negative branch when no negative
         prompt is given and force_zeros_for_empty_prompt.  The refiner has only encoder 2 (text_encoder is None).
         -> ((2B, D1 + D2, 1, S) fp16, (2B, P) fp32), uncond half first."""
         pairs = [(self.tokenizer, self.text_encoder), (self.tokenizer_2, self.text_encoder_2)]
-        if self.text_encoder is None:
+        if self.text_encoder is None or only_second:  # the refiner is conditioned on the second encoder only
             pairs = pairs[1:]
         texts = [prompts, prompts_2 if prompts_2 is not None else prompts][-len(pairs):]
 
@@ -224,6 +307,9 @@ class B200StableDiffusionPipeline:
                                      f"{len(prompts)}")
                 neg, neg_pooled = run([neg_1, neg_2][-len(pairs):])
             emb, pooled = np.concatenate([neg, emb], 0), np.concatenate([neg_pooled, pooled], 0)
+        else:
+            # the UNet always runs both batch halves: without guidance both carry the prompt (like _encode_prompt)
+            emb, pooled = np.concatenate([emb, emb], 0), np.concatenate([pooled, pooled], 0)
         return np.ascontiguousarray(emb.transpose(0, 2, 1)[:, :, None, :]).astype(np.float16), pooled
 
     def prepare_latents(self, batch, channels, height, width, latents=None, seed=None, rng="numpy"):
@@ -248,8 +334,9 @@ class B200StableDiffusionPipeline:
         out = []
         for cond in controlnet_cond:
             cond = np.stack([np.asarray(cond)] * batch_size * num_images_per_prompt)
-            if do_classifier_free_guidance:
-                cond = np.concatenate([cond] * 2)
+            # doubled like the latents: this engine always runs both batch halves (with guidance <= 1 both carry the
+            # prompt), where the reference doubles only under guidance (pipeline.py:345-356)
+            cond = np.concatenate([cond] * 2)
             out.append(cond)
         return out
 
@@ -291,7 +378,7 @@ class B200StableDiffusionPipeline:
                                                                     st.push_x0_slot, st.push_x_slot)
         return k
 
-    def _loop_on_static_buffers(self, plan, guidance_scale, ts_rows, use_controlnet=False):
+    def _loop_on_static_buffers(self, plan, guidance_scale, ts_rows, use_controlnet=False, refiner_start_step=None):
         """The whole N-step loop on static device buffers (no host-side tensor arguments): what the loop graph
         captures.  Prologue, once per prompt: cross-attention K/V of all blocks from the text states, the
         time-embedding biases of all ResNet blocks for ALL timesteps (`ts_rows`: each step's timestep repeated per
@@ -299,20 +386,32 @@ class B200StableDiffusionPipeline:
         sequence and ONE fused kernel for guidance + scheduler update, which also writes the next step's UNet
         input (fp16 NHWC, both CFG halves: pipeline.py:502 np.concatenate([latents] * 2)) -- no fill / copy /
         layout kernels in between."""
-        u, n = self.unet, self.images_per_call
+        n = self.images_per_call
+        rs = len(plan) if refiner_start_step is None else max(0, min(len(plan), refiner_start_step))
+        # which UNet runs each step: the SDXL refiner takes over at refiner_start_step with its own conditioning
+        # (StableDiffusionXLPipeline.swift:205-225); each model gets its per-prompt prologue and its own time table
+        models = [self.unet if i < rs else self.unet_refiner for i in range(len(plan))]
         self._hist.zero_()
-        u.prepare_prompt()
-        table = u.time_table(ts_rows)
-        L.nchw_to_nhwc(self._latents, c_pad=u.engine.in_pad, out=u._x_nhwc[:n])
-        L.nchw_to_nhwc(self._latents, c_pad=u.engine.in_pad, out=u._x_nhwc[n:])
+        b = self.unet.batch
+        tables = {}
+        for m, lo, hi in ((self.unet, 0, rs), (self.unet_refiner, rs, len(plan))):
+            if hi > lo:
+                m.prepare_prompt()
+                tables[id(m)] = (m.time_table(ts_rows[lo * b: hi * b]), lo)
+        first = models[0]
+        L.nchw_to_nhwc(self._latents, c_pad=first.engine.in_pad, out=first._x_nhwc[:n])
+        L.nchw_to_nhwc(self._latents, c_pad=first.engine.in_pad, out=first._x_nhwc[n:])
         if use_controlnet:
             self.prepare_controlnets(ts_rows)
         for i, st in enumerate(plan):
-            u._run_core(table[i], self.controlnet_residuals(i) if use_controlnet else None)
+            u = models[i]
+            table, lo = tables[id(u)]
+            u._run_core(table[i - lo], self.controlnet_residuals(i) if use_controlnet else None)
             k = self._coeffs(st, guidance_scale)
             k.noise_pred_nhwc = 1
+            nxt = models[i + 1] if i + 1 < len(plan) else u
             L.cfg_scheduler_step(u._out_nhwc, self._latents, k, hist=self._hist, denoised=self._denoised,
-                                 unet_in=u._x_nhwc)
+                                 unet_in=nxt._x_nhwc)
 
     def set_control_conditions(self, controlnet_cond):
         """Copy the conditioning images (each (2B, 3, H, W)) into the ControlNets' static input buffers."""
@@ -341,7 +440,7 @@ class B200StableDiffusionPipeline:
         return torch.tensor([float(st.timestep) for st in plan for _ in range(self.unet.batch)], dtype=torch.float32,
                             device=self.device)
 
-    def _loop_graph_for(self, key, plan, guidance_scale, use_controlnet=False):
+    def _loop_graph_for(self, key, plan, guidance_scale, use_controlnet=False, refiner_start_step=None):
         g = self._loop_graphs.get(key)
         if g is None:
             keep = self._latents.clone()
@@ -350,12 +449,14 @@ class B200StableDiffusionPipeline:
             s.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(s):
                 self._loop_on_static_buffers(plan[:1], guidance_scale, ts_rows[: self.unet.batch], use_controlnet)
+                if refiner_start_step is not None and refiner_start_step < len(plan):  # warm the refiner's kernels too
+                    self._loop_on_static_buffers(plan[-1:], guidance_scale, ts_rows[-self.unet.batch:], use_controlnet, 0)
             torch.cuda.current_stream().wait_stream(s)
             torch.cuda.synchronize()
             self._latents.copy_(keep)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                self._loop_on_static_buffers(plan, guidance_scale, ts_rows, use_controlnet)
+                self._loop_on_static_buffers(plan, guidance_scale, ts_rows, use_controlnet, refiner_start_step)
             g._b200sd_keep = ts_rows
             self._latents.copy_(keep)  # capture does not execute, but keep the contract obvious
             if len(self._loop_graphs) >= 4:
@@ -365,7 +466,7 @@ class B200StableDiffusionPipeline:
 
     def denoise(self, text_embeddings, latents, num_inference_steps, guidance_scale, callback=None,
                 callback_steps=1, time_ids=None, text_embeds=None, return_denoised=False, record=None,
-                controlnet_cond=None, start_step=0):
+                controlnet_cond=None, start_step=0, refiner=None, refiner_start=0.8):
         """Runs the N-step loop (from ``start_step``: image-to-image) entirely on the device.  ``text_embeddings`` (2B, D, 1, S) and ``latents``
         (B, C, h, w) may be numpy (copied once, before the loop) or CUDA tensors.  ``record`` (a list) receives
         (timestep, noise_pred, latents_after_step) clones per step -- a debugging / testing aid.  Without
@@ -386,10 +487,21 @@ class B200StableDiffusionPipeline:
                 u._text_embeds.copy_(torch.as_tensor(text_embeds))
             if controlnet_cond:
                 self.set_control_conditions(controlnet_cond)
+            rstep = None
+            if refiner is not None:
+                if self.unet_refiner is None:
+                    raise ValueError("refiner inputs were given but the pipeline has no unet_refiner")
+                r = self.unet_refiner
+                r._ctx.copy_(torch.as_tensor(refiner["encoder_hidden_states"]))
+                r._time_ids.copy_(torch.as_tensor(refiner["time_ids"]).reshape(r._time_ids.shape))
+                r._text_embeds.copy_(torch.as_tensor(refiner["text_embeds"]))
+                rstep = int(np.float32(len(plan)) * np.float32(refiner_start))  # Int(Float(timeSteps.count) * refinerStart)
             key = (self.scheduler_name, int(num_inference_steps), float(guidance_scale), int(start_step),
-                   bool(controlnet_cond), tuple(sorted(self.scheduler_kwargs.items())))
-            self._loop_graph_for(key, plan, guidance_scale, bool(controlnet_cond)).replay()
+                   bool(controlnet_cond), tuple(sorted(self.scheduler_kwargs.items())), rstep)
+            self._loop_graph_for(key, plan, guidance_scale, bool(controlnet_cond), rstep).replay()
             return self._denoised if return_denoised else self._latents
+        if refiner is not None:
+            raise ValueError("the refiner hand-off runs in the device loop only (no callback / record)")
         self._hist.zero_()
         k = L.StepCoeffs()
         for i, st in enumerate(plan):
@@ -423,7 +535,8 @@ class B200StableDiffusionPipeline:
                  return_dict=True, callback=None, callback_steps=1, controlnet_cond=None,
                  original_size: Optional[Tuple[int, int]] = None, crops_coords_top_left: Tuple[int, int] = (0, 0),
                  target_size: Optional[Tuple[int, int]] = None, unet_batch_one=False, prompt_embeds=None,
-                 starting_image=None, strength=0.5, seed=None, rng="numpy", **kwargs):
+                 starting_image=None, strength=0.5, seed=None, rng="numpy", refiner_start=0.8, aesthetic_score=6.0,
+                 negative_aesthetic_score=2.5, **kwargs):
         """``starting_image`` ((B, 3, H, W) in [-1, 1], the vae_encoder input) + ``strength`` select the Swift
         pipeline's image-to-image mode (StableDiffusionPipeline.swift:250-262, 361-378): the encoded image is noised
         to timestep ``timeSteps[startStep]`` and only the remaining steps run."""
@@ -477,8 +590,25 @@ class B200StableDiffusionPipeline:
             lat = sched.add_noise(x0.astype(np.float32), lat, strength)
         if controlnet_cond:  # pipeline.py:488-494
             controlnet_cond = self.prepare_control_cond(controlnet_cond, do_cfg, len(prompts), 1)
+        refiner = None
+        if self.unet_refiner is not None:
+            # refiner conditioning (StableDiffusionXLPipeline.swift:314-345): the second encoder's embeddings only, its
+            # pooled output, geometry = (original size, crop, aesthetic score) with the negative score on the uncond row
+            r_emb = kwargs.get("refiner_prompt_embeds")
+            r_pool = kwargs.get("refiner_pooled_prompt_embeds")
+            if r_emb is None:
+                if self.text_encoder_2 is None:
+                    raise ValueError("the refiner needs text_encoder_2 or refiner_prompt_embeds / refiner_pooled_prompt_embeds")
+                r_emb, r_pool = self._encode_prompt_xl(prompts, do_cfg, negative_prompt, only_second=True,
+                                                       negative_prompt_2=kwargs.get("negative_prompt_2"))
+            osz, crop = list(original_size or (height, width)), list(crops_coords_top_left)
+            rows = [osz + crop + [negative_aesthetic_score]] * self.images_per_call + \
+                   [osz + crop + [aesthetic_score]] * self.images_per_call
+            refiner = {"encoder_hidden_states": r_emb, "text_embeds": torch.as_tensor(np.asarray(r_pool), dtype=torch.float32),
+                       "time_ids": torch.tensor(rows, dtype=torch.float32)}
         final = self.denoise(text_embeddings, lat, num_inference_steps, guidance_scale, callback, callback_steps,
-                             time_ids, text_embeds, controlnet_cond=controlnet_cond or None, start_step=start_step)
+                             time_ids, text_embeds, controlnet_cond=controlnet_cond or None, start_step=start_step,
+                             refiner=refiner, refiner_start=refiner_start)
         image = self.decode_latents(final).cpu().numpy()  # single device->host copy of the result
         has_nsfw = None  # the safety checker is out of scope
         if output_type == "pil":

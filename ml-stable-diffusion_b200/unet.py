@@ -345,7 +345,6 @@ class UNetEngine:
                 skips.append((x, xs))
         if additional_residuals is not None:  # the sums have no producer-side statistics: standalone GroupNorm there
             skips = [(L.add(s, r), None) for (s, _), r in zip(skips, additional_residuals[:-1])]
-            x, xs = skips[-1]
         x, xs = self._resnet_f("mid_block.resnets.0", x, xs, None, None, temb_all)
         x, xs = self._transformer_f("mid_block.attentions.0", x, xs, kv_all, batch, self.heads[-1], s_ctx)
         x, xs = self._resnet_f("mid_block.resnets.1", x, xs, None, None, temb_all)

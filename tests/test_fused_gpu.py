@@ -41,7 +41,8 @@ def _chan_sums(x):  # NHWC fp16 -> [n, c, 2] (sum, sum of squares) in fp64 -> fp
 
 @pytest.mark.parametrize("n,h,w,ci,co", [(2, 64, 64, 320, 320), (2, 32, 32, 640, 640), (2, 16, 16, 128, 256),
                                          (2, 8, 8, 256, 128), (1, 5, 7, 64, 32), (3, 24, 24, 96, 64),
-                                         (1, 64, 64, 64, 4)])
+                                         (1, 64, 64, 64, 4), (1, 128, 128, 64, 64), (2, 96, 96, 128, 96),
+                                         (1, 200, 136, 32, 32)])
 def test_halo_conv_plain(cuda_lib, n, h, w, ci, co):
     x = _rand(n, h, w, ci, seed=1)
     wt = _rand(co, ci, 3, 3, scale=(9 * ci) ** -0.5, seed=2)
@@ -64,7 +65,8 @@ def test_halo_conv_two_sources_temb_residual(cuda_lib):
 
 @pytest.mark.parametrize("n,h,w,c0,c1,co,silu", [(2, 64, 64, 320, 0, 320, True), (2, 32, 32, 640, 320, 640, True),
                                                  (2, 16, 16, 1280, 640, 1280, True), (2, 8, 8, 1280, 0, 1280, True),
-                                                 (1, 12, 20, 64, 32, 64, False)])
+                                                 (1, 12, 20, 64, 32, 64, False), (2, 96, 96, 128, 64, 128, True),
+                                                 (1, 256, 256, 128, 0, 128, True)])
 def test_halo_conv_groupnorm_silu(cuda_lib, n, h, w, c0, c1, co, silu):
     """GroupNorm(32 groups over the concatenated channels) -> SiLU -> conv, statistics handed over as per-channel sums."""
     x0 = _rand(n, h, w, c0, seed=1, shift=0.3)
@@ -97,7 +99,8 @@ def test_halo_upsample_conv(cuda_lib):
 
 
 @pytest.mark.parametrize("halo", [False, True])
-@pytest.mark.parametrize("n,h,w,ci,co", [(2, 64, 64, 64, 320), (2, 16, 16, 128, 640), (2, 8, 8, 128, 1280)])
+@pytest.mark.parametrize("n,h,w,ci,co", [(2, 64, 64, 64, 320), (2, 16, 16, 128, 640), (2, 8, 8, 128, 1280),
+                                         (2, 96, 96, 64, 128)])
 def test_conv_column_statistics(cuda_lib, halo, n, h, w, ci, co):
     x = _rand(n, h, w, ci, seed=1)
     wt = _rand(co, ci, 3, 3, scale=(9 * ci) ** -0.5, seed=2)

@@ -331,3 +331,22 @@ def test_cfg_scheduler_step(cuda_lib):
     _close(unet_in[:n, ..., :4], want, 2e-3, 1e-3, "next unet input (uncond half)")
     _close(unet_in[n:, ..., :4], want, 2e-3, 1e-3, "next unet input (cond half)")
     assert (unet_in[..., 4:] == 0).all()
+
+
+def test_attention_large_scores_take_the_rescale_path(cuda_lib):
+    """Scores whose running maximum grows by far more than 2^8 from one 64-key half to the next force the lazy
+    reference-maximum refresh (O rescaled in TMEM, attention.cu `kTau`); random-init inputs almost never do."""
+    b, h, s, d = 1, 2, 512, 64
+    g = torch.Generator(device="cuda").manual_seed(5)
+    q = torch.randn(b * s, h * d, generator=g, device="cuda")
+    k = torch.randn(b * s, h * d, generator=g, device="cuda")
+    v = torch.randn(b * s, h * d, generator=g, device="cuda")
+    # later keys are scaled up so that every half raises the row maxima by a large step
+    ramp = torch.linspace(0.5, 12.0, s, device="cuda").repeat(b)[:, None]
+    k = (k * ramp).half()
+    q, v = (q * 3.0).half(), v.half()
+    out = cuda_lib.attention(q, k, v, b, h, s, s)
+    qf, kf, vf = (t.float().reshape(b, s, h, d).permute(0, 2, 1, 3) for t in (q, k, v))
+    ref = torch.softmax(qf @ kf.transpose(-1, -2) * d ** -0.5, dim=-1) @ vf
+    ref = ref.permute(0, 2, 1, 3).reshape(b * s, h * d)
+    _close(out, ref, 3e-3, 3e-3, "attention with growing score maxima")

@@ -64,9 +64,9 @@ def test_unet_tiny_cuda_graph_equals_eager_and_validates(cuda_lib):
     gm = UNetModel(cfg, sd, batch=2, height=16, width=16, use_cuda_graph=True)
     g1 = gm(**kw)["noise_pred"]
     g2 = gm(**kw)["noise_pred"]
-    # GroupNorm statistics use shared-memory float atomics (summation order varies run to run), so two
-    # executions agree to rounding, not bitwise
-    assert np.abs(eager - g1).max() < 2e-3 and np.abs(g1 - g2).max() < 2e-3
+    # every reduction of the path (GroupNorm / LayerNorm statistics, split-K) runs in a fixed order: eager launches, the
+    # captured graph and its replays are bit-identical
+    assert np.array_equal(eager, g1) and np.array_equal(g1, g2)
     assert gm.launches_per_call and gm.launches_per_call > 50
     # per-row timesteps really differ
     kw2 = dict(kw, timestep=np.array([501.0, 501.0], np.float16))
@@ -203,7 +203,9 @@ def test_pipeline_tiny_batched_and_schedulers(cuda_lib):
         emb = pipe._encode_prompt(prompts, True, None)
         rec = []
         final = pipe.denoise(emb, lat0.astype(np.float32), steps, g, record=rec).cpu().clone()
-        mk = (lambda: R.DPMSolverPP2M(steps)) if name == "DPMSolverMultistep" else (lambda: R.PNDM(steps))
+        # the pipeline mirrors the reference's Python pipeline: diffusers' DPM-Solver++ ending (final_sigmas_type="zero")
+        mk = ((lambda: R.DPMSolverPP2M(steps, final_sigmas_type="zero")) if name == "DPMSolverMultistep"
+              else (lambda: R.PNDM(steps)))
         # (a) scheduler + CFG kernel in isolation
         sched = mk()
         assert [r[0] for r in rec] == list(sched.timesteps)
@@ -491,5 +493,11 @@ def test_controlnet_sd21_vs_reference_golden(cuda_lib):
     assert len(out) == 13
     for i in range(13):
         ref = gold[f"residual_{i}"].astype(np.float32)
-        _check(out[f"additional_residual_{i}"][:, :, ::st, ::st], ref, f"SD-2.1 controlnet residual {i}",
-               max_abs=MAX_ABS * max(1.0, float(np.abs(ref).max())))
+        _check(out[f"additional_residual_{i}"][:, :, ::st, ::st], ref, f"SD-2.1 controlnet residual {i} (reference golden)")
+    # the committed golden is stride-subsampled for size; every element is checked against the restatement (pinned to
+    # that golden in the CPU suite, tests/test_oracle.py) run here on the host
+    with torch.no_grad():
+        live = R.controlnet_forward({k: v.float() for k, v in sd.items()}, cfg, x.half().float(),
+                                    torch.tensor([501.0, 501.0]), c.half().float(), cond.half().float())
+    for i, r in enumerate(live):
+        _check(out[f"additional_residual_{i}"], r.numpy(), f"SD-2.1 controlnet residual {i} (full grid)")
