@@ -160,6 +160,12 @@ int b200sd_group_norm(const void* x0, const void* x1, int32_t c0, int32_t c1, in
                       int32_t groups, float eps, const float* gamma, const float* beta, int32_t silu,
                       void* out, float* stats_ws, size_t stats_ws_bytes, void* stream);
 size_t b200sd_group_norm_workspace_bytes(int32_t n_img, int32_t hw, int32_t c, int32_t groups);
+/* GroupNorm (+SiLU, + concat) from PRODUCER-SIDE statistics: chan0 / chan1 are the per-channel (sum, sum of squares)
+ * [n_img][c][2] a b200sd_gemm call left behind (cs_chan); no statistics pass, one read + one write of the tensor.  Used
+ * where the consumer is not the halo convolution (which applies the normalisation in its own operand path). */
+int b200sd_group_norm_apply(const void* x0, const void* x1, int32_t c0, int32_t c1, int32_t n_img, int32_t hw,
+                            int32_t groups, float eps, const float* chan0, const float* chan1, const float* gamma,
+                            const float* beta, int32_t silu, void* out, void* stream);
 
 /* LayerNorm over channels of a token matrix [rows, c] (LayerNormANE, layer_norm.py:51-80, in the
  * x_hat*w+b convention of the checkpoint, cf. unet.py:132-138). */

@@ -91,6 +91,7 @@ struct __align__(64) GemmParams {
     const float* ln_wg;        // [N] sum_k W'[j, k]
     int ln_parts, ln_k;
     float ln_eps;
+    long long* dbg;            // optional timeline of CTA 0 (clock64 at fixed points; tools/halo_timeline.py)
     int staged;                // staged epilogue (fp16 tile in shared memory, coalesced row-wise stores)
     int stage_dedicated;       // the staging tile has its own shared memory (persistent CTAs with several tiles)
 };
@@ -980,6 +981,10 @@ __device__ __forceinline__ float silu_fast(float y) {
     return fmaf(hy, th, hy);
 }
 
+__device__ __forceinline__ void dbg_mark(const GemmParams& p, int slot) {
+    if (p.dbg != nullptr && blockIdx.x == 0) p.dbg[slot] = clock64();
+}
+
 __device__ __forceinline__ void ldr_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 template <bool kFp32Direct>
@@ -1028,6 +1033,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) halo_conv_kernel(const __grid
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
     pdl_trigger();
+    if (threadIdx.x == 64) dbg_mark(p, 0);
 
     const int total_work = p.m_tiles * p.n_tiles;
     const int work0 = blockIdx.x, work_step = gridDim.x;
@@ -1064,6 +1070,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) halo_conv_kernel(const __grid
                 const int pa = ait & 1;
                 mbar_wait(&full_a[pa], (ait >> 1) & 1);
                 tc_fence_after();
+                if (lane == 0 && j < 24) dbg_mark(p, 64 + 2 * j);
                 const uint32_t pbase = smem_u32(patch + pa * p.patch_bytes) + 1024;
                 for (int tap = 0; tap < p.taps; ++tap, ++it) {
                     const int st = it % p.stages;
@@ -1086,6 +1093,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) halo_conv_kernel(const __grid
                         if (tap == p.taps - 1) {
                             umma_commit(&empty_a[pa]);
                             if (j == kc - 1) umma_commit(&tmem_full[as]);
+                            if (j < 24) dbg_mark(p, 65 + 2 * j);
                         }
                     }
                     __syncwarp();
@@ -1106,6 +1114,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) halo_conv_kernel(const __grid
             *reinterpret_cast<uint4*>(patch + which * p.patch_bytes + 7 * 128 + (ltid & 7) * 16) = make_uint4(0, 0, 0, 0);
         }
         pdl_wait();
+        if (ltid == 0) dbg_mark(p, 1);
         int cur_img = -1, ait = 0, iter = 0;
         for (int work = work0; work < total_work; work += work_step, ++iter) {
             const TileCoord t = decode_work(p, work);
@@ -1150,6 +1159,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) halo_conv_kernel(const __grid
                         regs[i] = __ldg(reinterpret_cast<const uint4*>(src + static_cast<size_t>(soff[i]) * csrc));
                 }
             }
+            if (ltid == 0) dbg_mark(p, 2);
             // (the first chunk's vectors are already in flight while the coefficient table is built)
             if (gn && img != cur_img) {
                 // ---- GroupNorm coefficients of this image: group statistics from the producers' per-channel sums ----
@@ -1196,7 +1206,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) halo_conv_kernel(const __grid
 #pragma unroll
                     for (int q = 0; q < 4; ++q) cf[q] = chan_ok ? *reinterpret_cast<const float4*>(tab + 2 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
+                if (ltid == 0 && j == 0) dbg_mark(p, 3);
                 mbar_wait(&empty_a[pa], ((ait >> 1) & 1) ^ 1);
+                if (ltid == 0 && j < 24) dbg_mark(p, 8 + 2 * j);
                 uint8_t* pbase = patch + pa * p.patch_bytes + 1024;
 #pragma unroll
                 for (int i = 0; i < NBMAX; ++i) {
@@ -1220,6 +1232,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) halo_conv_kernel(const __grid
                 }
                 fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
                 mbar_arrive(&full_a[pa]);
+                if (ltid == 0 && j < 24) dbg_mark(p, 9 + 2 * j);
             }
             // ---- epilogue ----
             const int as = p.acc_bufs == 2 ? (iter & 1) : 0;
@@ -1235,6 +1248,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) halo_conv_kernel(const __grid
             if (!kFp32Direct) staged_prefetch_residual(p, t, ew, lane, res_pre);  // hides behind the last chunk's MMAs
             mbar_wait(&tmem_full[as], aphase);
             tc_fence_after();
+            if (ltid == 0) dbg_mark(p, 4);
             epi_bar_sync();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_group * 32) << 16) + as * p.acc_stride;
             if (kFp32Direct) {
@@ -1259,6 +1273,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) halo_conv_kernel(const __grid
             }
             tc_fence_before();
             mbar_arrive(&tmem_empty[as]);
+            if (ltid == 0) dbg_mark(p, 5);
             epi_bar_sync();  // staging buffers (and, when aliased, the pipeline memory) are free again
         }
     }
@@ -1735,6 +1750,10 @@ static int launch_gemm(const b200sd_gemm_args& a, cudaStream_t stream) {
     p.rs_out = a.rs_out;
     p.ln_stat = a.ln_stat, p.ln_wg = a.ln_wg, p.ln_parts = a.ln_parts, p.ln_eps = a.ln_eps, p.ln_k = a.c0 + a.c1;
     p.staged = pl.staged, p.stage_dedicated = pl.stage_dedicated;
+    {
+        const char* e = getenv("B200SD_DBG_PTR");  // tools/halo_timeline.py: device address of a 128-slot int64 buffer
+        p.dbg = (e && e[0]) ? reinterpret_cast<long long*>(strtoull(e, nullptr, 0)) : nullptr;
+    }
     {
         // one accumulator buffer when no CTA sees a second tile (nothing to overlap the epilogue with); the allocation
         // is the smallest power of two that holds the buffers, so small tiles leave TMEM for a co-resident CTA

@@ -217,6 +217,77 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __half* __restrict_
     }
 }
 
+// ---- GroupNorm apply from producer-side statistics -----------------------------------------------------------------
+// The statistics pass is gone: the kernel that produced the tensor left per-channel (sum, sum of squares) behind
+// (staged GEMM epilogue, b200sd_gemm_args.cs_chan).  grid = (pixel blocks, n_img); every block folds the channel sums
+// of its image into group statistics (warp per group, fixed order), builds the per-channel scale / shift table in
+// shared memory and normalises (+SiLU, + concat of two sources) its pixel range: one read and one write of the tensor.
+__global__ void __launch_bounds__(256) gn_apply_chan_kernel(const __half* __restrict__ x0, const __half* __restrict__ x1,
+                                                            int c0, int c1, int hw, int groups, float eps,
+                                                            const float* __restrict__ chan0, const float* __restrict__ chan1,
+                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                            int silu, __half* __restrict__ out, int px_per_block) {
+    pdl_wait();
+    const int C = c0 + c1;
+    const int cpg = C / groups;
+    const int vecs = C / 8;
+    const int n = blockIdx.y;
+    extern __shared__ float sm[];  // scale[C], shift[C], stat[groups][2]
+    float* s_scale = sm;
+    float* s_shift = sm + C;
+    float* s_stat = sm + 2 * C;
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    const float inv_cnt = 1.0f / (static_cast<float>(cpg) * static_cast<float>(hw));
+    for (int g = wrp; g < groups; g += 8) {
+        float s = 0.f, q = 0.f;
+        for (int c = g * cpg + lane; c < (g + 1) * cpg; c += 32) {
+            const float2 v = (c < c0) ? *reinterpret_cast<const float2*>(chan0 + (static_cast<size_t>(n) * c0 + c) * 2)
+                                      : *reinterpret_cast<const float2*>(chan1 + (static_cast<size_t>(n) * c1 + c - c0) * 2);
+            s += v.x, q += v.y;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            s += __shfl_xor_sync(0xffffffffu, s, o);
+            q += __shfl_xor_sync(0xffffffffu, q, o);
+        }
+        if (lane == 0) {
+            const float mean = s * inv_cnt;
+            s_stat[2 * g] = mean;
+            s_stat[2 * g + 1] = rsqrtf(fmaxf(q * inv_cnt - mean * mean, 0.f) + eps);
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const int g = c / cpg;
+        const float sc = gamma[c] * s_stat[2 * g + 1];
+        s_scale[c] = sc;
+        s_shift[c] = beta[c] - s_stat[2 * g] * sc;
+    }
+    __syncthreads();
+    const int px0 = blockIdx.x * px_per_block;
+    const int px1 = min(hw, px0 + px_per_block);
+    const int total = (px1 - px0) * vecs;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        const int px = px0 + i / vecs;
+        const int ch = (i % vecs) * 8;
+        const __half* src = (ch < c0) ? x0 + (static_cast<size_t>(n) * hw + px) * c0 + ch
+                                      : x1 + (static_cast<size_t>(n) * hw + px) * c1 + (ch - c0);
+        float f[8];
+        load8(src, f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const float y = f[e] * s_scale[ch + e] + s_shift[ch + e];
+            f[e] = silu ? silu_f(y) : y;
+        }
+        uint4 pk;
+        pk.x = pack_half2(f[0], f[1]);
+        pk.y = pack_half2(f[2], f[3]);
+        pk.z = pack_half2(f[4], f[5]);
+        pk.w = pack_half2(f[6], f[7]);
+        *reinterpret_cast<uint4*>(out + (static_cast<size_t>(n) * hw + px) * C + ch) = pk;
+    }
+}
+
 // ---- GroupNorm on thread-block clusters (the default path) ---------------------------------------
 // grid = (cs, C / chunk, n_img) with cluster dims (cs, 1, 1): one cluster per (image, channel chunk), where a
 // chunk is a whole number of groups and of 16-byte vectors.  The cs CTAs of a cluster split the image's
@@ -597,6 +668,28 @@ extern "C" int b200sd_group_norm(const void* x0, const void* x1, int32_t c0, int
         gamma, beta, silu, reinterpret_cast<__half*>(out), px_per_block));
     B200SD_CHECK_CUDA(cudaGetLastError());
     count_launch(2);
+    return 0;
+}
+
+extern "C" int b200sd_group_norm_apply(const void* x0, const void* x1, int32_t c0, int32_t c1, int32_t n_img, int32_t hw,
+                                       int32_t groups, float eps, const float* chan0, const float* chan1,
+                                       const float* gamma, const float* beta, int32_t silu, void* out, void* stream_) {
+    if (!b200sd::launch_class_enabled(4)) return 0;  // bench.py's per-class timing graphs
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const int C = c0 + c1;
+    B200SD_REQUIRE(x0 && out && gamma && beta && chan0 && (c1 == 0 || (x1 && chan1)), "b200sd_group_norm_apply: null pointer");
+    B200SD_REQUIRE(c0 > 0 && c0 % 8 == 0 && c1 >= 0 && c1 % 8 == 0 && groups > 0 && C % groups == 0 && n_img <= 65535,
+                   "b200sd_group_norm_apply: bad channel / group counts (c0=%d c1=%d groups=%d)", c0, c1, groups);
+    const int want_blocks = std::max(1, (num_sms() * 2) / std::max(1, n_img));
+    const int px_per_block = std::max(1, (hw + want_blocks - 1) / want_blocks);
+    const int blocks = (hw + px_per_block - 1) / px_per_block;
+    const size_t smem = (2 * static_cast<size_t>(C) + 2 * groups) * sizeof(float);
+    B200SD_REQUIRE(smem <= 48 * 1024, "b200sd_group_norm_apply: too many channels (%d)", C);
+    B200SD_CHECK_CUDA(launch_kernel(gn_apply_chan_kernel, dim3(blocks, n_img), dim3(256), smem, stream,
+                                    reinterpret_cast<const __half*>(x0), reinterpret_cast<const __half*>(x1), c0, c1, hw, groups, eps,
+                                    chan0, chan1, gamma, beta, silu, reinterpret_cast<__half*>(out), px_per_block));
+    B200SD_CHECK_CUDA(cudaGetLastError());
+    count_launch(1);
     return 0;
 }
 

@@ -67,6 +67,9 @@ _SIGNATURES = {
                                     C.c_float, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
                                     C.c_size_t, C.c_void_p]),
     "b200sd_group_norm_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "b200sd_group_norm_apply": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                          C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
+                                          C.c_void_p]),
     "b200sd_layer_norm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                     C.c_float, C.c_void_p]),
     "b200sd_softmax_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_void_p]),
@@ -439,6 +442,18 @@ def group_norm(x, gamma, beta, groups, eps, silu=False, x1=None, out=None):
     _check(load().b200sd_group_norm(_ptr(x), _ptr(x1), c0, c1, nimg, h * w, groups, float(eps), _ptr(gamma),
                                     _ptr(beta), int(silu), _ptr(out), _ptr(ws), ws.numel() * 4, _stream()),
            "b200sd_group_norm")
+    return out
+
+
+def group_norm_apply(x, chan0, gamma, beta, groups, eps, silu=False, x1=None, chan1=None, out=None):
+    """GroupNorm (+SiLU, + concat) from the producers' per-channel sums ``chan0`` / ``chan1`` [N, C, 2]: no statistics pass."""
+    _req(x, torch.float16, "group_norm_apply x")
+    nimg, h, w, c0 = x.shape
+    c1 = 0 if x1 is None else x1.shape[-1]
+    if out is None:
+        out = torch.empty(nimg, h, w, c0 + c1, dtype=torch.float16, device=x.device)
+    _check(load().b200sd_group_norm_apply(_ptr(x), _ptr(x1), c0, c1, nimg, h * w, groups, float(eps), _ptr(chan0), _ptr(chan1),
+                                          _ptr(gamma), _ptr(beta), int(silu), _ptr(out), _stream()), "b200sd_group_norm_apply")
     return out
 
 

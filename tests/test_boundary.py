@@ -185,6 +185,7 @@ def test_sdxl_prompt_encoding_follows_the_reference_branch():
     refiner = types.SimpleNamespace(tokenizer=None, tokenizer_2=tok, text_encoder=None, text_encoder_2=enc(10, 5, 2.0),
                                     force_zeros_for_empty_prompt=True)
     emb3, pooled3 = P._encode_prompt_xl(refiner, ["ab"], False)
-    assert emb3.shape == (1, 10, 1, 77) and pooled3.shape == (1, 5)
+    # without guidance both batch halves of the UNet carry the prompt (the engine always runs 2B rows)
+    assert emb3.shape == (2, 10, 1, 77) and pooled3.shape == (2, 5) and np.array_equal(emb3[0], emb3[1])
     with pytest.raises(ValueError, match="batch size"):
         P._encode_prompt_xl(stub, ["ab", "cd"], True, negative_prompt=["x"])

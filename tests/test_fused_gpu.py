@@ -176,3 +176,19 @@ def test_halo_1x1_groupnorm_rowstats(cuda_lib):
     _close(out, ref, 5e-3, 3e-3, "halo 1x1 + GroupNorm")
     o = out.double().reshape(-1, c)
     _close(rs["rows"].double().sum(0)[:, 0], o.sum(1), 1e-2, 1e-4, "row sums (halo 1x1)")
+
+
+@pytest.mark.parametrize("n,h,w,c0,c1,silu", [(2, 64, 64, 320, 0, True), (2, 16, 16, 1280, 640, True), (2, 8, 8, 1280, 0, False)])
+def test_group_norm_apply_from_producer_statistics(cuda_lib, n, h, w, c0, c1, silu):
+    x0 = _rand(n, h, w, c0, seed=1, shift=0.3)
+    x1 = _rand(n, h, w, c1, seed=2, scale=1.7) if c1 else None
+    c = c0 + c1
+    gamma = (1.0 + 0.2 * torch.randn(c, device="cuda")).contiguous()
+    beta = (0.1 * torch.randn(c, device="cuda")).contiguous()
+    xc = x0 if x1 is None else torch.cat([x0, x1], -1)
+    out = cuda_lib.group_norm_apply(x0, _chan_sums(x0), gamma, beta, 32, 1e-5, silu=silu, x1=x1,
+                                    chan1=None if x1 is None else _chan_sums(x1))
+    y = F.group_norm(xc.float().permute(0, 3, 1, 2), 32, gamma, beta, 1e-5)
+    if silu:
+        y = F.silu(y)
+    _close(out, y.permute(0, 2, 3, 1), 3e-3, 3e-3, "group_norm_apply")
