@@ -252,6 +252,68 @@ int b200sd_latent_prep(const float* z, const float* w, const float* b, float inv
 int b200sd_image_postprocess(const void* in, int32_t in_f32, int32_t c_pad, float* out_f32, uint8_t* out_u8,
                              int32_t n, int32_t h, int32_t w, int32_t c, void* stream);
 
+/* ================================================================================================================
+ * Model-level handles: one "predict" per model, like the reference's device boundary.
+ *
+ * The op-level entry points above are what the hot path is made of; a host that is not Python should not have to
+ * re-implement the launch graph.  A handle owns the packed weights (given once, in the reference's own parameter names
+ * and layouts: the diffusers UNet2DConditionModel state dict the reference loads unchanged, unet.py:121-146 /
+ * torch2coreml.py:915-918), the activation arena, the statistics buffers and the launch sequence; per call only device
+ * pointers go in.  Replaces `CoreMLModel.__call__` for the unet (coreml_model.py:118-120, tensor names
+ * pipeline.py:531-536) and `Unet.predictNoise` (swift/StableDiffusion/pipeline/Unet.swift:90-144).
+ * Not thread-safe: one handle per stream / thread (the reference serialises per model, ManagedMLModel.swift:23-66). */
+typedef struct b200sd_unet b200sd_unet;
+
+typedef struct {
+    const char* name;     /* diffusers key, e.g. "down_blocks.0.resnets.0.conv1.weight" */
+    const void* data;     /* HOST pointer, row-major */
+    int32_t dtype;        /* 0 = fp16, 1 = fp32 */
+    int32_t ndim;         /* 1..4; linear weights may be [out, in] or [out, in, 1, 1] */
+    int64_t shape[4];
+} b200sd_weight;
+
+typedef struct {
+    /* architecture (the keys of the reference's UNet config, unet.py:733-800) */
+    int32_t in_channels, out_channels, layers_per_block, norm_num_groups, cross_attention_dim;
+    float norm_eps;
+    int32_t n_blocks;                 /* len(block_out_channels) */
+    int32_t block_out_channels[8];
+    int32_t attention_heads[8];       /* `attention_head_dim` of the reference = number of heads (unet.py:929) */
+    int32_t transformer_layers[8];    /* transformer_layers_per_block, per down block */
+    int32_t mid_transformer_layers;
+    int32_t down_cross_attn[8];       /* 1: CrossAttnDownBlock2D, 0: DownBlock2D */
+    int32_t up_cross_attn[8];         /* 1: CrossAttnUpBlock2D, 0: UpBlock2D (in up-block order) */
+    int32_t flip_sin_to_cos;
+    float freq_shift;
+    int32_t addition_embed_text_time; /* SDXL `text_time` conditioning (unet.py:1051-1152) */
+    int32_t addition_time_embed_dim, projection_class_embeddings_input_dim;
+    int32_t num_time_ids;             /* 6 (SDXL base), 5 (refiner); 0 = 6 */
+    int32_t support_controlnet;       /* forward accepts additional_residuals (unet.py:1009-1022) */
+    /* geometry the handle is built for */
+    int32_t batch, height, width, seq_len;   /* UNet batch (2 x images), latent height / width, text tokens */
+} b200sd_unet_config;
+
+/* Packs the weights (fp16, tiled per call site, LayerNorm folded into its consumer GEMMs), runs one sizing pass and
+ * allocates the activation arena.  `stream`: the stream the sizing pass runs on. */
+int b200sd_unet_create(const b200sd_unet_config* cfg, const b200sd_weight* weights, int32_t n_weights, void* stream,
+                       b200sd_unet** out);
+/* Optional per-prompt prologue: cross-attention K / V of every block from encoder_hidden_states (fp16 device
+ * (batch, cross_attention_dim, 1, seq_len)); later forwards may then pass encoder_hidden_states = NULL. */
+int b200sd_unet_prepare_prompt(b200sd_unet* h, const void* encoder_hidden_states, void* stream);
+/* noise_pred = UNet(sample, timestep, encoder_hidden_states [, time_ids, text_embeds][, additional_residual_i]).
+ * All pointers are DEVICE pointers: sample NCHW fp16 (or fp32 with sample_f32) (batch, in_channels, h, w); timesteps
+ * fp32 [batch]; encoder_hidden_states fp16 BC1S or NULL after b200sd_unet_prepare_prompt; time_ids fp32 (batch,
+ * num_time_ids) and text_embeds fp32 (batch, pooled) for SDXL, else NULL; additional_residuals: NULL or an array (host)
+ * of device pointers to the fp16 NCHW ControlNet residuals in controlnet.py:218-229 order; noise_pred fp32 NCHW. */
+int b200sd_unet_forward(b200sd_unet* h, const void* sample, int32_t sample_f32, const float* timesteps,
+                        const void* encoder_hidden_states, const float* time_ids, const float* text_embeds,
+                        const void* const* additional_residuals, float* noise_pred, void* stream);
+/* the reference's attention switch (unet.py:33-39): 0 ORIGINAL, 1 SPLIT_EINSUM, 2 SPLIT_EINSUM_V2 (same result) */
+int b200sd_unet_set_attention_impl(b200sd_unet* h, int32_t impl);
+/* bytes of activation arena + scratch the handle holds (weights excluded) */
+size_t b200sd_unet_device_bytes(const b200sd_unet* h);
+void b200sd_destroy(b200sd_unet* h);
+
 #ifdef __cplusplus
 }
 #endif

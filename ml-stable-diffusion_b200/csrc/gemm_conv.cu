@@ -28,7 +28,7 @@ static constexpr int kEpiThreads = 256;
 static constexpr int kMaxStages = 8;
 static constexpr int kHaloMaxStages = 24;  // weight ring of the halo kernel (narrow tiles need many stages in flight)
 static constexpr int kSmemBudget = 220 * 1024;
-static constexpr int kEpiFixed = 2 * 256 * 4 + 256 * 4 + 32;  // bias vectors, LayerNorm fold vector, flags
+static constexpr int kEpiFixed = 2 * 256 * 4 + 256 * 4 + 64;  // bias vectors, LayerNorm fold vector, flags + image ids
 
 // Shared-memory budget of one GEMM CTA.  B200SD_SMEM_KB (read per call: tuning scripts flip it) caps the pipeline
 // depth: at <= ~110 KB (and <= 256 TMEM columns) two CTAs fit on one SM, so under programmatic dependent launch the
@@ -68,6 +68,7 @@ struct __align__(64) GemmParams {
     float* partial;
     // ---- mode 2 (halo-reuse 3x3 convolution): the image is walked in padded-linear order q = y * (W + 1) + x ----
     int H, W, Wp, tiles_per_img, patch_rows, patch_bytes, upsample;
+    int inv_wp;                // ceil(2^20 / Wp): i / Wp == (i * inv_wp) >> 20 for the patch indices used here
     int win, tw, th, tiles_x;  // mode 2 windowed tiling (wide images): tiles of th rows x tw columns, pitch Wp = tw + halo
     int desc_bo;            // 1: row-shifted A descriptors carry (address >> 7) & 7 in the matrix-base-offset field
     const __half* a0;       // raw NHWC sources (loader warps read them with plain loads)
@@ -281,7 +282,7 @@ __device__ __forceinline__ bool tile_row(const GemmParams& p, const TileCoord& t
     }
     if (p.mode == 2) {  // patch pixel -> image pixel; pad columns and the tile tail are junk rows
         const int pi = t.c0 + row;
-        const int r = pi / p.Wp;
+        const int r = (pi * p.inv_wp) >> 20;
         const int y = t.ya + r, x = t.xa + (pi - r * p.Wp);
         out_row = (t.n0 * p.H + y) * p.W + x;
         return x >= t.xlo && x < t.xhi && y >= t.ylo && y < t.yhi;
@@ -316,10 +317,15 @@ __device__ __forceinline__ float4 ld_dsmem_f4(uint32_t local_addr, uint32_t cta_
 }
 
 
+// out-of-line copy for the staged epilogue (called from several unrolled places: code size is fetch time there)
+__device__ __noinline__ bool tile_row_nl(const GemmParams& p, const TileCoord& t, int row, int& out_row) {
+    return tile_row(p, t, row, out_row);
+}
+
 // image a tile row belongs to (statistics are per image); -1 for rows outside the problem
 __device__ __forceinline__ int row_image(const GemmParams& p, const TileCoord& t, int row) {
     int out_row;
-    if (!tile_row(p, t, row, out_row)) {
+    if (!tile_row_nl(p, t, row, out_row)) {
         if (p.mode != 2) return -1;
         return t.n0;  // a junk row of a mode-2 tile still belongs to the tile's image
     }
@@ -343,27 +349,35 @@ __device__ __forceinline__ float2 ln_row_coeffs(const GemmParams& p, int out_row
     return make_float2(rstd, -mu * rstd);
 }
 
-// Residual rows of this warp's 16 tile rows, requested while the main loop (or its tail) still runs: the staged
-// epilogue's store pass would otherwise pay one L2 round trip per row.  Same lane <-> (row, vector) mapping as phase B.
-__device__ __forceinline__ void staged_prefetch_residual(const GemmParams& p, const TileCoord& t, int ew, int lane,
-                                                         uint4 (&res)[8], int it0 = 0) {
-    const int bn = p.block_n;
-    const int vpr = bn >> 3;
-    int L = 8;
-    while (L < vpr) L <<= 1;
-    const int rpi = 32 / L;
-    const int lr = lane / L, lcv = lane - lr * L;
-    const int ncol0 = t.n_tile * bn;
-    const bool col_ok = lcv < vpr && (ncol0 + lcv * 8) < p.N;
+// lane <-> (row slot, 16-byte column vector) mapping of the staged epilogue's store pass: L lanes walk one tile row
+struct StagedMap {
+    int L, rpi, lr, lcv, nit;
+    bool col_ok;
+};
+__device__ __forceinline__ StagedMap staged_map(const GemmParams& p, const TileCoord& t, int lane) {
+    StagedMap m;
+    const int vpr = p.block_n >> 3;
+    m.L = 8;
+    while (m.L < vpr) m.L <<= 1;
+    m.rpi = 32 / m.L;
+    m.lr = lane / m.L;
+    m.lcv = lane - m.lr * m.L;
+    m.nit = 16 / m.rpi;
+    m.col_ok = m.lcv < vpr && (t.n_tile * p.block_n + m.lcv * 8) < p.N;
+    return m;
+}
+
+// Residual vectors of four consecutive store-pass iterations of this warp (zeros where there is nothing to add).
+__device__ __forceinline__ void staged_load_residual(const GemmParams& p, const TileCoord& t, const StagedMap& m, int ew,
+                                                     int it0, uint4 (&res)[4]) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int it = it0 + i;
-        res[i] = make_uint4(0, 0, 0, 0);
-        if (it < 16 / rpi && p.residual != nullptr) {
-            const int r = ew * 16 + it * rpi + lr;
+    for (int q = 0; q < 4; ++q) {
+        res[q] = make_uint4(0, 0, 0, 0);
+        const int it = it0 + q;
+        if (p.residual != nullptr && it < m.nit && m.col_ok) {
             int orow;
-            if (tile_row(p, t, r, orow) && col_ok)
-                res[i] = *reinterpret_cast<const uint4*>(p.residual + static_cast<size_t>(orow) * p.N + ncol0 + lcv * 8);
+            if (tile_row_nl(p, t, ew * 16 + it * m.rpi + m.lr, orow))
+                res[q] = *reinterpret_cast<const uint4*>(p.residual + static_cast<size_t>(orow) * p.N + t.n_tile * p.block_n + m.lcv * 8);
         }
     }
 }
@@ -373,29 +387,35 @@ __device__ __forceinline__ void staged_prefetch_residual(const GemmParams& p, co
 //          -> staging tile in shared memory [128][block_n + 8].
 // Phase B: warp w owns rows [16 w, 16 w + 16); its lanes walk a row as 16-byte vectors, so the residual read and the
 //          output store are contiguous row segments; the same pass accumulates the per-channel (column) sums that the
-//          consumer's GroupNorm needs and the per-row sums its LayerNorm needs, from the ROUNDED outputs.
+//          consumer's GroupNorm needs and the per-row sums its LayerNorm needs, from the ROUNDED outputs.  Residual
+//          vectors are requested four iterations ahead (the first four before the accumulator wait).
 // Phase C: column sums: lanes -> warps (shared memory, fixed order) -> one partial per (image, tile); the last CTA to
 //          arrive for an (image, n_tile) adds the partials of all tiles in slot order: deterministic, no float atomics.
-__device__ __forceinline__ void staged_epilogue(const GemmParams& p, const TileCoord& t, uint32_t taddr, __half* tile_s,
-                                                float* scratch, unsigned int* flag_s, const float* bias_row,
-                                                const float* wg_s, int ew, int lane, int row, int out_row, bool valid,
-                                                const uint4 (&res_pre)[8]) {
+// Kept compact on purpose (runtime loops, small unroll factors): these kernels execute every instruction once per
+// CTA, so code size is instruction-fetch time.
+__device__ __noinline__ void staged_epilogue(const GemmParams& p, const TileCoord& t, uint32_t taddr, __half* tile_s,
+                                             float* scratch, unsigned int* flag_s, const float* bias_row,
+                                             const float* wg_s, int ew, int lane, int row, int out_row, bool valid,
+                                             uint4 (&res)[4]) {
     const int bn = p.block_n;
     const int ldt = bn + 8;
-    const int half = ew >> 2;
     const int ncol0 = t.n_tile * bn;
     // ---------------- phase A ----------------
     {
         const float2 lc = ln_row_coeffs(p, out_row, valid);
         const bool ln = p.ln_parts != 0;
         __half* trow = tile_s + row * ldt;
-        auto convert32 = [&](const uint32_t (&v)[32], int c) {
+        uint32_t va[32];
+#pragma unroll 1
+        for (int c = 32 * (ew >> 2); c < bn; c += 64) {
+            tmem_ld32(taddr + c, va);
+            tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
                 float x[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
-                    float a = __uint_as_float(v[j + e]);
+                    float a = __uint_as_float(va[j + e]);
                     if (ln) a = fmaf(a, lc.x, lc.y * wg_s[c + j + e]);
                     if (bias_row != nullptr) a += bias_row[c + j + e];
                     x[e] = a;
@@ -407,102 +427,81 @@ __device__ __forceinline__ void staged_epilogue(const GemmParams& p, const TileC
                 pk.w = pack_half2(x[6], x[7]);
                 *reinterpret_cast<uint4*>(trow + c + j) = pk;
             }
-        };
-        // (single TMEM buffer: the kernel runs at the 168-register cap of three warps per scheduler, and the TMEM read
-        // is a small part of this epilogue)
-        uint32_t va[32];
-        for (int c = 32 * half; c < bn; c += 64) {
-            tmem_ld32(taddr + c, va);
-            tmem_ld_wait();
-            convert32(va, c);
         }
     }
     epi_bar_sync();
     // ---------------- phase B ----------------
-    const int vpr = bn >> 3;
-    int L = 8;
-    while (L < vpr) L <<= 1;
-    const int rpi = 32 / L;
-    const int lr = lane / L, lcv = lane - lr * L;
-    const bool col_ok = lcv < vpr && (ncol0 + lcv * 8) < p.N;
+    const StagedMap m = staged_map(p, t, lane);
+    const bool want_stats = p.cs_partial != nullptr || p.rs_out != nullptr;
     float cs[8], cq[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) cs[e] = cq[e] = 0.f;
-    // residual rows: the first eight iterations were requested before the accumulator wait; the second eight are
-    // requested now and land while the first eight are processed
-    uint4 res_late[8];
-    staged_prefetch_residual(p, t, ew, lane, res_late, 8);
+#pragma unroll 1
+    for (int it0 = 0; it0 < m.nit; it0 += 4) {
+        uint4 nxt[4];
+        staged_load_residual(p, t, m, ew, it0 + 4, nxt);  // lands while this group is processed
 #pragma unroll
-    for (int it = 0; it < 16; ++it) {
-        if (it >= 16 / rpi) break;
-        const int r = ew * 16 + it * rpi + lr;
-        int orow;
-        const bool rv = tile_row(p, t, r, orow);
-        float rsum = 0.f, rsq = 0.f;
-        if (rv && col_ok) {
-            const uint4 raw = *reinterpret_cast<const uint4*>(tile_s + r * ldt + lcv * 8);
-            const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
-            float x[8];
+        for (int q = 0; q < 4; ++q) {
+            const int it = it0 + q;
+            if (it >= m.nit) break;
+            const int r = ew * 16 + it * m.rpi + m.lr;
+            int orow;
+            const bool rv = tile_row_nl(p, t, r, orow);
+            float rsum = 0.f, rsq = 0.f;
+            if (rv && m.col_ok) {
+                const uint4 raw = *reinterpret_cast<const uint4*>(tile_s + r * ldt + m.lcv * 8);
+                const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+                const __half2* r2 = reinterpret_cast<const __half2*>(&res[q]);
+                uint4 pk;
+                __half2* o2 = reinterpret_cast<__half2*>(&pk);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float2 f = __half22float2(h2[q]);
-                x[2 * q] = f.x, x[2 * q + 1] = f.y;
-            }
-            const size_t off = static_cast<size_t>(orow) * p.N + ncol0 + lcv * 8;
-            if (p.residual != nullptr) {
-                const uint4 rr = it < 8 ? res_pre[it] : res_late[it - 8];
-                const __half2* r2 = reinterpret_cast<const __half2*>(&rr);
+                for (int k = 0; k < 4; ++k) {
+                    const float2 f = __half22float2(h2[k]), g = __half22float2(r2[k]);
+                    o2[k] = __floats2half2_rn(f.x + g.x, f.y + g.y);
+                }
+                *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out) + static_cast<size_t>(orow) * p.N + ncol0 + m.lcv * 8) = pk;
+                if (want_stats) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const float2 f = __half22float2(r2[q]);
-                    x[2 * q] += f.x, x[2 * q + 1] += f.y;
+                    for (int k = 0; k < 4; ++k) {  // statistics of what the consumer will read: the rounded values
+                        const float2 f = __half22float2(o2[k]);
+                        cs[2 * k] += f.x, cs[2 * k + 1] += f.y;
+                        cq[2 * k] = fmaf(f.x, f.x, cq[2 * k]), cq[2 * k + 1] = fmaf(f.y, f.y, cq[2 * k + 1]);
+                        rsum += f.x + f.y;
+                        rsq = fmaf(f.x, f.x, fmaf(f.y, f.y, rsq));
+                    }
                 }
             }
-            uint4 pk;
-            __half2* o2 = reinterpret_cast<__half2*>(&pk);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) o2[q] = __floats2half2_rn(x[2 * q], x[2 * q + 1]);
-            *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out) + off) = pk;
-            if (p.cs_partial != nullptr || p.rs_out != nullptr) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {  // statistics of what the consumer will read: the rounded values
-                    const float2 f = __half22float2(o2[q]);
-                    cs[2 * q] += f.x, cs[2 * q + 1] += f.y;
-                    cq[2 * q] = fmaf(f.x, f.x, cq[2 * q]), cq[2 * q + 1] = fmaf(f.y, f.y, cq[2 * q + 1]);
-                    rsum += f.x + f.y;
-                    rsq = fmaf(f.x, f.x, fmaf(f.y, f.y, rsq));
+            if (p.rs_out != nullptr) {
+                for (int o = 1; o < m.L; o <<= 1) {
+                    rsum += __shfl_xor_sync(0xffffffffu, rsum, o);
+                    rsq += __shfl_xor_sync(0xffffffffu, rsq, o);
                 }
+                if (rv && m.lcv == 0)
+                    *reinterpret_cast<float2*>(p.rs_out + (static_cast<size_t>(t.n_tile) * p.M + orow) * 2) = make_float2(rsum, rsq);
             }
         }
-        if (p.rs_out != nullptr) {
-            for (int o = 1; o < L; o <<= 1) {
-                rsum += __shfl_xor_sync(0xffffffffu, rsum, o);
-                rsq += __shfl_xor_sync(0xffffffffu, rsq, o);
-            }
-            if (rv && lcv == 0)
-                *reinterpret_cast<float2*>(p.rs_out + (static_cast<size_t>(t.n_tile) * p.M + orow) * 2) = make_float2(rsum, rsq);
-        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) res[q] = nxt[q];
     }
     if (p.cs_partial == nullptr) return;
     // ---------------- phase C ----------------
-    for (int o = L; o < 32; o <<= 1) {
+    for (int o = m.L; o < 32; o <<= 1) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             cs[e] += __shfl_xor_sync(0xffffffffu, cs[e], o);
             cq[e] += __shfl_xor_sync(0xffffffffu, cq[e], o);
         }
     }
-    if (lr == 0 && lcv < vpr) {
-        float2* dst = reinterpret_cast<float2*>(scratch) + ew * bn + lcv * 8;
+    if (m.lr == 0 && m.lcv < (bn >> 3)) {
+        float2* dst = reinterpret_cast<float2*>(scratch) + ew * bn + m.lcv * 8;
 #pragma unroll
         for (int e = 0; e < 8; ++e) dst[e] = make_float2(cs[e], cq[e]);
     }
+    // the image of each of the tile's eight 16-row groups (uniform inside a group by construction, see the launcher)
+    int* img_s = reinterpret_cast<int*>(flag_s) + 8;
+    if (lane == 0) img_s[ew] = row_image(p, t, ew * 16);
     epi_bar_sync();
     const int tid_e = ew * 32 + lane;
-    // the images of the tile's eight 16-row groups (uniform inside a group by construction, see the launcher)
-    int img_of[8];
-#pragma unroll
-    for (int w = 0; w < 8; ++w) img_of[w] = row_image(p, t, w * 16);
     int slot = 0;
     if (p.mode == 2) slot = t.w0;
     else if (p.mode == 0) slot = p.cs_hw >= kBM ? (t.m_tile % (p.cs_hw / kBM)) : 0;
@@ -512,10 +511,10 @@ __device__ __forceinline__ void staged_epilogue(const GemmParams& p, const TileC
         if (ncol0 + col >= p.N) continue;
         int w = 0;
         while (w < 8) {
-            const int img = img_of[w];
+            const int img = img_s[w];
             float a = 0.f, b = 0.f;
             int w2 = w;
-            while (w2 < 8 && img_of[w2] == img) {
+            while (w2 < 8 && img_s[w2] == img) {
                 a += sc2[w2 * bn + col].x, b += sc2[w2 * bn + col].y;
                 ++w2;
             }
@@ -528,29 +527,29 @@ __device__ __forceinline__ void staged_epilogue(const GemmParams& p, const TileC
     __threadfence();
     epi_bar_sync();
     if (tid_e == 0) {
-        int w = 0, k = 0;
+        int w = 0;
         while (w < 8) {
-            const int img = img_of[w];
+            const int img = img_s[w];
             int w2 = w;
-            while (w2 < 8 && img_of[w2] == img) ++w2;
+            while (w2 < 8 && img_s[w2] == img) ++w2;
             unsigned int last = 0;
             if (img >= 0) {
                 const unsigned int old = atomicAdd(&p.cs_tickets[img * p.n_tiles + t.n_tile], 1u);
                 last = (old == static_cast<unsigned int>(p.cs_slots - 1)) ? 1u : 0u;
                 if (last) p.cs_tickets[img * p.n_tiles + t.n_tile] = 0;  // self-reset for the next launch
             }
-            flag_s[k++] = last;
+            flag_s[w] = last;  // indexed by the group's first warp
             w = w2;
         }
     }
     epi_bar_sync();
     {
-        int w = 0, k = 0;
+        int w = 0;
         while (w < 8) {
-            const int img = img_of[w];
+            const int img = img_s[w];
             int w2 = w;
-            while (w2 < 8 && img_of[w2] == img) ++w2;
-            if (flag_s[k++] != 0) {
+            while (w2 < 8 && img_s[w2] == img) ++w2;
+            if (flag_s[w] != 0) {
                 __threadfence();
                 for (int col = tid_e; col < bn; col += kEpiThreads) {
                     if (ncol0 + col >= p.N) continue;
@@ -586,7 +585,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) umma_gemm_kernel(const __grid
     float* bias_s = reinterpret_cast<float*>(tmem_ptr + 4);           // [2][block_n] (16 B aligned)
     float* wg_s = bias_s + 2 * 256;                                   // [block_n] LayerNorm fold vector
     unsigned int* flag_s = reinterpret_cast<unsigned int*>(wg_s + 256);  // [8]
-    __half* res_s = reinterpret_cast<__half*>(flag_s + 8);            // [128][block_n + 8] residual / staging tile
+    __half* res_s = reinterpret_cast<__half*>(flag_s + 16);           // [128][block_n + 8] residual / staging tile
     const int ldr = p.block_n + 8;
 
     const int warp = threadIdx.x >> 5;
@@ -794,8 +793,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) umma_gemm_kernel(const __grid
             }
             if (p.ln_parts != 0)
                 for (int c = tid_e; c < p.block_n; c += kEpiThreads) wg_s[c] = (ncol0 + c < p.N) ? p.ln_wg[ncol0 + c] : 0.f;
-            uint4 res_pre[8];
-            if (kStaged) staged_prefetch_residual(p, t, warp - 2, lane, res_pre);
+            uint4 res_pre[4];
+            if (kStaged) staged_load_residual(p, t, staged_map(p, t, lane), warp - 2, 0, res_pre);
             if (p.res_smem) {
                 const int vpr = p.block_n >> 3;  // 16-byte vectors per tile row
                 for (int i = tid_e; i < kBM * vpr; i += kEpiThreads) {
@@ -1003,7 +1002,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) halo_conv_kernel(const __grid
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
     float* bias_s = reinterpret_cast<float*>(tmem_ptr + 4);               // [256]
     unsigned int* flag_s = reinterpret_cast<unsigned int*>(bias_s + 256);   // [8]
-    float2* stat_s = reinterpret_cast<float2*>(flag_s + 8);               // [64] (mean, rstd) per group
+    float2* stat_s = reinterpret_cast<float2*>(flag_s + 16);              // [64] (mean, rstd) per group
     float2* scsh = stat_s + 64;                                           // [C0 + C1] (scale, shift) per channel
     const int Cin = p.C0 + p.C1;
     __half* stage_tile = reinterpret_cast<__half*>(scsh + ((Cin + 7) & ~7));  // dedicated staging tile (if any)
@@ -1134,7 +1133,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) halo_conv_kernel(const __grid
             for (int i = 0; i < NBMAX; ++i) {
                 const int v = ltid + kEpiThreads * i;
                 const int pi = v >> 3;
-                const int yy = ya + pi / p.Wp, xx = xa + pi % p.Wp;
+                const int prow = (pi * p.inv_wp) >> 20;
+                const int yy = ya + prow, xx = xa + (pi - prow * p.Wp);
                 const bool in_patch = i < nb && v < nvec;
                 const bool ok = in_patch && yy >= 0 && yy < p.H && xx >= 0 && xx < p.W;
                 const int ys = ups ? (yy >> 1) : yy, xs = ups ? (xx >> 1) : xx;
@@ -1244,8 +1244,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) halo_conv_kernel(const __grid
             }
             int out_row;
             const bool valid = tile_row(p, t, row, out_row);
-            uint4 res_pre[8];
-            if (!kFp32Direct) staged_prefetch_residual(p, t, ew, lane, res_pre);  // hides behind the last chunk's MMAs
+            uint4 res_pre[4];
+            if (!kFp32Direct) staged_load_residual(p, t, staged_map(p, t, lane), ew, 0, res_pre);  // hides behind the last chunk's MMAs
             mbar_wait(&tmem_full[as], aphase);
             tc_fence_after();
             if (ltid == 0) dbg_mark(p, 4);
@@ -1425,7 +1425,7 @@ static int plan_halo(const b200sd_gemm_args& a, GemmPlan& pl) {
     pl.staged = fp32_direct ? 0 : 1;
     pl.stage_dedicated = (pl.staged && pl.acc_bufs == 2) ? 1 : 0;
     const int cin = a.c0 + a.c1;
-    const int fixed = 2 * pl.patch_bytes + (2 * kHaloMaxStages + 8) * 8 + 16 + 256 * 4 + 32 + 64 * 8 + ((cin + 7) & ~7) * 8 +
+    const int fixed = 2 * pl.patch_bytes + (2 * kHaloMaxStages + 8) * 8 + 16 + 256 * 4 + 64 + 64 * 8 + ((cin + 7) & ~7) * 8 +
                       (pl.stage_dedicated ? kBM * (pl.block_n + 8) * 2 + 8 * pl.block_n * 8 : 0) + 1024;
     const int b_stage = pl.block_n * kBK * 2;
     pl.stages = std::min(kHaloMaxStages, (227 * 1024 - fixed) / b_stage);
@@ -1732,6 +1732,7 @@ static int launch_gemm(const b200sd_gemm_args& a, cudaStream_t stream) {
     p.m_pairs = (pl.m_tiles + 1) / 2;
     p.H = a.h, p.W = a.w, p.Wp = pl.Wp, p.tiles_per_img = pl.tiles_per_img;
     p.win = pl.win, p.tw = pl.tw, p.th = pl.th, p.tiles_x = pl.tiles_x;
+    p.inv_wp = pl.Wp > 0 ? (1 << 20) / pl.Wp + 1 : 0;
     p.patch_rows = pl.patch_rows, p.patch_bytes = pl.patch_bytes;
     p.upsample = a.upsample2x, p.desc_bo = desc_base_offset_enabled() ? 1 : 0;
     p.a0 = reinterpret_cast<const __half*>(a.a0), p.a1 = reinterpret_cast<const __half*>(a.a1), p.C1 = a.c1;

@@ -54,6 +54,14 @@ _SIGNATURES = {
     "b200sd_launch_count": (C.c_uint64, []),
     "b200sd_set_pdl": (None, [C.c_int]),
     "b200sd_set_launch_classes": (None, [C.c_uint32]),
+    # model-level handles (capi.py holds the struct mirrors)
+    "b200sd_unet_create": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "b200sd_unet_prepare_prompt": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b200sd_unet_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b200sd_unet_set_attention_impl": (C.c_int, [C.c_void_p, C.c_int32]),
+    "b200sd_unet_device_bytes": (C.c_size_t, [C.c_void_p]),
+    "b200sd_destroy": (None, [C.c_void_p]),
     "b200sd_gemm": (C.c_int, [C.POINTER(GemmArgs), C.c_void_p]),
     "b200sd_gemm_workspace_bytes": (C.c_size_t, [C.POINTER(GemmArgs)]),
     "b200sd_gemm_plan": (C.c_int, [C.POINTER(GemmArgs), C.POINTER(C.c_int32)]),

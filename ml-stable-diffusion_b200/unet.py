@@ -102,6 +102,11 @@ class UNetEngine:
         # into the consumer GEMM, statistics from the producers' epilogues.  B200SD_FUSED=0 keeps the round-1 graph
         # (standalone GroupNorm / LayerNorm launches) for A/B measurements.
         self.fused = os.environ.get("B200SD_FUSED", "1") != "0"
+        # how a GroupNorm whose statistics came from the producer is applied: "halo" = inside the halo convolution's
+        # operand path (no launch); "apply" = one elementwise launch (b200sd_group_norm_apply) in front of the 9-tap TMA
+        # convolution; B200SD_FUSED=1 halo everywhere, 2 apply everywhere, 3 halo on maps of >= B200SD_HALO_MIN_HW pixels
+        fm = os.environ.get("B200SD_FUSED", "1")
+        self.halo_min_hw = {"1": 0, "2": 1 << 30, "3": int(os.environ.get("B200SD_HALO_MIN_HW", "1024"))}.get(fm, 0)
         for c, h in zip(boc, self.heads):
             if c % h or c // h != 64:
                 raise L.B200SDError(f"b200sd attention kernel needs head dim 64 (got {c}/{h})")
@@ -268,12 +273,20 @@ class UNetEngine:
     # An activation travels as (tensor, chan): chan = per-channel (sum, sum of squares) [n, C, 2] left behind by the
     # epilogue that produced the tensor, or None when the producer could not emit them (then the consumer falls back
     # to the standalone GroupNorm kernel).
+    def _use_halo(self, x):
+        return x.shape[1] * x.shape[2] >= self.halo_min_hw
+
     def _gn_conv(self, x, xs, x1, x1s, gamma, beta, eps, silu, wgt, bias, residual=None, stats=None, **kw):
-        if xs is not None and (x1 is None or x1s is not None):
+        have = xs is not None and (x1 is None or x1s is not None)
+        halo = self._use_halo(x)
+        if have and halo:
             gn = dict(chan0=xs, chan1=x1s, gamma=gamma, beta=beta, groups=self.groups, eps=eps, silu=silu)
             return L.conv3x3(x, wgt, bias, residual, x1=x1, halo=True, gn=gn, stats=stats, **kw)
-        hh = L.group_norm(x, gamma, beta, self.groups, eps, silu=silu, x1=x1)
-        return L.conv3x3(hh, wgt, bias, residual, halo=True, stats=stats, **kw)
+        if have:
+            hh = L.group_norm_apply(x, xs, gamma, beta, self.groups, eps, silu=silu, x1=x1, chan1=x1s)
+        else:
+            hh = L.group_norm(x, gamma, beta, self.groups, eps, silu=silu, x1=x1)
+        return L.conv3x3(hh, wgt, bias, residual, halo=halo, stats=stats, **kw)
 
     def _resnet_f(self, p, x, xs, x1, x1s, temb_all):
         r = self.w[p]
@@ -297,11 +310,12 @@ class UNetEngine:
         m, s = n * h * wd, h * wd
         impl = _IMPL_CODE[ATTENTION_IMPLEMENTATION_IN_EFFECT]
         rs = {}
-        if xs is not None:
+        if xs is not None and self._use_halo(x):
             gn = dict(chan0=xs, chan1=None, gamma=t["ng"], beta=t["nb"], groups=32, eps=1e-6, silu=False)
             tok = L.conv3x3(x, t["pi"], t["pib"], halo=True, taps=1, gn=gn, rowstats=rs).reshape(m, c)
         else:
-            hn = L.group_norm(x, t["ng"], t["nb"], 32, 1e-6, silu=False)
+            hn = (L.group_norm_apply(x, xs, t["ng"], t["nb"], 32, 1e-6) if xs is not None
+                  else L.group_norm(x, t["ng"], t["nb"], 32, 1e-6, silu=False))
             tok = L.linear(hn.reshape(m, c), t["pi"], t["pib"], static_w=True, rowstats=rs)
 
         def ln_of(rs, blk, name):
@@ -360,7 +374,10 @@ class UNetEngine:
             if i != self.nb - 1:
                 u = self.w[f"up_blocks.{i}.upsamplers.0.conv"]
                 st = {}
-                x = L.conv3x3(x, u["w"], u["b"], halo=True, upsample=True, stats=st)
+                if 4 * x.shape[1] * x.shape[2] >= self.halo_min_hw:
+                    x = L.conv3x3(x, u["w"], u["b"], halo=True, upsample=True, stats=st)
+                else:
+                    x = L.conv3x3(L.upsample2x(x), u["w"], u["b"], stats=st)
                 xs = st.get("chan")
         o = self.w["out"]
         return self._gn_conv(x, xs, None, None, o["g"], o["b"], self.eps, True, o["w"], o["cb"], out_dtype=torch.float32,

@@ -33,18 +33,24 @@ def test_struct_layouts_match_header(tmp_path):
     import shutil
     import subprocess
 
-    from b200sd import lib
+    from b200sd import capi, lib
     gcc = shutil.which("gcc")
     if gcc is None:
         pytest.skip("gcc not available")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     fields_g = [f[0] for f in lib.GemmArgs._fields_]
     fields_s = [f[0] for f in lib.StepCoeffs._fields_]
+    fields_u = [f[0] for f in capi.UNetConfig._fields_]
+    fields_w = [f[0] for f in capi.Weight._fields_]
     src = ['#include <stdio.h>', '#include <stddef.h>', '#include "b200sd.h"', 'int main(void) {',
            'printf("%zu\\n", sizeof(b200sd_gemm_args));']
     src += [f'printf("%zu\\n", offsetof(b200sd_gemm_args, {f}));' for f in fields_g]
     src += ['printf("%zu\\n", sizeof(b200sd_step_coeffs));']
     src += [f'printf("%zu\\n", offsetof(b200sd_step_coeffs, {f}));' for f in fields_s]
+    src += ['printf("%zu\\n", sizeof(b200sd_unet_config));']
+    src += [f'printf("%zu\\n", offsetof(b200sd_unet_config, {f}));' for f in fields_u]
+    src += ['printf("%zu\\n", sizeof(b200sd_weight));']
+    src += [f'printf("%zu\\n", offsetof(b200sd_weight, {f}));' for f in fields_w]
     src += ['return 0; }']
     c = tmp_path / "layout.c"
     c.write_text("\n".join(src))
@@ -53,6 +59,8 @@ def test_struct_layouts_match_header(tmp_path):
     vals = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
     want = [ctypes.sizeof(lib.GemmArgs)] + [getattr(lib.GemmArgs, f).offset for f in fields_g]
     want += [ctypes.sizeof(lib.StepCoeffs)] + [getattr(lib.StepCoeffs, f).offset for f in fields_s]
+    want += [ctypes.sizeof(capi.UNetConfig)] + [getattr(capi.UNetConfig, f).offset for f in fields_u]
+    want += [ctypes.sizeof(capi.Weight)] + [getattr(capi.Weight, f).offset for f in fields_w]
     assert vals == want
 
 
