@@ -71,7 +71,7 @@ class ControlNetEngine(UNetEngine):
         e = self.embed_condition(cond_nhwc) if emb is None else emb
         if self.fused:
             st = {}
-            x = L.conv3x3(sample, self.w["conv_in"]["w"], self.w["conv_in"]["b"], e, stats=st)
+            x = L.conv3x3(sample, self.w["conv_in"]["w"], self.w["conv_in"]["b"], e, stats=st if self.fuse_gn else None)
             xs = st.get("chan")
             skips = [x]
             for i, typ in enumerate(self.down_types):
@@ -83,7 +83,7 @@ class ControlNetEngine(UNetEngine):
                 if i != self.nb - 1:
                     d = self.w[f"down_blocks.{i}.downsamplers.0.conv"]
                     st = {}
-                    x = L.conv3x3(x, d["w"], d["b"], stride=2, stats=st)
+                    x = L.conv3x3(x, d["w"], d["b"], stride=2, stats=st if self.fuse_gn else None)
                     xs = st.get("chan")
                     skips.append(x)
             x, xs = self._resnet_f("mid_block.resnets.0", x, xs, None, None, temb_all)

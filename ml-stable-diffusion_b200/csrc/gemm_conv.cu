@@ -170,7 +170,7 @@ __device__ __forceinline__ void split_range(const GemmParams& p, int split, int&
 // vector code only, which keeps the kernel small enough for the instruction cache of these microsecond kernels.
 template <bool kGeneric, bool kGeglu, bool kOutF32, bool kPartial>
 __device__ __forceinline__ void epilogue_store16(const GemmParams& p, float (&acc)[16], int out_row, int col0,
-                                                 int split, const float* bias, const __half* res) {
+                                                 int split, const float* bias, const __half* res, float2& rowacc) {
     const bool partial = kGeneric ? (p.partial != nullptr) : kPartial;
     const bool geglu = kGeneric ? (p.geglu != 0) : kGeglu;
     const bool out_f32 = kGeneric ? (p.out_f32 != 0) : kOutF32;
@@ -264,6 +264,15 @@ __device__ __forceinline__ void epilogue_store16(const GemmParams& p, float (&ac
                     pk.z = pack_half2(acc[j + 4], acc[j + 5]);
                     pk.w = pack_half2(acc[j + 6], acc[j + 7]);
                     *reinterpret_cast<uint4*>(o + j) = pk;
+                    if (p.rs_out != nullptr) {  // per-row sums of the ROUNDED outputs for the consumer's LayerNorm
+                        const __half2* h2 = reinterpret_cast<const __half2*>(&pk);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float2 f = __half22float2(h2[q]);
+                            rowacc.x += f.x + f.y;
+                            rowacc.y = fmaf(f.x, f.x, fmaf(f.y, f.y, rowacc.y));
+                        }
+                    }
                 }
             }
         } else {
@@ -317,8 +326,9 @@ __device__ __forceinline__ float4 ld_dsmem_f4(uint32_t local_addr, uint32_t cta_
 }
 
 
-// out-of-line copy for the staged epilogue (called from several unrolled places: code size is fetch time there)
-__device__ __noinline__ bool tile_row_nl(const GemmParams& p, const TileCoord& t, int row, int& out_row) {
+// (kept inline: an out-of-line copy would read the kernel parameters through a generic pointer -- LD.E instead of the
+// constant bank -- which measured 2.5x slower for the whole epilogue)
+__device__ __forceinline__ bool tile_row_nl(const GemmParams& p, const TileCoord& t, int row, int& out_row) {
     return tile_row(p, t, row, out_row);
 }
 
@@ -392,8 +402,9 @@ __device__ __forceinline__ void staged_load_residual(const GemmParams& p, const 
 // Phase C: column sums: lanes -> warps (shared memory, fixed order) -> one partial per (image, tile); the last CTA to
 //          arrive for an (image, n_tile) adds the partials of all tiles in slot order: deterministic, no float atomics.
 // Kept compact on purpose (runtime loops, small unroll factors): these kernels execute every instruction once per
-// CTA, so code size is instruction-fetch time.
-__device__ __noinline__ void staged_epilogue(const GemmParams& p, const TileCoord& t, uint32_t taddr, __half* tile_s,
+// CTA, so code size is instruction-fetch time.  Inlined: the parameters must come from the constant bank and the
+// shared-memory pointers must keep their address space (an out-of-line version used generic LD.E / ST.E for both).
+__device__ __forceinline__ void staged_epilogue(const GemmParams& p, const TileCoord& t, uint32_t taddr, __half* tile_s,
                                              float* scratch, unsigned int* flag_s, const float* bias_row,
                                              const float* wg_s, int ew, int lane, int row, int out_row, bool valid,
                                              uint4 (&res)[4]) {
@@ -524,9 +535,9 @@ __device__ __noinline__ void staged_epilogue(const GemmParams& p, const TileCoor
             w = w2;
         }
     }
-    __threadfence();
-    epi_bar_sync();
+    epi_bar_sync();  // every thread's partial is written (CTA scope) ...
     if (tid_e == 0) {
+        __threadfence();  // ... and published at GPU scope by the thread that takes the tickets (cumulative fence)
         int w = 0;
         while (w < 8) {
             const int img = img_s[w];
@@ -569,8 +580,12 @@ __device__ __noinline__ void staged_epilogue(const GemmParams& p, const TileCoor
 
 template <bool kGeneric, bool kGeglu, bool kOutF32, bool kPartial, bool kTwoCta = false, bool kStaged = false>
 __global__ void __launch_bounds__(kGemmThreads, 1) umma_gemm_kernel(const __grid_constant__ GemmParams p) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // 1024-byte aligned by declaration (SWIZZLE_128B atoms): keeping the base a plain shared-memory symbol -- not an
+    // integer-rounded pointer -- lets the compiler emit LDS / STS for everything derived from it; rounding through
+    // uintptr_t turned every shared access of the loader and the epilogues into generic LD.E / ST.E
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw;
+    if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) __trap();
     // a CTA of a pair stages only its half of the B tile (block_n / 2 rows); the MMA reads both halves
     const int b_rows = kTwoCta ? (p.block_n >> 1) : p.block_n;
     const int b_stage = b_rows * (kBK * 2);
@@ -822,6 +837,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) umma_gemm_kernel(const __grid
                 continue;
             }
             const float2 lnc = ln_row_coeffs(p, out_row, valid);
+            float2 rowacc = make_float2(0.f, 0.f);
             auto process16 = [&](float (&acc)[16], int c) {  // c: column offset inside the tile
                 if (p.ln_parts != 0) {
 #pragma unroll
@@ -834,7 +850,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) umma_gemm_kernel(const __grid
                 if (p.res_smem) rptr = res_s + row * ldr + c;
                 else if (kGeneric && p.residual != nullptr)
                     rptr = p.residual + static_cast<size_t>(out_row) * p.n_store + ((ncol0 + c) >> (p.geglu ? 1 : 0));
-                epilogue_store16<kGeneric, kGeglu, kOutF32, kPartial>(p, acc, out_row, ncol0 + c, t.split, bptr, rptr);
+                epilogue_store16<kGeneric, kGeglu, kOutF32, kPartial>(p, acc, out_row, ncol0 + c, t.split, bptr, rptr, rowacc);
             };
             auto process32 = [&](const uint32_t (&v)[32], int c) {
                 if (kPartial && p.cluster) {
@@ -889,6 +905,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) umma_gemm_kernel(const __grid
                     }
                 }
             }
+            if (!kPartial && p.rs_out != nullptr && valid)  // one partial per (n_tile, column half): 2 * n_tiles parts
+                *reinterpret_cast<float2*>(p.rs_out + (static_cast<size_t>(t.n_tile * 2 + half) * p.M + out_row) * 2) = rowacc;
             tc_fence_before();
             if (kTwoCta) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[as]), 0));  // the leader's MMA warp waits
             else mbar_arrive(&tmem_empty[as]);
@@ -988,8 +1006,12 @@ __device__ __forceinline__ void ldr_bar_sync() { asm volatile("bar.sync 1, 256;"
 
 template <bool kFp32Direct>
 __global__ void __launch_bounds__(kGemmThreads, 1) halo_conv_kernel(const __grid_constant__ GemmParams p) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // 1024-byte aligned by declaration (SWIZZLE_128B atoms): keeping the base a plain shared-memory symbol -- not an
+    // integer-rounded pointer -- lets the compiler emit LDS / STS for everything derived from it; rounding through
+    // uintptr_t turned every shared access of the loader and the epilogues into generic LD.E / ST.E
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw;
+    if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) __trap();
     const int b_stage = p.block_n * (kBK * 2);
     uint8_t* patch = smem;                                  // [2][patch_bytes]
     uint8_t* smem_b = smem + 2 * p.patch_bytes;             // [stages][block_n * 128]
@@ -1166,20 +1188,21 @@ __global__ void __launch_bounds__(kGemmThreads, 1) halo_conv_kernel(const __grid
                 const int cpg = Cin / p.gn_groups;
                 const float inv_cnt = 1.0f / (static_cast<float>(cpg) * static_cast<float>(p.gn_hw));
                 ldr_bar_sync();  // previous tile's readers of the table are done
-                for (int g = ew; g < p.gn_groups; g += 8) {
+                // eight lanes per group, all groups of a round in flight at once (one L2 round trip for <= 32 groups)
+                for (int g = ltid >> 3; g < p.gn_groups; g += kEpiThreads >> 3) {
                     float s = 0.f, q = 0.f;
-                    for (int c = g * cpg + lane; c < (g + 1) * cpg; c += 32) {
+                    for (int c = g * cpg + (ltid & 7); c < (g + 1) * cpg; c += 8) {
                         const float2 v = (c < p.C0)
-                            ? *reinterpret_cast<const float2*>(p.gn_chan0 + (static_cast<size_t>(img) * p.C0 + c) * 2)
-                            : *reinterpret_cast<const float2*>(p.gn_chan1 + (static_cast<size_t>(img) * p.C1 + c - p.C0) * 2);
+                            ? __ldg(reinterpret_cast<const float2*>(p.gn_chan0 + (static_cast<size_t>(img) * p.C0 + c) * 2))
+                            : __ldg(reinterpret_cast<const float2*>(p.gn_chan1 + (static_cast<size_t>(img) * p.C1 + c - p.C0) * 2));
                         s += v.x, q += v.y;
                     }
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
+                    for (int o = 4; o > 0; o >>= 1) {
                         s += __shfl_xor_sync(0xffffffffu, s, o);
                         q += __shfl_xor_sync(0xffffffffu, q, o);
                     }
-                    if (lane == 0) {
+                    if ((ltid & 7) == 0) {
                         const float mean = s * inv_cnt;
                         stat_s[g] = make_float2(mean, rsqrtf(fmaxf(q * inv_cnt - mean * mean, 0.f) + p.gn_eps));
                     }
@@ -1361,10 +1384,10 @@ static int ilog2(int v) {
 }
 
 static bool staged_enabled() {
-    // B200SD_STAGED=0: residual-only GEMMs keep the register epilogue with the residual tile prefetched into shared
-    // memory (statistics outputs always take the staged epilogue)
+    // B200SD_STAGED=1: residual-only GEMMs also take the staged epilogue (default: the register epilogue with the
+    // residual tile prefetched into shared memory during the main loop; column statistics always need the staged one)
     const char* e = getenv("B200SD_STAGED");
-    return !(e && e[0] == '0');
+    return e && e[0] == '1';
 }
 
 static bool desc_base_offset_enabled() {
@@ -1597,8 +1620,13 @@ static int plan_gemm(const b200sd_gemm_args& a, GemmPlan& pl) {
         pl.acc_bufs = ((!pl.cluster && units > num_sms()) || pl.two_cta) ? 2 : 1;
         // staged epilogue: fp16 tile in shared memory, row-contiguous residual reads / stores, statistics outputs
         const bool eligible = regular && pl.splits == 1 && !pl.two_cta && !a.geglu && !a.out_f32 && a.n % 8 == 0;
-        pl.staged = (eligible && (want_stats || (a.residual != nullptr && staged_enabled()))) ? 1 : 0;
-        B200SD_REQUIRE(!want_stats || pl.staged, "b200sd_gemm: this shape cannot emit statistics (n=%d block_n=%d)", a.n, pl.block_n);
+        // column statistics need the staged epilogue; row statistics alone ride on the register epilogue (every thread
+        // owns a row there), which keeps the residual tile prefetched in shared memory during the main loop
+        pl.staged = (eligible && (a.cs_partial != nullptr || (a.residual != nullptr && staged_enabled()))) ? 1 : 0;
+        B200SD_REQUIRE(a.cs_partial == nullptr || pl.staged, "b200sd_gemm: this shape cannot emit column statistics (n=%d block_n=%d)", a.n,
+                       pl.block_n);
+        B200SD_REQUIRE(a.rs_out == nullptr || pl.staged || (regular && !a.geglu && !a.out_f32 && pl.splits == 1 && !pl.two_cta),
+                       "b200sd_gemm: this shape cannot emit row statistics (n=%d block_n=%d)", a.n, pl.block_n);
         if (pl.staged) pl.res_smem = 0;
         pl.stage_dedicated = (pl.staged && pl.acc_bufs == 2) ? 1 : 0;
         if (a.cs_partial != nullptr) {

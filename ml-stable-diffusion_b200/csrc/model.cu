@@ -93,6 +93,11 @@ public:
     __half* kv_all = nullptr;
     bool kv_ready = false;
     int attn_impl = 1;
+    // GroupNorm fusion (B200SD_FUSED=1 at create time): GroupNorm + SiLU inside the halo convolution's operand path with
+    // statistics from the producers' epilogues.  Default off, like the Python host: on a B200 at batch 2 the one-launch
+    // cluster GroupNorm in front of the 9-tap TMA convolution measured faster (profiles/README.md); LayerNorm is always
+    // folded into its consumer GEMM.
+    bool fuse_gn = false;
 
     ~UNet() {
         for (void* p : warm_allocs) cudaFree(p);
@@ -426,7 +431,6 @@ public:
 
     int ensure_scratch(size_t bytes) {
         if (bytes <= scratch_bytes) return 0;
-        B200SD_REQUIRE(!bump, "b200sd_unet: scratch would grow after the sizing pass");
         void* d;
         MODEL_TRY(dev_alloc(&d, bytes));
         scratch = static_cast<float*>(d);
@@ -437,6 +441,7 @@ public:
     // out = epilogue(A * W^T): the common part of linear() / conv3x3() of lib.py (statistics, weight tiling, scratch)
     int gemm(b200sd_gemm_args a, Mat& w, int taps, int n_img_stats, bool want_cs, float** chan_out, RowStats* rs, int m_rows) {
         int32_t pl[8];
+        want_cs = want_cs && fuse_gn;
         if (want_cs) {
             a.cs_partial = reinterpret_cast<float*>(16);
             if (b200sd_gemm_plan_ex(&a, pl) != 0) {  // this geometry cannot emit column statistics: consumer falls back
@@ -448,6 +453,7 @@ public:
         if (rs) a.rs_out = reinterpret_cast<float*>(16);
         MODEL_TRY(b200sd_gemm_plan_ex(&a, pl));
         const int bn = pl[0], n_tiles = pl[3], slots = pl[4];
+        const int rs_parts = pl[5] ? n_tiles : 2 * n_tiles;  // register epilogue: one partial per column half of a tile
         if (want_cs) {
             void* c;
             MODEL_TRY(act_alloc(&c, static_cast<size_t>(n_img_stats) * a.n * 8));
@@ -459,9 +465,9 @@ public:
         }
         if (rs) {
             void* r;
-            MODEL_TRY(act_alloc(&r, static_cast<size_t>(n_tiles) * m_rows * 8));
+            MODEL_TRY(act_alloc(&r, static_cast<size_t>(rs_parts) * m_rows * 8));
             a.rs_out = static_cast<float*>(r);
-            rs->rows = a.rs_out, rs->parts = n_tiles;
+            rs->rows = a.rs_out, rs->parts = rs_parts;
         }
         void* wt;
         MODEL_TRY(tiled(w, a.c0, a.c1, taps, bn, a.halo != 0, &wt));
@@ -538,6 +544,12 @@ public:
                 const float* bias, int bias_rows, int bias_stride, const __half* residual, bool want_cs, bool out_f32, void* out_override,
                 Act* out) {
         const float *gamma = vecs.at(gkey), *beta = vecs.at(bkey);
+        if (!fuse_gn) {
+            Act hn;
+            MODEL_TRY(group_norm(x, x1, gamma, beta, eps, silu, &hn));
+            return conv(hn, nullptr, w, cout, bias, bias_rows, bias_stride, residual, false, 9, 1, false, nullptr, false, nullptr, out_f32,
+                        out_override, out);
+        }
         if (x.chan && (!x1 || x1->chan)) {
             GnSpec g{x.chan, x1 ? x1->chan : nullptr, gamma, beta, cfg.norm_num_groups, eps, silu};
             return conv(x, x1, w, cout, bias, bias_rows, bias_stride, residual, true, 9, 1, false, &g, want_cs, nullptr, out_f32, out_override,
@@ -748,8 +760,18 @@ public:
             }
             if (i != nb - 1) {
                 const std::string p = "up_blocks." + std::to_string(i) + ".upsamplers.0.conv";
-                MODEL_TRY(conv(x, nullptr, *mats.at(p), x.c, vec_or_null(p + ".b"), 0, 0, nullptr, true, 9, 1, true, nullptr, true, nullptr, false,
-                               nullptr, &y));
+                if (fuse_gn) {
+                    MODEL_TRY(conv(x, nullptr, *mats.at(p), x.c, vec_or_null(p + ".b"), 0, 0, nullptr, true, 9, 1, true, nullptr, true, nullptr,
+                                   false, nullptr, &y));
+                } else {  // nearest x2 copy + 9-tap convolution
+                    Act up = x;
+                    void* u;
+                    MODEL_TRY(act_alloc(&u, static_cast<size_t>(x.rows()) * 4 * x.c * 2));
+                    MODEL_TRY(b200sd_upsample2x(x.p, u, x.n, x.h, x.w, x.c, st));
+                    up.p = static_cast<__half*>(u), up.h = 2 * x.h, up.w = 2 * x.w, up.chan = nullptr;
+                    MODEL_TRY(conv(up, nullptr, *mats.at(p), x.c, vec_or_null(p + ".b"), 0, 0, nullptr, false, 9, 1, false, nullptr, false, nullptr,
+                                   false, nullptr, &y));
+                }
                 x = y;
             }
         }
@@ -802,6 +824,10 @@ extern "C" int b200sd_unet_create(const b200sd_unet_config* cfg, const b200sd_we
     u.in_pad = std::max(8, (cfg->in_channels + 7) / 8 * 8);
     u.xl = cfg->addition_embed_text_time != 0;
     u.st = static_cast<cudaStream_t>(stream);
+    {
+        const char* e = getenv("B200SD_FUSED");
+        u.fuse_gn = e && e[0] == '1';
+    }
     for (int i = 0; i < n_weights; ++i) {
         const b200sd_weight& w = weights[i];
         B200SD_REQUIRE(w.name && w.data && w.ndim >= 1 && w.ndim <= 4 && (w.dtype == 0 || w.dtype == 1), "b200sd_unet_create: bad weight entry %d", i);

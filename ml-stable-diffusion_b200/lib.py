@@ -340,9 +340,10 @@ def _fused_args(args, x_dev, *, n_img, cout, gn=None, stats=None, cs_hw=0, ln=No
             stats["chan"] = chan
             keep.append(chan)
         if rowstats is not None:
-            rows = torch.empty(n_tiles, m, 2, dtype=torch.float32, device=x_dev)
+            parts = n_tiles if pl[5] else 2 * n_tiles  # register epilogue: one partial per column half of a tile
+            rows = torch.empty(parts, m, 2, dtype=torch.float32, device=x_dev)
             args.rs_out = rows.data_ptr()
-            rowstats["rows"], rowstats["parts"] = rows, n_tiles
+            rowstats["rows"], rowstats["parts"] = rows, parts
             keep.append(rows)
     return keep
 

@@ -98,15 +98,19 @@ class UNetEngine:
         self.in_pad = max(8, (self.in_ch + 7) // 8 * 8)
         self.xl = cfg.get("addition_embed_type") == "text_time"
         self.support_controlnet = bool(cfg.get("support_controlnet", False))
-        # fused normalisation (round 2): GroupNorm + SiLU in the halo convolution's operand path, LayerNorm folded
-        # into the consumer GEMM, statistics from the producers' epilogues.  B200SD_FUSED=0 keeps the round-1 graph
-        # (standalone GroupNorm / LayerNorm launches) for A/B measurements.
-        self.fused = os.environ.get("B200SD_FUSED", "1") != "0"
-        # how a GroupNorm whose statistics came from the producer is applied: "halo" = inside the halo convolution's
-        # operand path (no launch); "apply" = one elementwise launch (b200sd_group_norm_apply) in front of the 9-tap TMA
-        # convolution; B200SD_FUSED=1 halo everywhere, 2 apply everywhere, 3 halo on maps of >= B200SD_HALO_MIN_HW pixels
-        fm = os.environ.get("B200SD_FUSED", "1")
-        self.halo_min_hw = {"1": 0, "2": 1 << 30, "3": int(os.environ.get("B200SD_HALO_MIN_HW", "1024"))}.get(fm, 0)
+        # Normalisation fusion level (B200SD_FUSED; measurements in profiles/README.md):
+        #   "ln" (default)  LayerNorm folded into its consumer GEMM, row statistics from the producer's epilogue;
+        #                   GroupNorm stays the one-launch cluster kernel in front of the 9-tap TMA convolution -- on
+        #                   a B200 at batch 2 every fused-GroupNorm variant below measured SLOWER than this
+        #   "1"  GroupNorm + SiLU applied in the halo convolution's operand path (no GroupNorm launch at all),
+        #        statistics from the producers' staged epilogues
+        #   "2"  statistics from the producers, one elementwise GroupNorm-apply launch + 9-tap convolution
+        #   "3"  "1" on maps of >= B200SD_HALO_MIN_HW pixels, "2" below
+        #   "0"  round-1 graph (standalone GroupNorm and LayerNorm launches)
+        fm = os.environ.get("B200SD_FUSED", "ln")
+        self.fused = fm != "0"
+        self.fuse_gn = fm in ("1", "2", "3")
+        self.halo_min_hw = {"1": 0, "2": 1 << 30, "3": int(os.environ.get("B200SD_HALO_MIN_HW", "1024"))}.get(fm, 1 << 30)
         for c, h in zip(boc, self.heads):
             if c % h or c // h != 64:
                 raise L.B200SDError(f"b200sd attention kernel needs head dim 64 (got {c}/{h})")
@@ -277,6 +281,9 @@ class UNetEngine:
         return x.shape[1] * x.shape[2] >= self.halo_min_hw
 
     def _gn_conv(self, x, xs, x1, x1s, gamma, beta, eps, silu, wgt, bias, residual=None, stats=None, **kw):
+        if not self.fuse_gn:  # standalone GroupNorm launch + 9-tap convolution, no statistics side outputs
+            hh = L.group_norm(x, gamma, beta, self.groups, eps, silu=silu, x1=x1)
+            return L.conv3x3(hh, wgt, bias, residual, **kw)
         have = xs is not None and (x1 is None or x1s is not None)
         halo = self._use_halo(x)
         if have and halo:
@@ -293,15 +300,15 @@ class UNetEngine:
         n, h, wd, _ = x.shape
         off, co = self.temb_slices[p]
         st1, st2 = {}, {}
-        hh = self._gn_conv(x, xs, x1, x1s, r["n1g"], r["n1b"], self.eps, True, r["c1"], temb_all[:, off:], stats=st1,
-                           bias_rows=h * wd, bias_stride=self.temb_total)
+        hh = self._gn_conv(x, xs, x1, x1s, r["n1g"], r["n1b"], self.eps, True, r["c1"], temb_all[:, off:],
+                           stats=st1 if self.fuse_gn else None, bias_rows=h * wd, bias_stride=self.temb_total)
         if "sc" in r:
             res = L.linear(x.reshape(n * h * wd, -1), r["sc"], r["scb"],
                            x1=None if x1 is None else x1.reshape(n * h * wd, -1), static_w=True)
         else:
             res = x
         out = self._gn_conv(hh, st1.get("chan"), None, None, r["n2g"], r["n2b"], self.eps, True, r["c2"], r["c2b"], res,
-                            stats=st2)
+                            stats=st2 if self.fuse_gn else None)
         return out, st2.get("chan")
 
     def _transformer_f(self, p, x, xs, kv_all, batch, heads, s_ctx):
@@ -310,11 +317,11 @@ class UNetEngine:
         m, s = n * h * wd, h * wd
         impl = _IMPL_CODE[ATTENTION_IMPLEMENTATION_IN_EFFECT]
         rs = {}
-        if xs is not None and self._use_halo(x):
+        if self.fuse_gn and xs is not None and self._use_halo(x):
             gn = dict(chan0=xs, chan1=None, gamma=t["ng"], beta=t["nb"], groups=32, eps=1e-6, silu=False)
             tok = L.conv3x3(x, t["pi"], t["pib"], halo=True, taps=1, gn=gn, rowstats=rs).reshape(m, c)
         else:
-            hn = (L.group_norm_apply(x, xs, t["ng"], t["nb"], 32, 1e-6) if xs is not None
+            hn = (L.group_norm_apply(x, xs, t["ng"], t["nb"], 32, 1e-6) if (self.fuse_gn and xs is not None)
                   else L.group_norm(x, t["ng"], t["nb"], 32, 1e-6, silu=False))
             tok = L.linear(hn.reshape(m, c), t["pi"], t["pib"], static_w=True, rowstats=rs)
 
@@ -336,13 +343,13 @@ class UNetEngine:
             rs = {}
             tok = L.linear(g, blk["f2"], blk["f2b"], tok, static_w=True, rowstats=rs if bi + 1 < nblk else None)
         st = {}
-        ok = s % 128 == 0 or (s >= 16 and 128 % s == 0)   # geometries whose tiles map onto whole images
+        ok = self.fuse_gn and (s % 128 == 0 or (s >= 16 and 128 % s == 0))   # geometries whose tiles map onto whole images
         out = L.linear(tok, t["po"], t["pob"], x.reshape(m, c), static_w=True, stats=st if ok else None, cs_hw=s)
         return out.reshape(n, h, wd, c), st.get("chan")
 
     def _forward_fused(self, sample, temb_all, kv_all, batch, s_ctx, additional_residuals, out=None):
         st = {}
-        x = L.conv3x3(sample, self.w["conv_in"]["w"], self.w["conv_in"]["b"], stats=st)
+        x = L.conv3x3(sample, self.w["conv_in"]["w"], self.w["conv_in"]["b"], stats=st if self.fuse_gn else None)
         xs = st.get("chan")
         skips = [(x, xs)]
         for i, typ in enumerate(self.down_types):
@@ -354,7 +361,7 @@ class UNetEngine:
             if i != self.nb - 1:
                 d = self.w[f"down_blocks.{i}.downsamplers.0.conv"]
                 st = {}
-                x = L.conv3x3(x, d["w"], d["b"], stride=2, stats=st)
+                x = L.conv3x3(x, d["w"], d["b"], stride=2, stats=st if self.fuse_gn else None)
                 xs = st.get("chan")
                 skips.append((x, xs))
         if additional_residuals is not None:  # the sums have no producer-side statistics: standalone GroupNorm there
@@ -374,10 +381,10 @@ class UNetEngine:
             if i != self.nb - 1:
                 u = self.w[f"up_blocks.{i}.upsamplers.0.conv"]
                 st = {}
-                if 4 * x.shape[1] * x.shape[2] >= self.halo_min_hw:
+                if self.fuse_gn and 4 * x.shape[1] * x.shape[2] >= self.halo_min_hw:
                     x = L.conv3x3(x, u["w"], u["b"], halo=True, upsample=True, stats=st)
                 else:
-                    x = L.conv3x3(L.upsample2x(x), u["w"], u["b"], stats=st)
+                    x = L.conv3x3(L.upsample2x(x), u["w"], u["b"], stats=st if self.fuse_gn else None)
                 xs = st.get("chan")
         o = self.w["out"]
         return self._gn_conv(x, xs, None, None, o["g"], o["b"], self.eps, True, o["w"], o["cb"], out_dtype=torch.float32,

@@ -32,7 +32,9 @@ def test_capi_unet_tiny_matches_python_engine_and_oracle(cuda_lib):
     assert torch.equal(out, again)
     py = UNetModel(cfg, sd, batch=2, height=16, width=16, use_cuda_graph=False)(
         sample=x.half().numpy(), timestep=t.half().numpy(), encoder_hidden_states=c.half().numpy())["noise_pred"]
-    assert np.array_equal(out.cpu().numpy(), py)            # same kernels, same launch order: bit-identical
+    # same kernels and launch order; the host-side weight folds (LayerNorm into the consumer GEMM) sum in a different
+    # order in C++ and torch, so agreement is to fp32 rounding of those folds, not bitwise
+    assert np.abs(out.cpu().numpy() - py).max() <= 2e-3
     with torch.no_grad():
         ref = R.unet_forward(sd, cfg, x, t, c).numpy()
     assert np.abs(out.cpu().numpy() - ref).max() <= 1e-2
