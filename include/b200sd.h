@@ -189,6 +189,16 @@ int b200sd_attention(const void* q, const void* k, const void* v, void* out, con
                      int32_t batch, int32_t heads, int32_t sq, int32_t sk, int32_t d,
                      int32_t ldq, int32_t ldk, int32_t ldv, int32_t ldo, float scale, int32_t impl,
                      void* stream);
+/* The same with a caller-provided device workspace of b200sd_attention_workspace_bytes() bytes, which lets the launch
+ * cut the (query tile x K/V tile) work into equal per-CTA ranges ("stream-K") when whole query tiles would fill the GPU
+ * badly (S = 4096: 320 tiles on 296 CTA slots).  Pieces of a split tile meet in the workspace and are merged in a fixed
+ * order, so results are reproducible.  The workspace must be zero-filled once before its first use (the kernel leaves its
+ * counters at zero) and must not be shared with a concurrently running attention launch. */
+size_t b200sd_attention_workspace_bytes(void);
+int b200sd_attention_ws(const void* q, const void* k, const void* v, void* out, const float* mask,
+                        int32_t batch, int32_t heads, int32_t sq, int32_t sk, int32_t d,
+                        int32_t ldq, int32_t ldk, int32_t ldv, int32_t ldo, float scale, int32_t impl,
+                        void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- layout / elementwise ----------------------------------------------------------------- */
 /* NCHW (fp16 or fp32) -> NHWC fp16 with channel padding to c_pad (zeros) */

@@ -90,6 +90,8 @@ public:
     float* scratch = nullptr;  // split-K / statistics partials
     size_t scratch_bytes = 0;
     unsigned int* tickets = nullptr;
+    void* attn_ws = nullptr;                                        // b200sd_attention_ws workspace (zeroed once)
+    size_t attn_ws_bytes = 0;
     __half* kv_all = nullptr;
     bool kv_ready = false;
     int attn_impl = 1;
@@ -585,7 +587,8 @@ public:
     int attention(const __half* q, int ldq, const __half* k, const __half* v, int ldkv, int heads, int sq, int sk, __half** out, int c) {
         void* o;
         MODEL_TRY(act_alloc(&o, static_cast<size_t>(B) * sq * c * 2));
-        MODEL_TRY(b200sd_attention(q, k, v, o, nullptr, B, heads, sq, sk, 64, ldq, ldkv, ldkv, c, 0.125f, attn_impl, st));
+        MODEL_TRY(b200sd_attention_ws(q, k, v, o, nullptr, B, heads, sq, sk, 64, ldq, ldkv, ldkv, c, 0.125f, attn_impl, attn_ws,
+                                      attn_ws_bytes, st));
         *out = static_cast<__half*>(o);
         return 0;
     }
@@ -848,6 +851,9 @@ extern "C" int b200sd_unet_create(const b200sd_unet_config* cfg, const b200sd_we
     if (int rc = u.dev_alloc(&tk, (1 << 16) * sizeof(unsigned int))) return rc;
     B200SD_CHECK_CUDA(cudaMemset(tk, 0, (1 << 16) * sizeof(unsigned int)));
     u.tickets = static_cast<unsigned int*>(tk);
+    u.attn_ws_bytes = b200sd_attention_workspace_bytes();
+    if (int rc = u.dev_alloc(&u.attn_ws, u.attn_ws_bytes)) return rc;
+    B200SD_CHECK_CUDA(cudaMemset(u.attn_ws, 0, u.attn_ws_bytes));
     if (u.mats.count("kv")) {
         void* kv;
         if (int rc = u.dev_alloc(&kv, static_cast<size_t>(u.B) * u.S * u.kv_total * 2)) return rc;

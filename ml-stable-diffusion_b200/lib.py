@@ -86,6 +86,10 @@ _SIGNATURES = {
     "b200sd_attention": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                    C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                    C.c_int32, C.c_float, C.c_int32, C.c_void_p]),
+    "b200sd_attention_workspace_bytes": (C.c_size_t, []),
+    "b200sd_attention_ws": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                      C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                      C.c_int32, C.c_float, C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]),
     "b200sd_nchw_to_nhwc": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                       C.c_int32, C.c_int32, C.c_void_p]),
     "b200sd_nhwc_to_nchw_f32": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
@@ -485,11 +489,26 @@ def attention(q, k, v, batch, heads, sq, sk, d=64, mask=None, impl=0, out=None, 
     if out is None:
         out = torch.empty(batch * sq, heads * d, dtype=torch.float16, device=q.device)
     scale = float(d) ** -0.5 if scale is None else float(scale)
-    _check(load().b200sd_attention(_ptr(q), _ptr(k), _ptr(v), _ptr(out), _ptr(mask), batch, heads, sq, sk, d,
-                                   q.stride(0), k.stride(0), v.stride(0), out.stride(0), scale,
-                                   int(impl) | (0x100 if causal else 0),
-                                   _stream()), "b200sd_attention")
+    ws = _attention_workspace(q.device)
+    _check(load().b200sd_attention_ws(_ptr(q), _ptr(k), _ptr(v), _ptr(out), _ptr(mask), batch, heads, sq, sk, d,
+                                      q.stride(0), k.stride(0), v.stride(0), out.stride(0), scale,
+                                      int(impl) | (0x100 if causal else 0), _ptr(ws), ws.numel(),
+                                      _stream()), "b200sd_attention_ws")
     return out
+
+
+_attn_ws = {}
+
+
+def _attention_workspace(device):
+    """Zero-filled once per device: the stream-K pieces of split query tiles meet here; its counters return to zero at
+    the end of every launch.  Launches on one stream are ordered, which is the only way this package launches."""
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    ws = _attn_ws.get(key)
+    if ws is None:
+        ws = torch.zeros(int(load().b200sd_attention_workspace_bytes()), dtype=torch.uint8, device=device)
+        _attn_ws[key] = ws
+    return ws
 
 
 def nchw_to_nhwc(x, c_pad=None, out=None):

@@ -479,6 +479,11 @@ class B200StableDiffusionPipeline:
         self._latents.copy_(torch.as_tensor(latents), non_blocking=True)
         if controlnet_cond:
             controlnet_cond = [torch.as_tensor(c).to(self.device, torch.float16) for c in controlnet_cond]
+        elif self.unet._res:
+            # a UNet built with additional_residual inputs but called without conditions: the static residual buffers
+            # would still hold the previous ControlNet call's last step (the reference cannot run this combination)
+            for buf in self.unet._res:
+                buf.zero_()
         if self.loop_graph and callback is None and record is None:
             u = self.unet
             u._ctx.copy_(self._ctx)

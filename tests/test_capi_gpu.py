@@ -34,7 +34,7 @@ def test_capi_unet_tiny_matches_python_engine_and_oracle(cuda_lib):
         sample=x.half().numpy(), timestep=t.half().numpy(), encoder_hidden_states=c.half().numpy())["noise_pred"]
     # same kernels and launch order; the host-side weight folds (LayerNorm into the consumer GEMM) sum in a different
     # order in C++ and torch, so agreement is to fp32 rounding of those folds, not bitwise
-    assert np.abs(out.cpu().numpy() - py).max() <= 2e-3
+    assert np.abs(out.cpu().numpy() - py).max() <= 5e-3
     with torch.no_grad():
         ref = R.unet_forward(sd, cfg, x, t, c).numpy()
     assert np.abs(out.cpu().numpy() - ref).max() <= 1e-2

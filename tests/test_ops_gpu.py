@@ -350,3 +350,32 @@ def test_attention_large_scores_take_the_rescale_path(cuda_lib):
     ref = torch.softmax(qf @ kf.transpose(-1, -2) * d ** -0.5, dim=-1) @ vf
     ref = ref.permute(0, 2, 1, 3).reshape(b * s, h * d)
     _close(out, ref, 3e-3, 3e-3, "attention with growing score maxima")
+
+
+@pytest.mark.parametrize("batch,heads,sq,sk,masked", [(2, 5, 4096, 4096, False), (1, 5, 4096, 4096, False),
+                                                      (2, 10, 2304, 2304, False), (2, 5, 4000, 3970, False),
+                                                      (1, 5, 4096, 2048, True)])
+def test_attention_stream_k(cuda_lib, monkeypatch, batch, heads, sq, sk, masked):
+    """Shapes whose query tiles fill the 296 CTA slots badly are cut into equal (query tile x K/V tile) ranges per CTA
+    (attention.cu `attention_slots`); the pieces of a split tile are merged in a fixed order, so the result matches the
+    one-CTA-per-tile schedule to rounding, is bit-reproducible, and leaves the workspace counters at zero."""
+    c = heads * 64
+    q, k, v = _rand(batch * sq, c, seed=1), _rand(batch * sk, c, seed=2), _rand(batch * sk, c, seed=3)
+    # growing keys: pieces of one tile end with very different reference maxima, so the merge has to rescale
+    k = (k.float() * torch.linspace(0.5, 6.0, sk, device="cuda").repeat(batch)[:, None]).half()
+    mask = None
+    if masked:
+        mask = torch.zeros(batch, sk, device="cuda")
+        mask[:, ::3] = -1e4
+    ref = _attn_ref(q, k, v, batch, heads, sq, sk, mask)
+    out = cuda_lib.attention(q, k, v, batch, heads, sq, sk, mask=mask)
+    _close(out, ref, 3e-3, 3e-3, f"stream-K attention {batch}x{heads}x{sq}x{sk}")
+    for _ in range(3):
+        assert torch.equal(out, cuda_lib.attention(q, k, v, batch, heads, sq, sk, mask=mask))
+    counters = cuda_lib._attention_workspace(q.device)[:65536]
+    assert int(counters.max()) == 0
+    monkeypatch.setenv("B200SD_ATTN_STREAMK", "0")
+    whole = cuda_lib.attention(q, k, v, batch, heads, sq, sk, mask=mask)
+    monkeypatch.delenv("B200SD_ATTN_STREAMK")
+    _close(whole, ref, 3e-3, 3e-3, "one CTA per query tile")
+    assert (out.float() - whole.float()).abs().max().item() <= 2e-3

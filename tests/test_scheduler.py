@@ -210,3 +210,47 @@ def test_dpm_final_sigmas_zero_lands_on_the_denoised_estimate(n):
 def test_pipeline_uses_the_diffusers_ending_for_dpm():
     from b200sd import scheduler as S
     assert S.make_scheduler("DPMSolverMultistep", 20, final_sigmas_type="zero").final_sigmas_type == "zero"
+
+
+@pytest.mark.parametrize("n", [2, 3, 4, 5])
+def test_pndm_first_steps_equal_the_swift_formulas_evaluated_by_hand(n):
+    """Pin without the oracle: the first model evaluations of PLMS written out from Scheduler.swift:218-343.
+    Step 0 is a plain formula-(9) update from t to t - d with e0.  The schedule then repeats its second timestep: step 1
+    restarts from the saved first sample with (e1 + e0) / 2 over [t, t - d] and does not store e1.  Steps 2, 3, 4 use the
+    2-, 3- and 4-term Adams-Bashforth weights over the stored outputs [e0, e2, e3, e4].  Guidance 1: eps = cond."""
+    d = 1000 // n
+    fwd = [int(round(i * float(d))) + 1 for i in range(n)]            # Scheduler.swift:188-191 (steps offset 1)
+    ts = (fwd[:-1] + [fwd[-2]] + [fwd[-1]])[::-1] if n > 1 else fwd   # :197-201
+    s = S.PNDMScheduler(n)
+    assert s.timesteps == ts
+    betas = np.linspace(0.00085 ** 0.5, 0.012 ** 0.5, 1000, dtype=np.float64) ** 2
+    abar = np.cumprod(1.0 - betas)
+    s.abar = abar
+
+    def prev_sample(x, t, tp, e):                                      # formula (9), :305-343
+        a_t, a_p = abar[t], abar[max(0, tp)]
+        coeff = np.sqrt(a_p / a_t)
+        denom = a_t * np.sqrt(1 - a_p) + np.sqrt(a_t * (1 - a_t) * a_p)
+        return coeff * x - (a_p - a_t) / denom * e
+
+    rng = np.random.RandomState(n)
+    x0 = rng.randn(3, 5)
+    es = [rng.randn(3, 5) for _ in range(n + 1)]
+    k = iter(range(n + 1))
+    xs, _ = _run_plan(s, lambda x, t: (np.zeros_like(x), es[next(k)]), x0, guidance=1.0)
+    t0 = ts[0]
+    x1 = prev_sample(x0, t0, t0 - d, es[0])                            # counter 0
+    assert np.allclose(xs[0], x1, rtol=1e-12, atol=1e-12)
+    # counter 1: timestep ts[1] = t0 - d arrives; prevStep = ts[1], timeStep = ts[1] + d = t0, sample = the saved x0
+    x2 = prev_sample(x0, t0, ts[1], 0.5 * es[1] + 0.5 * es[0])
+    assert ts[1] == t0 - d and np.allclose(xs[1], x2, rtol=1e-12, atol=1e-12)
+    if n >= 2:
+        # counter 2: ets = [e0, e2] (the counter-1 output is not stored): (3 e2 - e0) / 2 from ts[2] to ts[2] - d
+        x3 = prev_sample(x2, ts[2], ts[2] - d, 1.5 * es[2] - 0.5 * es[0])
+        assert np.allclose(xs[2], x3, rtol=1e-12, atol=1e-12)
+    if n >= 3:
+        x4 = prev_sample(x3, ts[3], ts[3] - d, (23 * es[3] - 16 * es[2] + 5 * es[0]) / 12.0)
+        assert np.allclose(xs[3], x4, rtol=1e-12, atol=1e-12)
+    if n >= 4:
+        x5 = prev_sample(x4, ts[4], ts[4] - d, (55 * es[4] - 59 * es[3] + 37 * es[2] - 9 * es[0]) / 24.0)
+        assert np.allclose(xs[4], x5, rtol=1e-12, atol=1e-12)

@@ -317,6 +317,11 @@ def test_pipeline_tiny_with_controlnet_vs_oracle(cuda_lib):
     # the public call accepts the reference's argument and rejects it without modules
     out = pipe("a cat", height=64, width=64, num_inference_steps=2, controlnet_cond=[cond], output_type="np")
     assert out.images.shape == (1, 64, 64, 3)
+    # without conditions the static residual buffers are cleared: two such calls agree bit for bit even though a
+    # ControlNet call ran in between (its last-step residuals must not leak into the next image)
+    first = pipe.denoise(emb_np, lat0.astype(np.float32), steps, g).clone()
+    pipe.denoise(emb_np, lat0.astype(np.float32), steps, g, controlnet_cond=cc)
+    assert torch.equal(first, pipe.denoise(emb_np, lat0.astype(np.float32), steps, g))
     plain = B200StableDiffusionPipeline.from_random_init("tiny", images_per_call=1, height=64, width=64, seed=21)
     with pytest.raises(ValueError, match="no controlnet modules"):
         plain("a cat", height=64, width=64, num_inference_steps=1, controlnet_cond=[cond])
