@@ -189,16 +189,17 @@ class LoopBench:
         self.cond = cond
         self.graphs = {}
 
-    def body(self, k_steps):
+    def body(self, k_steps, first=0):
         L, pipe = self.L, self.pipe
         u, n = pipe.unet, pipe.images_per_call
-        for i in range(k_steps):
+        table = getattr(self, "_table", None)
+        for i in range(first, first + k_steps):
             j = i % N_STEPS_IMG
             if j == 0:
                 pipe._latents.copy_(self.lat0)
                 pipe._hist.zero_()
                 u.prepare_prompt()
-                table = u.time_table(self.ts_rows)
+                table = self._table = u.time_table(self.ts_rows)
                 L.nchw_to_nhwc(pipe._latents, c_pad=u.engine.in_pad, out=u._x_nhwc[:n])
                 L.nchw_to_nhwc(pipe._latents, c_pad=u.engine.in_pad, out=u._x_nhwc[n:])
                 if self.cond is not None:
@@ -210,6 +211,21 @@ class LoopBench:
             k.noise_pred_nhwc = 1
             k.n_hist, k.push_eps_slot, k.push_x0_slot, k.push_x_slot = 0, -1, -1, -1
             L.cfg_scheduler_step(u._out_nhwc, pipe._latents, k, unet_in=u._x_nhwc)
+
+    def profile_one_step(self):
+        """For ``ncu --profile-from-start off``: warm up eagerly, then run exactly ONE mid-image iteration (the launch
+        sequence every timed step replays; no per-prompt prologue) between cudaProfilerStart / Stop."""
+        self.ts_rows = self.pipe._ts_rows(self.plan)
+        if self.cond is not None:
+            self.pipe.set_control_conditions(self.cond)
+        self.body(2)
+        torch.cuda.synchronize()
+        n0 = self.L.launch_count()
+        torch.cuda.profiler.start()
+        self.body(1, first=2)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return self.L.launch_count() - n0
 
     def capture(self, k_steps, classes=0xF):
         key = (k_steps, classes)
@@ -358,6 +374,9 @@ def run_gpu_arm(args, rank, local_rank, world):
 
     # ---- value: K iterations of the pipeline's device loop (UNet forward bs=2 + fused CFG/DDIM step), one graph ----
     loop = LoopBench(pipe, lat0)
+    if args.profile_step:
+        print(json.dumps({"profile_step": True, "launches": loop.profile_one_step()}), flush=True)
+        return
     graph = loop.capture(args.steps)
     launches_per_step = loop.launches_per_image / N_STEPS_IMG
     for _ in range(max(1, (max(3, args.warmup) + args.steps - 1) // args.steps)):  # >= W warm-up steps
@@ -520,6 +539,8 @@ def main():
     ap.add_argument("--no-batched", action="store_true", help="skip the 8-prompts-per-GPU images/s measurement")
     ap.add_argument("--quick", action="store_true", help="device-resident iter/s only (tuning runs; not a bench line)")
     ap.add_argument("--no-extra", action="store_true", help="skip the SDXL-768 / ControlNet configs (N = 1 only)")
+    ap.add_argument("--profile-step", action="store_true",
+                    help="run ONE eager denoising iteration between cudaProfilerStart/Stop (for ncu --profile-from-start off)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
