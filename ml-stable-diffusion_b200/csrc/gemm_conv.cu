@@ -71,6 +71,7 @@ struct __align__(64) GemmParams {
     int inv_wp;                // ceil(2^20 / Wp): i / Wp == (i * inv_wp) >> 20 for the patch indices used here
     int win, tw, th, tiles_x;  // mode 2 windowed tiling (wide images): tiles of th rows x tw columns, pitch Wp = tw + halo
     int desc_bo;            // 1: row-shifted A descriptors carry (address >> 7) & 7 in the matrix-base-offset field
+    int tma_patch, patch_tx;  // plain convolution: the producer warp loads each patch with ONE 4-D TMA box of patch_tx bytes
     const __half* a0;       // raw NHWC sources (loader warps read them with plain loads)
     const __half* a1;
     int C1;
@@ -1004,8 +1005,13 @@ __device__ __forceinline__ void dbg_mark(const GemmParams& p, int slot) {
 
 __device__ __forceinline__ void ldr_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-template <bool kFp32Direct>
+// kKind 0: loader warps + staged epilogue (GroupNorm / upsample on the patch, column statistics);  1: loader warps + tiny
+// fp32 epilogue (conv_out);  2: plain convolution -- the producer warp fetches each patch with one TMA box (hardware zero
+// fill for the padding ring and the pad column) and the eight epilogue warps use the register epilogue of the GEMM kernel.
+template <int kKind>
 __global__ void __launch_bounds__(kGemmThreads, 1) halo_conv_kernel(const __grid_constant__ GemmParams p) {
+    constexpr bool kFp32Direct = kKind == 1;
+    constexpr bool kTmaPatch = kKind == 2;
     // 1024-byte aligned by declaration (SWIZZLE_128B atoms): keeping the base a plain shared-memory symbol -- not an
     // integer-rounded pointer -- lets the compiler emit LDS / STS for everything derived from it; rounding through
     // uintptr_t turned every shared access of the loader and the epilogues into generic LD.E / ST.E
@@ -1033,12 +1039,16 @@ __global__ void __launch_bounds__(kGemmThreads, 1) halo_conv_kernel(const __grid
     const int lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&p.tmB);
+        if (kTmaPatch) {
+            prefetch_tmap(&p.tmA0);
+            prefetch_tmap(&p.tmA1);
+        }
         for (int s = 0; s < p.stages; ++s) {
             mbar_init(&full_b[s], 1);
             mbar_init(&empty_b[s], 1);
         }
         for (int s = 0; s < 2; ++s) {
-            mbar_init(&full_a[s], kEpiThreads);
+            mbar_init(&full_a[s], kTmaPatch ? 1 : kEpiThreads);
             mbar_init(&empty_a[s], 1);
             mbar_init(&tmem_full[s], 1);
             mbar_init(&tmem_empty[s], kEpiThreads);
@@ -1048,6 +1058,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) halo_conv_kernel(const __grid
     if (warp == 1) {
         tmem_alloc(tmem_ptr, static_cast<uint32_t>(p.tmem_cols));
         tmem_relinquish();
+    }
+    if (threadIdx.x >= 64 && threadIdx.x < 80) {  // "pixel -1" of both patches: the zero pad column that precedes the patch
+        const int which = (threadIdx.x - 64) >> 3;
+        *reinterpret_cast<uint4*>(patch + which * p.patch_bytes + 7 * 128 + (threadIdx.x & 7) * 16) = make_uint4(0, 0, 0, 0);
+        fence_proxy_async_smem();
     }
     tc_fence_before();
     __syncthreads();
@@ -1064,15 +1079,38 @@ __global__ void __launch_bounds__(kGemmThreads, 1) halo_conv_kernel(const __grid
         // ------------------------------- weight producer (TMA; constant data: no grid dependency) -------------------
         if (lane == 0) {
             int it = 0;
+            // kTmaPatch: this thread also fetches the activation patches, one chunk ahead of the weight tiles that use
+            // them (two patch buffers): the next patch is requested as soon as its buffer is free, checked without
+            // blocking between weight tiles so the weight ring never drains behind a patch wait
+            int ci = 0, pai = 0, pwork = work0, pj = 0;
+            auto issue_patch = [&](bool blocking) -> bool {
+                const int pa = pai & 1;
+                const uint32_t ph = ((pai >> 1) & 1) ^ 1;
+                if (blocking) mbar_wait(&empty_a[pa], ph);
+                else if (!mbar_try_wait(&empty_a[pa], ph)) return false;
+                const TileCoord pt = decode_work(p, pwork);
+                const bool src1 = pj >= p.kc0;
+                mbar_expect_tx(&full_a[pa], static_cast<uint32_t>(p.patch_tx));
+                tma_load_4d(patch + pa * p.patch_bytes + 1024, src1 ? &p.tmA1 : &p.tmA0, &full_a[pa],
+                            (src1 ? pj - p.kc0 : pj) * kBK, pt.xa, pt.ya, pt.n0, kEvictNormal);
+                ++pai;
+                if (++pj == kc) pj = 0, pwork += work_step;
+                return true;
+            };
+            if (kTmaPatch) pdl_wait();  // the activations are the previous kernel's output
             for (int work = work0; work < total_work; work += work_step) {
                 const TileCoord t = decode_work(p, work);
-                for (int kb = 0; kb < kc * p.taps; ++kb, ++it) {
-                    const int st = it % p.stages;
-                    const uint32_t ph = (it / p.stages) & 1;
-                    mbar_wait(&empty_b[st], ph ^ 1);
-                    mbar_expect_tx(&full_b[st], b_stage);
-                    tma_load_2d(smem_b + st * b_stage, &p.tmB, &full_b[st], 0, (t.n_tile * p.kb_total + kb) * p.block_n,
-                                kEvictFirst);
+                for (int j = 0; j < kc; ++j, ++ci) {
+                    if (kTmaPatch && pai == ci) issue_patch(true);
+                    for (int tap = 0; tap < p.taps; ++tap, ++it) {
+                        if (kTmaPatch && pai == ci + 1 && pwork < total_work) issue_patch(false);
+                        const int st = it % p.stages;
+                        const uint32_t ph = (it / p.stages) & 1;
+                        mbar_wait(&empty_b[st], ph ^ 1);
+                        mbar_expect_tx(&full_b[st], b_stage);
+                        tma_load_2d(smem_b + st * b_stage, &p.tmB, &full_b[st], 0,
+                                    (t.n_tile * p.kb_total + j * p.taps + tap) * p.block_n, kEvictFirst);
+                    }
                 }
             }
         }
@@ -1130,10 +1168,6 @@ __global__ void __launch_bounds__(kGemmThreads, 1) halo_conv_kernel(const __grid
         const bool gn = p.gn_gamma != nullptr;
         const bool ups = p.upsample != 0;
         const int Hs = ups ? (p.H >> 1) : p.H, Ws = ups ? (p.W >> 1) : p.W;
-        if (ltid < 16) {  // "pixel -1" of both patches: the zero pad column that precedes the patch
-            const int which = ltid >> 3;
-            *reinterpret_cast<uint4*>(patch + which * p.patch_bytes + 7 * 128 + (ltid & 7) * 16) = make_uint4(0, 0, 0, 0);
-        }
         pdl_wait();
         if (ltid == 0) dbg_mark(p, 1);
         int cur_img = -1, ait = 0, iter = 0;
@@ -1141,6 +1175,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) halo_conv_kernel(const __grid
             const TileCoord t = decode_work(p, work);
             const int img = t.n0;
             const int ya = t.ya, xa = t.xa;
+            if (!kTmaPatch) {
             // ---- operand patches: one per 64-channel chunk ----
             // Thread t always handles vector (t & 7) of the patch pixels t / 8, t / 8 + 32, ...: pixel offsets and
             // shared-memory destinations are computed once per tile, the eight (scale, shift) pairs once per chunk, and
@@ -1257,6 +1292,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) halo_conv_kernel(const __grid
                 mbar_arrive(&full_a[pa]);
                 if (ltid == 0 && j < 24) dbg_mark(p, 9 + 2 * j);
             }
+            }  // !kTmaPatch
             // ---- epilogue ----
             const int as = p.acc_bufs == 2 ? (iter & 1) : 0;
             const uint32_t aphase = (p.acc_bufs == 2 ? (iter >> 1) : iter) & 1;
@@ -1268,7 +1304,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) halo_conv_kernel(const __grid
             int out_row;
             const bool valid = tile_row(p, t, row, out_row);
             uint4 res_pre[4];
-            if (!kFp32Direct) staged_load_residual(p, t, staged_map(p, t, lane), ew, 0, res_pre);  // hides behind the last chunk's MMAs
+            if (kKind == 0) staged_load_residual(p, t, staged_map(p, t, lane), ew, 0, res_pre);  // hides behind the last chunk's MMAs
             mbar_wait(&tmem_full[as], aphase);
             tc_fence_after();
             if (ltid == 0) dbg_mark(p, 4);
@@ -1287,6 +1323,42 @@ __global__ void __launch_bounds__(kGemmThreads, 1) halo_conv_kernel(const __grid
                             else reinterpret_cast<__half*>(p.out)[static_cast<size_t>(out_row) * p.N + ncol0 + c] = __float2half_rn(x);
                         }
                     }
+                }
+            } else if (kTmaPatch) {
+                // register epilogue: this warp's 32-column chunks (two warps per TMEM lane quarter), TMEM load of the next
+                // chunk in flight while the current one is converted and stored
+                const int half = ew >> 2;
+                float2 rowacc = make_float2(0.f, 0.f);
+                auto process32 = [&](const uint32_t (&v)[32], int c) {
+                    if (!valid) return;
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        const int cc = c + 16 * hh;
+                        if (ncol0 + cc < p.N) {
+                            float acc[16];
+#pragma unroll
+                            for (int q = 0; q < 16; ++q) acc[q] = __uint_as_float(v[16 * hh + q]);
+                            const float* bptr = p.bias != nullptr ? bias_s + cc : nullptr;
+                            const __half* rptr = p.residual != nullptr
+                                ? p.residual + static_cast<size_t>(out_row) * p.n_store + ncol0 + cc : nullptr;
+                            epilogue_store16<true, false, false, false>(p, acc, out_row, ncol0 + cc, 0, bptr, rptr, rowacc);
+                        }
+                    }
+                };
+                uint32_t va[32], vb[32];
+                int c = 32 * half;
+                if (c < p.block_n) tmem_ld32(taddr + c, va);
+                while (c < p.block_n) {
+                    tmem_ld_wait();
+                    const int c2 = c + 64;
+                    if (c2 < p.block_n) tmem_ld32(taddr + c2, vb);
+                    process32(va, c);
+                    if (c2 >= p.block_n) break;
+                    tmem_ld_wait();
+                    const int c3 = c2 + 64;
+                    if (c3 < p.block_n) tmem_ld32(taddr + c3, va);
+                    process32(vb, c2);
+                    c = c3;
                 }
             } else {
                 __half* tile_s = p.stage_dedicated ? stage_tile : reinterpret_cast<__half*>(smem);
@@ -1360,6 +1432,7 @@ struct GemmPlan {
     int Wp, tiles_per_img, patch_rows, patch_bytes;
     int win, tw, th, tiles_x;
     int staged, stage_dedicated, acc_bufs;
+    int tma_patch;
     int cs_slots;  // statistics slots per image this tiling produces (0: column statistics not available)
     int smem_bytes;
 };
@@ -1405,6 +1478,10 @@ static int plan_halo(const b200sd_gemm_args& a, GemmPlan& pl) {
     B200SD_REQUIRE(!a.upsample2x || (a.h % 2 == 0 && a.w % 2 == 0 && a.c1 == 0 && a.gn_groups == 0),
                    "b200sd_gemm: upsample2x needs even output size, one source, no GroupNorm");
     pl.halo = 1;
+    pl.tma_patch = a.halo == 2 ? 1 : 0;
+    B200SD_REQUIRE(!pl.tma_patch || (a.gn_groups == 0 && !a.upsample2x && a.cs_partial == nullptr && !a.out_f32 &&
+                                     a.block_n % 32 == 0 && a.c0 % 8 == 0 && a.c1 % 8 == 0),
+                   "b200sd_gemm: halo = 2 (TMA patches) is the plain convolution: no GroupNorm / upsample / statistics / fp32 output");
     pl.bw = pl.bh = pl.bn_img = pl.tiles_w = pl.tiles_h = pl.tiles_n = 1;
     pl.Hout = a.h, pl.Wout = a.w;
     pl.M = a.n_img * a.h * a.w;
@@ -1433,7 +1510,8 @@ static int plan_halo(const b200sd_gemm_args& a, GemmPlan& pl) {
     pl.m_tiles = a.n_img * pl.tiles_per_img;
     const int rows_needed = std::max(pl.patch_rows * pl.Wp, (2 * halo + 1) * pl.Wp + kBM) + 8 + 1;
     pl.patch_bytes = ((rows_needed + 7) / 8) * 1024;
-    B200SD_REQUIRE(pl.patch_rows * pl.Wp * 8 <= 12 * kEpiThreads, "b200sd_gemm: image too wide for the halo kernel's patch (w=%d)", a.w);
+    B200SD_REQUIRE(pl.tma_patch || pl.patch_rows * pl.Wp * 8 <= 12 * kEpiThreads, "b200sd_gemm: image too wide for the halo kernel's patch (w=%d)", a.w);
+    B200SD_REQUIRE(!pl.tma_patch || (pl.Wp <= 256 && pl.patch_rows <= 256), "b200sd_gemm: patch exceeds a TMA box (w=%d)", a.w);
     pl.block_n = a.block_n;
     B200SD_REQUIRE(pl.block_n == 16 || (pl.block_n % 32 == 0 && pl.block_n <= 256), "b200sd_gemm: halo block_n %d", pl.block_n);
     pl.n_tiles = (a.n + pl.block_n - 1) / pl.block_n;
@@ -1445,7 +1523,7 @@ static int plan_halo(const b200sd_gemm_args& a, GemmPlan& pl) {
     const bool fp32_direct = a.out_f32 || pl.block_n == 16;
     B200SD_REQUIRE(!fp32_direct || (pl.block_n == 16 && a.residual == nullptr && a.cs_partial == nullptr),
                    "b200sd_gemm: halo fp32 / narrow output needs block_n 16, no residual, no statistics");
-    pl.staged = fp32_direct ? 0 : 1;
+    pl.staged = (fp32_direct || pl.tma_patch) ? 0 : 1;
     pl.stage_dedicated = (pl.staged && pl.acc_bufs == 2) ? 1 : 0;
     const int cin = a.c0 + a.c1;
     const int fixed = 2 * pl.patch_bytes + (2 * kHaloMaxStages + 8) * 8 + 16 + 256 * 4 + 64 + 64 * 8 + ((cin + 7) & ~7) * 8 +
@@ -1670,7 +1748,25 @@ static int launch_gemm(const b200sd_gemm_args& a, cudaStream_t stream) {
     // ---- tensor maps ----
     const uint32_t es1[4] = {1, 1, 1, 1};
     if (pl.halo) {
-        // activations are read by the loader warps with plain loads; only the weights go through TMA
+        // activations are read by the loader warps with plain loads (only the weights go through TMA) unless this is the
+        // plain convolution, whose patches are 4-D boxes {64 channels, patch pitch, patch rows, 1 image}; positions outside
+        // the image (the padding ring, the pad column of the padded-linear walk) are zero-filled by the hardware
+        if (pl.tma_patch) {
+            const uint32_t box[4] = {kBK, static_cast<uint32_t>(pl.Wp), static_cast<uint32_t>(pl.patch_rows), 1};
+            for (int src = 0; src < 2; ++src) {
+                const int c = src == 0 ? a.c0 : a.c1;
+                if (c == 0) {
+                    p.tmA1 = p.tmA0;
+                    continue;
+                }
+                const uint64_t dims[4] = {static_cast<uint64_t>(c), static_cast<uint64_t>(a.w),
+                                          static_cast<uint64_t>(a.h), static_cast<uint64_t>(a.n_img)};
+                const uint64_t str[3] = {static_cast<uint64_t>(c) * 2, static_cast<uint64_t>(c) * 2 * a.w,
+                                         static_cast<uint64_t>(c) * 2 * a.w * a.h};
+                if (int rc = encode_tmap_f16(src == 0 ? &p.tmA0 : &p.tmA1, src == 0 ? a.a0 : a.a1, 4, dims, str, box, es1))
+                    return rc;
+            }
+        }
     } else if (a.mode == 0) {
         const uint32_t box[2] = {kBK, kBM};
         {
@@ -1763,6 +1859,7 @@ static int launch_gemm(const b200sd_gemm_args& a, cudaStream_t stream) {
     p.inv_wp = pl.Wp > 0 ? (1 << 20) / pl.Wp + 1 : 0;
     p.patch_rows = pl.patch_rows, p.patch_bytes = pl.patch_bytes;
     p.upsample = a.upsample2x, p.desc_bo = desc_base_offset_enabled() ? 1 : 0;
+    p.tma_patch = pl.tma_patch, p.patch_tx = pl.patch_rows * pl.Wp * kBK * 2;
     p.a0 = reinterpret_cast<const __half*>(a.a0), p.a1 = reinterpret_cast<const __half*>(a.a1), p.C1 = a.c1;
     if (pl.halo && a.gn_groups > 0) {
         B200SD_REQUIRE(a.gn_chan0 && a.gn_gamma && a.gn_beta && (a.c1 == 0 || a.gn_chan1) && a.gn_groups <= 64 &&
@@ -1795,12 +1892,12 @@ static int launch_gemm(const b200sd_gemm_args& a, cudaStream_t stream) {
     }
     if (pl.halo) {
         using HaloFn = void (*)(GemmParams);
-        const bool direct = pl.staged == 0;
-        HaloFn hfn = direct ? halo_conv_kernel<true> : halo_conv_kernel<false>;
-        static bool hattr[2] = {false, false};
-        if (!hattr[direct ? 1 : 0]) {
+        const int kind = pl.tma_patch ? 2 : (pl.staged == 0 ? 1 : 0);
+        HaloFn hfn = kind == 2 ? halo_conv_kernel<2> : (kind == 1 ? halo_conv_kernel<1> : halo_conv_kernel<0>);
+        static bool hattr[3] = {false, false, false};
+        if (!hattr[kind]) {
             B200SD_CHECK_CUDA(cudaFuncSetAttribute(hfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            hattr[direct ? 1 : 0] = true;
+            hattr[kind] = true;
         }
         const int units = pl.m_tiles * pl.n_tiles;
         B200SD_CHECK_CUDA(launch_kernel(hfn, dim3(std::min(units, num_sms())), dim3(kGemmThreads), pl.smem_bytes, stream, p));

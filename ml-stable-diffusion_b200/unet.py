@@ -111,6 +111,9 @@ class UNetEngine:
         self.fused = fm != "0"
         self.fuse_gn = fm in ("1", "2", "3")
         self.halo_min_hw = {"1": 0, "2": 1 << 30, "3": int(os.environ.get("B200SD_HALO_MIN_HW", "1024"))}.get(fm, 1 << 30)
+        # plain stride-1 3x3 convolutions on maps of at least this many pixels take the halo-reuse kernel with TMA patches
+        # (lib.conv3x3(halo=2)); smaller maps keep the 9-tap form, whose split-K fills the GPU.  0 disables.
+        self.halo_tma_min_hw = int(os.environ.get("B200SD_HALO_TMA", "0"))
         for c, h in zip(boc, self.heads):
             if c % h or c // h != 64:
                 raise L.B200SDError(f"b200sd attention kernel needs head dim 64 (got {c}/{h})")
@@ -280,10 +283,17 @@ class UNetEngine:
     def _use_halo(self, x):
         return x.shape[1] * x.shape[2] >= self.halo_min_hw
 
+    def _halo_tma(self, x, wgt, kw=None):
+        """2 (halo reuse with TMA patches) for a plain fp16 stride-1 convolution on a large enough map, else False."""
+        kw = kw or {}
+        ok = (self.halo_tma_min_hw > 0 and x.shape[1] * x.shape[2] >= self.halo_tma_min_hw and wgt.shape[0] % 32 == 0
+              and kw.get("stride", 1) == 1 and kw.get("out_dtype", torch.float16) == torch.float16 and not kw.get("act"))
+        return 2 if ok else False
+
     def _gn_conv(self, x, xs, x1, x1s, gamma, beta, eps, silu, wgt, bias, residual=None, stats=None, **kw):
-        if not self.fuse_gn:  # standalone GroupNorm launch + 9-tap convolution, no statistics side outputs
+        if not self.fuse_gn:  # standalone GroupNorm launch + plain convolution, no statistics side outputs
             hh = L.group_norm(x, gamma, beta, self.groups, eps, silu=silu, x1=x1)
-            return L.conv3x3(hh, wgt, bias, residual, **kw)
+            return L.conv3x3(hh, wgt, bias, residual, halo=self._halo_tma(hh, wgt, kw), **kw)
         have = xs is not None and (x1 is None or x1s is not None)
         halo = self._use_halo(x)
         if have and halo:
@@ -384,7 +394,9 @@ class UNetEngine:
                 if self.fuse_gn and 4 * x.shape[1] * x.shape[2] >= self.halo_min_hw:
                     x = L.conv3x3(x, u["w"], u["b"], halo=True, upsample=True, stats=st)
                 else:
-                    x = L.conv3x3(L.upsample2x(x), u["w"], u["b"], stats=st if self.fuse_gn else None)
+                    up = L.upsample2x(x)
+                    x = L.conv3x3(up, u["w"], u["b"], stats=st if self.fuse_gn else None,
+                                  halo=False if self.fuse_gn else self._halo_tma(up, u["w"]))
                 xs = st.get("chan")
         o = self.w["out"]
         return self._gn_conv(x, xs, None, None, o["g"], o["b"], self.eps, True, o["w"], o["cb"], out_dtype=torch.float32,

@@ -52,6 +52,33 @@ def test_halo_conv_plain(cuda_lib, n, h, w, ci, co):
     _close(out, _conv_ref(x, wt, b), 3e-3, 3e-3, f"halo conv {n}x{h}x{w} {ci}->{co}")
 
 
+@pytest.mark.parametrize("n,h,w,ci,co", [(2, 64, 64, 320, 320), (2, 32, 32, 640, 640), (2, 16, 16, 128, 256),
+                                         (2, 8, 8, 256, 128), (1, 5, 7, 64, 32), (3, 24, 24, 96, 64),
+                                         (1, 128, 128, 64, 64), (2, 96, 96, 128, 96), (1, 200, 136, 32, 32),
+                                         (4, 64, 64, 64, 640)])
+def test_halo_conv_tma_patches(cuda_lib, n, h, w, ci, co):
+    """halo=2: the plain convolution whose patches arrive as one TMA box per 64-channel chunk (zero fill for the padding
+    ring and the pad column) with the register epilogue; persistent CTAs with several tiles included (4x64x64 -> 640)."""
+    x = _rand(n, h, w, ci, seed=1)
+    wt = _rand(co, ci, 3, 3, scale=(9 * ci) ** -0.5, seed=2)
+    b = torch.randn(co, device="cuda")
+    out = cuda_lib.conv3x3(x, _pack(wt), b, halo=2)
+    torch.cuda.synchronize()
+    _close(out, _conv_ref(x, wt, b), 3e-3, 3e-3, f"TMA halo conv {n}x{h}x{w} {ci}->{co}")
+    assert torch.equal(out, cuda_lib.conv3x3(x, _pack(wt), b, halo=2))
+
+
+def test_halo_conv_tma_two_sources_temb_residual(cuda_lib):
+    n, h, w, c0, c1, co = 2, 32, 32, 640, 320, 640
+    x0, x1 = _rand(n, h, w, c0, seed=1), _rand(n, h, w, c1, seed=2)
+    wt = _rand(co, c0 + c1, 3, 3, scale=(9 * (c0 + c1)) ** -0.5, seed=3)
+    temb = torch.randn(n, co + 64, device="cuda")  # strided per-image bias table
+    res = _rand(n, h, w, co, seed=4)
+    out = cuda_lib.conv3x3(x0, _pack(wt), temb[:, 32:], res, x1=x1, bias_rows=h * w, bias_stride=co + 64, halo=2)
+    ref = _conv_ref(torch.cat([x0, x1], -1), wt) + temb[:, 32:32 + co].reshape(n, 1, 1, co) + res.float()
+    _close(out, ref, 4e-3, 3e-3, "TMA halo conv two sources + temb + residual")
+
+
 def test_halo_conv_two_sources_temb_residual(cuda_lib):
     n, h, w, c0, c1, co = 2, 32, 32, 640, 320, 640
     x0, x1 = _rand(n, h, w, c0, seed=1), _rand(n, h, w, c1, seed=2)
