@@ -195,11 +195,19 @@ class B200StableDiffusionPipeline:
             if not os.path.isdir(os.path.join(model_dir, enc_dir)):
                 return None, None
             tcfg = K.read_config(model_dir, enc_dir)
-            enc = TextEncoderModel(tcfg, K.load_component(model_dir, enc_dir, tcfg), batch=1, device=device)
+            # SDXL conditions on hidden_states[-2] of both encoders (torch2coreml.py:416-446: ``hidden_embeds``)
+            enc = TextEncoderModel(tcfg, K.load_component(model_dir, enc_dir, tcfg), batch=1, device=device,
+                                   hidden_layer=-2 if xl else None)
             tok = None
             tdir = os.path.join(model_dir, tok_dir)
             if os.path.exists(os.path.join(tdir, "merges.txt")):
-                tok = BPETokenizer.from_files(os.path.join(tdir, "merges.txt"), os.path.join(tdir, "vocab.json"))
+                pad = "<|endoftext|>"
+                stm = os.path.join(tdir, "special_tokens_map.json")  # SDXL's second tokenizer pads with "!"
+                if os.path.exists(stm):
+                    with open(stm) as fh:
+                        pt = json.load(fh).get("pad_token", pad)
+                    pad = pt.get("content", pad) if isinstance(pt, dict) else pt
+                tok = BPETokenizer.from_files(os.path.join(tdir, "merges.txt"), os.path.join(tdir, "vocab.json"), pad_token=pad)
             return enc, tok
 
         enc1, tok1 = text_pair("text_encoder", "tokenizer")

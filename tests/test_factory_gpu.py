@@ -109,3 +109,53 @@ def test_sdxl_refiner_hand_off_vs_oracle_loop(cuda_lib):
     # without refiner inputs the base UNet runs every step: a different result
     plain = pipe.denoise(emb, lat0, steps, gs, time_ids=tid, text_embeds=pooled).cpu()
     assert not torch.allclose(plain, final)
+
+
+def test_sdxl_call_through_both_text_encoders(cuda_lib, tmp_path):
+    """SDXL ``__call__`` from a model directory with two tokenizers and two text encoders (pipeline.py:123-257): the
+    prompt goes through both BPE tokenizers and both encoders on the device, ``hidden_embeds`` are concatenated on the
+    feature axis (encoder 1 first), the pooled / projected output of encoder 2 conditions ``text_time``, negatives are
+    zeros.  Checked against the same call fed with embeddings computed by the oracle's CLIP restatement."""
+    from b200sd.pipeline import B200StableDiffusionPipeline
+    from oracle import clip_text
+
+    st = pytest.importorskip("safetensors.torch")
+    c1, c2 = config.TINY_CLIP_TEXT, config.TINY_CLIP_TEXT_PROJ
+    ucfg = dict(config.TINY_XL_UNET, cross_attention_dim=c1["hidden_size"] + c2["hidden_size"],
+                projection_class_embeddings_input_dim=c2["projection_dim"] + 6 * 32)
+    _model_dir(tmp_path, ucfg, seed=31)
+    sds = {}
+    for name, cfg, seed in (("text_encoder", c1, 41), ("text_encoder_2", c2, 42)):
+        sds[name] = config.random_clip_text_state_dict(cfg, seed=seed, dtype=torch.float16)
+        os.makedirs(tmp_path / name, exist_ok=True)
+        st.save_file({k: v.contiguous() for k, v in sds[name].items()}, str(tmp_path / name / "model.safetensors"))
+        (tmp_path / name / "config.json").write_text(json.dumps(dict(cfg, _class_name="CLIPTextModel")))
+    vocab = {"<|startoftext|>": 998, "<|endoftext|>": 999, "low</w>": 2, "er</w>": 3, "new": 4, "lo": 5, "w": 6, "!": 0}
+    for tdir, extra in (("tokenizer", {}), ("tokenizer_2", {"pad_token": "!"})):
+        os.makedirs(tmp_path / tdir, exist_ok=True)
+        (tmp_path / tdir / "merges.txt").write_text("#version: 0.2\nl o\nlo w</w>\ne r</w>\nn e\nne w\n")
+        (tmp_path / tdir / "vocab.json").write_text(json.dumps(vocab))
+        if extra:
+            (tmp_path / tdir / "special_tokens_map.json").write_text(json.dumps({"pad_token": {"content": extra["pad_token"]}}))
+    pipe = B200StableDiffusionPipeline.from_pretrained(str(tmp_path), height=64, width=64)
+    assert pipe.xl and pipe.force_zeros_for_empty_prompt and pipe.text_encoder_2 is not None and pipe.tokenizer_2 is not None
+    assert pipe.tokenizer_2.pad_token == "!" and pipe.tokenizer.pad_token == "<|endoftext|>"
+    assert list(np.asarray(pipe.tokenizer_2("low"))[0][:5]) == [998, 2, 999, 0, 0]
+    kw = dict(height=64, width=64, num_inference_steps=3, guidance_scale=5.0, output_type="np", seed=9, rng="torch")
+    img = pipe("low newer", **kw).images
+    assert img.shape == (1, 64, 64, 3) and np.isfinite(img).all()
+    # the same call with the oracle's embeddings for the same token ids
+    hid, pooled = [], None
+    for name, cfg, tok in (("text_encoder", c1, pipe.tokenizer), ("text_encoder_2", c2, pipe.tokenizer_2)):
+        ids = torch.from_numpy(np.asarray(tok("low newer"))).long()
+        with torch.no_grad():
+            ref = clip_text.clip_text_forward(cfg, sds[name], ids, return_all=True)
+        hid.append(ref["hidden_states"][-2])
+        pooled = ref["text_embeds" if cfg.get("projection_dim") else "pooler_output"]
+    emb = torch.cat(hid, -1).permute(0, 2, 1)[:, :, None, :]                       # [1, 256, 1, 77]
+    emb = torch.cat([torch.zeros_like(emb), emb]).half().numpy()                   # zero negatives, uncond half first
+    pool = torch.cat([torch.zeros_like(pooled), pooled]).float().numpy()
+    ref_img = pipe("low newer", prompt_embeds=emb, pooled_prompt_embeds=pool, **kw).images
+    err = float(np.abs(img.astype(np.float32) - ref_img.astype(np.float32)).max())
+    print(f"SDXL __call__ through both encoders vs oracle embeddings: max image diff {err:.4f}")
+    assert err <= 0.03
