@@ -292,10 +292,11 @@ __global__ void __launch_bounds__(256) gn_apply_chan_kernel(const __half* __rest
 // grid = (cs, C / chunk, n_img) with cluster dims (cs, 1, 1): one cluster per (image, channel chunk), where a
 // chunk is a whole number of groups and of 16-byte vectors.  The cs CTAs of a cluster split the image's
 // pixels; each keeps its [pixels x chunk] slab in shared memory, so the tensor is read from L2/HBM exactly
-// once.  Statistics are exact two-pass (mean, then sum of squared deviations from the slab) and are exchanged
-// between the CTAs through distributed shared memory in rank order -- no global barrier, no partial buffers,
-// no atomics (bitwise reproducible).  Thread t owns vector column t % vpr for all its pixels, so per-channel
+// once.  Statistics are one pass (sum and sum of squares in fp32, see below) and are exchanged ONCE between the CTAs
+// through distributed shared memory in rank order -- no global barrier, no partial buffers, no atomics (bitwise
+// reproducible).  Thread t owns vector column t % vpr for all its pixels, so per-channel
 // partial sums live in registers and fold rows -> channels -> groups in a fixed order.
+template <int kRowsInFlight>
 __global__ void gn_cluster_kernel(const __half* __restrict__ x0, const __half* __restrict__ x1, int c0, int c1, int hw,
                                   int groups, int chunk_ch, int rows_per_cta, float eps,
                                   const float* __restrict__ gamma, const float* __restrict__ beta, int silu,
@@ -332,18 +333,32 @@ __global__ void gn_cluster_kernel(const __half* __restrict__ x0, const __half* _
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[e] = acq[e] = 0.f;
     if (active) {
-#pragma unroll 8
-        for (int px = px0 + ty; px < px1; px += TY) {
-            const uint4 raw = *reinterpret_cast<const uint4*>(src + static_cast<size_t>(px) * ld);
-            slab[(px - px0) * vpr + cv] = raw;
-            const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+        // eight rows per thread are requested before the first one is consumed (the compiler keeps only two loads in
+        // flight across the shared-memory stores of a plainly unrolled loop: ncu showed every row's first use stalling)
+        // (kRowsInFlight = 2 for the small maps: a thread has one or two rows there and the 32 extra registers would cost a
+        // resident CTA per SM)
+        for (int pxb = px0 + ty; pxb < px1; pxb += TY * kRowsInFlight) {
+            uint4 raw[kRowsInFlight];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float2 t = __half22float2(h2[q]);
-                acc[2 * q] += t.x;
-                acc[2 * q + 1] += t.y;
-                acq[2 * q] = fmaf(t.x, t.x, acq[2 * q]);
-                acq[2 * q + 1] = fmaf(t.y, t.y, acq[2 * q + 1]);
+            for (int i = 0; i < kRowsInFlight; ++i) {
+                const int px = pxb + i * TY;
+                raw[i] = px < px1 ? __ldg(reinterpret_cast<const uint4*>(src + static_cast<size_t>(px) * ld)) : make_uint4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int i = 0; i < kRowsInFlight; ++i) {
+                const int px = pxb + i * TY;
+                if (px < px1) {
+                    slab[(px - px0) * vpr + cv] = raw[i];
+                    const __half2* h2 = reinterpret_cast<const __half2*>(&raw[i]);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float2 t = __half22float2(h2[q]);
+                        acc[2 * q] += t.x;
+                        acc[2 * q + 1] += t.y;
+                        acq[2 * q] = fmaf(t.x, t.x, acq[2 * q]);
+                        acq[2 * q + 1] = fmaf(t.y, t.y, acq[2 * q + 1]);
+                    }
+                }
             }
         }
     }
@@ -593,11 +608,12 @@ extern "C" int b200sd_group_norm(const void* x0, const void* x1, int32_t c0, int
         const size_t csmem = static_cast<size_t>(rows_per_cta) * vpr * 16 +
                              (2 * static_cast<size_t>(TY) * chunk + 2 * chunk + 4 * (chunk / cpg)) * sizeof(float);
         if (mode == 1 && vpr <= 64 && C % chunk == 0 && csmem <= 200 * 1024 && n_img <= 65535 && C / chunk <= 65535) {
-            static bool attr = false;
-            if (!attr) {
-                B200SD_CHECK_CUDA(cudaFuncSetAttribute(gn_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                       200 * 1024));
-                attr = true;
+            const int deep = (rows_per_cta + TY - 1) / TY >= 3 ? 1 : 0;
+            auto kern = deep ? gn_cluster_kernel<8> : gn_cluster_kernel<2>;
+            static bool attr[2] = {false, false};
+            if (!attr[deep]) {
+                B200SD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                attr[deep] = true;
             }
             cudaLaunchConfig_t cfg;
             memset(&cfg, 0, sizeof(cfg));
@@ -617,7 +633,7 @@ extern "C" int b200sd_group_norm(const void* x0, const void* x1, int32_t c0, int
                 at[1].val.programmaticStreamSerializationAllowed = 1;
                 cfg.numAttrs = 2;
             }
-            B200SD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gn_cluster_kernel, reinterpret_cast<const __half*>(x0),
+            B200SD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, reinterpret_cast<const __half*>(x0),
                                                  reinterpret_cast<const __half*>(x1), static_cast<int>(c0),
                                                  static_cast<int>(c1), static_cast<int>(hw), static_cast<int>(groups), chunk,
                                                  rows_per_cta, eps, gamma, beta, static_cast<int>(silu),
