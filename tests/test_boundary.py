@@ -197,3 +197,20 @@ def test_sdxl_prompt_encoding_follows_the_reference_branch():
     assert emb3.shape == (2, 10, 1, 77) and pooled3.shape == (2, 5) and np.array_equal(emb3[0], emb3[1])
     with pytest.raises(ValueError, match="batch size"):
         P._encode_prompt_xl(stub, ["ab", "cd"], True, negative_prompt=["x"])
+
+
+def test_bench_refuses_to_run_the_product_arm_without_a_gpu():
+    """bench.py has no CPU fallback for the product arm: without a CUDA device it prints an error line and exits 1
+    (the CPU numbers come from `--impl reference` only)."""
+    import json
+    import subprocess
+    import sys
+
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 1
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert "no CUDA device" in line["error"] and "--impl reference" in line["error"]
