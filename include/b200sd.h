@@ -98,7 +98,9 @@ typedef struct {
      * row scale in the epilogue (LayerNorm folded into the weights). */
     int32_t halo;          /* mode 1, stride 1, pad 1: halo-reuse kernel: one (rows + 2) x (w + 1) activation patch per
                               64-channel chunk in shared memory, the nine taps are row-shifted MMA descriptors; `wgt`
-                              must be pre-tiled chunk-major: k-block = chunk * 9 + tap */
+                              must be pre-tiled chunk-major: k-block = chunk * 9 + tap.  1: loader warps fill the patch
+                              (GroupNorm / SiLU / upsample on the way in, statistics outputs); 2: plain convolution, the
+                              patch is one TMA box per chunk (no gn_*, upsample2x, cs_*; fp16 output, block_n % 32 == 0) */
     int32_t upsample2x;    /* halo: a0 is [n_img, h/2, w/2, c0] and is read nearest-x2 upsampled (Upsample2D, unet.py:499) */
     int32_t gn_groups;     /* halo: > 0 = y = silu?(groupnorm(a0 ++ a1)) feeds the convolution */
     int32_t gn_silu;
