@@ -603,7 +603,13 @@ extern "C" int b200sd_group_norm(const void* x0, const void* x1, int32_t c0, int
         int cs = 8;
         while (cs > 1 && (hw / cs < 32 || clusters * cs > 4L * num_sms())) cs >>= 1;
         const int rows_per_cta = (hw + cs - 1) / cs;
-        const int threads = 256;  // 512 threads for the large slabs measured 0.4 % slower
+        // B200SD_GN_THREADS (tuning aid): 512 threads for slabs of >= 256 rows
+        static int big_threads = -1;
+        if (big_threads < 0) {
+            const char* e = getenv("B200SD_GN_THREADS");
+            big_threads = (e && atoi(e) == 512) ? 512 : 256;
+        }
+        const int threads = rows_per_cta >= 256 ? big_threads : 256;
         const int TY = threads / std::max(1, vpr);
         const size_t csmem = static_cast<size_t>(rows_per_cta) * vpr * 16 +
                              (2 * static_cast<size_t>(TY) * chunk + 2 * chunk + 4 * (chunk / cpg)) * sizeof(float);
