@@ -394,7 +394,7 @@ def run_gpu_arm(args, rank, local_rank, world):
         if rank == 0:
             print(json.dumps({"quick": True, "iter_per_s": round(world * args.steps / (ms_dev * 1e-3), 2),
                               "ms_per_step": round(ms_dev / args.steps, 4), "launches_per_step": round(launches_per_step, 1),
-                              "fused": os.environ.get("B200SD_FUSED", "ln"), "pdl": os.environ.get("B200SD_PDL", "0")}),
+                              "fused": os.environ.get("B200SD_FUSED", "ln"), "pdl": os.environ.get("B200SD_PDL", "1")}),
                   flush=True)
         sampler.stop()
         if world > 1:

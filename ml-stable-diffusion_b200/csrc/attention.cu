@@ -141,7 +141,8 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
-    pdl_wait();  // PDL: the prologue above overlapped the previous kernel's tail
+    pdl_trigger();  // after this CTA's TMEM allocation: a dependent CTA can never take the columns this grid still needs
+    pdl_wait();     // PDL: the prologue above overlapped the previous kernel's tail
     const uint32_t tmem_s = tmem_base;        // 2 x 64 columns (double-buffered S halves)
     const uint32_t tmem_o = tmem_base + 128;  // 64 columns
 
@@ -509,7 +510,6 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
         }
     }
 
-    pdl_trigger();
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {

@@ -26,6 +26,7 @@ namespace {
     } while (0)
 
 __global__ void add_f32_kernel(float* __restrict__ a, const float* __restrict__ b, int n) {
+    pdl_trigger();  // no TMEM / large shared memory here: dependents may start their prologue at once
     pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) a[i] += b[i];
