@@ -214,3 +214,24 @@ def test_bench_refuses_to_run_the_product_arm_without_a_gpu():
     assert r.returncode == 1
     line = json.loads(r.stdout.strip().splitlines()[-1])
     assert "no CUDA device" in line["error"] and "--impl reference" in line["error"]
+
+
+def test_every_kernel_waits_for_its_grid_dependency():
+    """Programmatic dependent launch is on by default, so EVERY kernel of the library must execute griddepcontrol.wait
+    (`pdl_wait()`) before it touches global memory, and a kernel that allocates TMEM may only release its dependents
+    (`pdl_trigger()`) after that allocation (a dependent CTA could otherwise take columns the running grid still needs).
+    Source scan: cheap guard against a new kernel forgetting either rule."""
+    csrc = os.path.join(ROOT, "ml-stable-diffusion_b200", "csrc")
+    seen = 0
+    for f in sorted(os.listdir(csrc)):
+        if not f.endswith(".cu"):
+            continue
+        src = open(os.path.join(csrc, f)).read()
+        for m in re.finditer(r"__global__[^{;]*\{", src):
+            end = src.find("\n}\n", m.end())
+            body = src[m.end():end]
+            seen += 1
+            assert "pdl_wait()" in body, f"{f}: kernel at offset {m.start()} never calls pdl_wait()"
+            if "tmem_alloc" in body and "pdl_trigger()" in body:
+                assert body.index("tmem_alloc") < body.index("pdl_trigger()"), f"{f}: dependents released before the TMEM allocation"
+    assert seen >= 20
