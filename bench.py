@@ -278,7 +278,7 @@ def gemm_census(pipe):
 
     def rec(args):
         m = args.m if (args.mode == 0 and not args.halo) else args.n_img * (args.h // max(1, args.stride)) * (args.w // max(1, args.stride))
-        k = (args.c0 + args.c1) * (9 if args.mode == 1 else 1)
+        k = (args.c0 + args.c1) * (9 if args.mode == 1 else 1) + args.c2 + args.c3  # (+ a folded shortcut)
         recs.append(2.0 * m * args.n * k)
         orig(args)
 

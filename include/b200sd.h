@@ -126,6 +126,13 @@ typedef struct {
     const float* ln_wg;
     int32_t ln_parts;
     float ln_eps;
+    /* ResNet shortcut folded into conv2 (mode 1, stride 1; ResnetBlock2D: out = conv2(h) + conv_shortcut(x),
+     * unet.py:483-489): a 1x1 convolution over a2 ++ a3 ([n_img, h, w, c2] / [.., c3], c3 may be 0) accumulated into the
+     * same output tile as extra k-blocks that read the centre tap only.  `wgt` then holds [n, 9 * (c0 + c1) + c2 + c3]
+     * (the shortcut's [n, c2 + c3] matrix appended along K; pre-tiled in that order) and `bias` the sum of both biases. */
+    const void* a2;
+    const void* a3;
+    int32_t c2, c3;
 } b200sd_gemm_args;
 
 int b200sd_gemm(const b200sd_gemm_args* args, void* stream);

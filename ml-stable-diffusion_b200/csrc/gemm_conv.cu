@@ -44,6 +44,8 @@ static int smem_budget() {
 
 struct __align__(64) GemmParams {
     CUtensorMap tmA0, tmA1, tmB;
+    CUtensorMap tmA2, tmA3;  // mode 1: centre-tap-only sources (the ResNet shortcut folded into conv2 as extra k-blocks)
+    int kc2, kc3;            // their 64-channel chunk counts; k-blocks [taps * kc, taps * kc + kc2 + kc3)
     int mode, M, N, n_store;  // n_store: columns written per row (N or N/2 for GEGLU)
     int C0, Kpt, kc0, kc, taps;
     int kb_total, kb_per_split, splits;
@@ -669,11 +671,21 @@ __global__ void __launch_bounds__(kGemmThreads, 1) umma_gemm_kernel(const __grid
                                 p.wgt_tiled ? kEvictFirst : kEvictLast);
             };
             auto load_a = [&](const TileCoord& t, int kb, int st) {
-                const int tap = kb / p.kc;
-                const int j = kb - tap * p.kc;
-                const bool src1 = j >= p.kc0;
-                const int c = (src1 ? (j - p.kc0) : j) * kBK;
-                const CUtensorMap* tmA = src1 ? &p.tmA1 : &p.tmA0;
+                int tap = kb / p.kc;
+                int j = kb - tap * p.kc;
+                const CUtensorMap* tmA;
+                int c;
+                if (tap >= p.taps) {  // shortcut region: a 1x1 convolution = the centre tap over its own sources
+                    j = kb - p.taps * p.kc;
+                    const bool src3 = j >= p.kc2;
+                    c = (src3 ? (j - p.kc2) : j) * kBK;
+                    tmA = src3 ? &p.tmA3 : &p.tmA2;
+                    tap = 4;
+                } else {
+                    const bool src1 = j >= p.kc0;
+                    c = (src1 ? (j - p.kc0) : j) * kBK;
+                    tmA = src1 ? &p.tmA1 : &p.tmA0;
+                }
                 void* dst_a = smem_a + st * kAStage;
                 const int r = tap / 3, s3 = tap - 3 * r;
                 if (kTwoCta) {
@@ -1567,7 +1579,9 @@ static int plan_gemm(const b200sd_gemm_args& a, GemmPlan& pl) {
     pl.kc0 = (a.c0 + kBK - 1) / kBK;
     pl.kc1 = (a.c1 + kBK - 1) / kBK;
     pl.taps = a.mode == 1 ? 9 : 1;
-    pl.kb_total = pl.taps * (pl.kc0 + pl.kc1);
+    pl.kb_total = pl.taps * (pl.kc0 + pl.kc1) + (a.c2 + kBK - 1) / kBK + (a.c3 + kBK - 1) / kBK;
+    B200SD_REQUIRE((a.c2 == 0 && a.c3 == 0) || (a.mode == 1 && a.stride == 1 && !a.halo && a.c2 > 0 && a.c2 % 8 == 0 && a.c3 % 8 == 0),
+                   "b200sd_gemm: shortcut sources (a2 / a3) need a stride-1 3x3 convolution and channel counts that are multiples of 8");
     pl.halo = 0, pl.Wp = 0, pl.tiles_per_img = 0, pl.patch_rows = 0, pl.patch_bytes = 0;
     pl.staged = 0, pl.stage_dedicated = 0, pl.acc_bufs = 1, pl.cs_slots = 0, pl.smem_bytes = 0;
     const bool want_stats = a.cs_partial != nullptr || a.rs_out != nullptr;
@@ -1786,18 +1800,21 @@ static int launch_gemm(const b200sd_gemm_args& a, cudaStream_t stream) {
         const uint32_t box[4] = {kBK, static_cast<uint32_t>(pl.bw) * st, static_cast<uint32_t>(pl.bh) * st,
                                  static_cast<uint32_t>(pl.bn_img)};
         const uint32_t es[4] = {1, st, st, 1};
-        for (int src = 0; src < 2; ++src) {
-            const int c = src == 0 ? a.c0 : a.c1;
+        CUtensorMap* maps[4] = {&p.tmA0, &p.tmA1, &p.tmA2, &p.tmA3};
+        const void* ptrs[4] = {a.a0, a.a1, a.a2, a.a3};
+        const int chans[4] = {a.c0, a.c1, a.c2, a.c3};
+        for (int src = 0; src < 4; ++src) {
+            const int c = chans[src];
             if (c == 0) {
-                p.tmA1 = p.tmA0;
+                *maps[src] = p.tmA0;
                 continue;
             }
+            B200SD_REQUIRE(ptrs[src] != nullptr, "b200sd_gemm: source %d has %d channels but a null pointer", src, c);
             const uint64_t dims[4] = {static_cast<uint64_t>(c), static_cast<uint64_t>(a.w),
                                       static_cast<uint64_t>(a.h), static_cast<uint64_t>(a.n_img)};
             const uint64_t str[3] = {static_cast<uint64_t>(c) * 2, static_cast<uint64_t>(c) * 2 * a.w,
                                      static_cast<uint64_t>(c) * 2 * a.w * a.h};
-            if (int rc = encode_tmap_f16(src == 0 ? &p.tmA0 : &p.tmA1, src == 0 ? a.a0 : a.a1, 4, dims, str, box, es))
-                return rc;
+            if (int rc = encode_tmap_f16(maps[src], ptrs[src], 4, dims, str, box, es)) return rc;
         }
     }
     if (a.wgt_tiled) {
@@ -1822,6 +1839,7 @@ static int launch_gemm(const b200sd_gemm_args& a, cudaStream_t stream) {
     p.Kpt = pl.Kpt;
     p.kc0 = pl.kc0;
     p.kc = pl.kc0 + pl.kc1;
+    p.kc2 = (a.c2 + kBK - 1) / kBK, p.kc3 = (a.c3 + kBK - 1) / kBK;
     p.taps = pl.taps;
     p.kb_total = pl.kb_total;
     p.kb_per_split = pl.kb_per_split;

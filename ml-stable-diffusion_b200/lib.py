@@ -36,6 +36,7 @@ class GemmArgs(C.Structure):
         ("cs_partial", C.c_void_p), ("cs_chan", C.c_void_p), ("cs_tickets", C.c_void_p), ("cs_hw", C.c_int32),
         ("rs_out", C.c_void_p),
         ("ln_stat", C.c_void_p), ("ln_wg", C.c_void_p), ("ln_parts", C.c_int32), ("ln_eps", C.c_float),
+        ("a2", C.c_void_p), ("a3", C.c_void_p), ("c2", C.c_int32), ("c3", C.c_int32),
     ]
 
 
@@ -214,17 +215,19 @@ TILED_WEIGHTS = os.environ.get("B200SD_TILED_W", "1") != "0"
 _tiled_cache = {}
 
 
-def pack_tiled(w2d, c0, c1, taps, bn, chunk_major=False):
-    """[N, taps*(c0+c1)] -> [n_tiles, k_blocks, bn, 64] fp16 in the exact k-block order of the kernel's main
+def pack_tiled(w2d, c0, c1, taps, bn, chunk_major=False, extra=(0, 0)):
+    """[N, taps*(c0+c1) (+ c2 + c3)] -> [n_tiles, k_blocks, bn, 64] fp16 in the exact k-block order of the kernel's main
     loop (tap-major; per tap the 64-channel chunks of source 0, then of source 1; ragged chunks zero padded), so
     that each weight tile is one contiguous bn*128-byte burst in HBM.  chunk_major: k-block = chunk * taps + tap
-    (the halo convolution walks all nine taps of one 64-channel chunk before the next chunk)."""
+    (the halo convolution walks all nine taps of one 64-channel chunk before the next chunk).  extra = (c2, c3): the
+    folded shortcut's columns follow the convolution's: their chunks (source 2, then source 3) are the last k-blocks."""
     n, kpt = w2d.shape[0], c0 + c1
     kc0, kc1 = (c0 + 63) // 64, (c1 + 63) // 64
     kc = kc0 + kc1
     nt = (n + bn - 1) // bn
+    c2, c3 = extra
     wp = torch.zeros(nt * bn, taps, kpt, dtype=w2d.dtype, device=w2d.device)
-    wp[:n] = w2d.reshape(n, taps, kpt)
+    wp[:n] = w2d[:, : taps * kpt].reshape(n, taps, kpt)
     out = torch.zeros(nt, taps, kc, bn, 64, dtype=w2d.dtype, device=w2d.device)
     for j in range(kc):
         lo = j * 64 if j < kc0 else c0 + (j - kc0) * 64
@@ -232,7 +235,20 @@ def pack_tiled(w2d, c0, c1, taps, bn, chunk_major=False):
         out[:, :, j, :, : hi - lo] = wp[:, :, lo:hi].reshape(nt, bn, taps, hi - lo).permute(0, 2, 1, 3)
     if chunk_major:
         out = out.permute(0, 2, 1, 3, 4)
-    return out.reshape(nt, taps * kc, bn, 64).contiguous()
+    out = out.reshape(nt, taps * kc, bn, 64)
+    if c2 + c3:
+        if chunk_major:
+            raise B200SDError("pack_tiled: shortcut columns are not supported in the chunk-major (halo) layout")
+        kc2, kc3 = (c2 + 63) // 64, (c3 + 63) // 64
+        we = torch.zeros(nt * bn, c2 + c3, dtype=w2d.dtype, device=w2d.device)
+        we[:n] = w2d[:, taps * kpt:]
+        ext = torch.zeros(nt, kc2 + kc3, bn, 64, dtype=w2d.dtype, device=w2d.device)
+        for j in range(kc2 + kc3):
+            lo = j * 64 if j < kc2 else c2 + (j - kc2) * 64
+            hi = min(lo + 64, c2 if j < kc2 else c2 + c3)
+            ext[:, j, :, : hi - lo] = we[:, lo:hi].reshape(nt, bn, hi - lo)
+        out = torch.cat([out, ext], 1)
+    return out.contiguous()
 
 
 def plan_ex(args):
@@ -245,7 +261,7 @@ def plan_ex(args):
 def _maybe_tile_weights(args, wgt, taps):
     """Static weight operands are re-laid out once per (weight, block_n) and cached."""
     bn = plan_ex(args)[0]
-    key = (wgt.data_ptr(), bn, args.c0, args.c1, taps, bool(args.halo))
+    key = (wgt.data_ptr(), bn, args.c0, args.c1, taps, bool(args.halo), args.c2, args.c3)
     hit = _tiled_cache.get(key)
     packed = None
     if hit is not None and hit[0]() is wgt and hit[1] == wgt._version:
@@ -253,7 +269,7 @@ def _maybe_tile_weights(args, wgt, taps):
     if packed is None:
         if torch.cuda.is_current_stream_capturing():
             return  # never pack during capture; the warm-up pass has populated the cache for these shapes
-        packed = pack_tiled(wgt, args.c0, args.c1, taps, bn, chunk_major=bool(args.halo))
+        packed = pack_tiled(wgt, args.c0, args.c1, taps, bn, chunk_major=bool(args.halo), extra=(args.c2, args.c3))
         if len(_tiled_cache) > 4096:  # drop entries whose source tensor is gone
             for k in [k for k, v in _tiled_cache.items() if v[0]() is None]:
                 del _tiled_cache[k]
@@ -384,13 +400,15 @@ def linear(x, wgt, bias=None, residual=None, *, x1=None, geglu=False, out_dtype=
 
 def conv3x3(x, wgt, bias=None, residual=None, *, x1=None, stride=1, out_dtype=torch.float16, split_k=0,
             block_n=0, bias_rows=0, bias_stride=0, out=None, act=0, static_w=True, pad_after_only=False,
-            halo=False, gn=None, upsample=False, stats=None, rowstats=None, taps=9):
+            halo=False, gn=None, upsample=False, stats=None, rowstats=None, taps=9, shortcut=None):
     """3x3 pad-1 convolution.  x NHWC fp16 [N, H, W, C0]; wgt [Cout, 9*(C0+C1)] fp16 (OHWI);
     bias fp32 [Cout] or [N_img, Cout] with bias_rows = Hout*Wout.
     halo: the halo-reuse kernel (stride 1); gn: GroupNorm (+SiLU) of x ++ x1 applied while loading (dict(chan0, chan1,
     gamma, beta, groups, eps, silu), needs halo); upsample: x is read nearest-x2 upsampled (halo); stats: dict that
     receives 'chan', the per-channel (sum, sum of squares) of the output for the consumer's GroupNorm; taps=1 with
-    halo: a 1x1 convolution (wgt [Cout, C0+C1]) that shares the halo kernel's GroupNorm operand path."""
+    halo: a 1x1 convolution (wgt [Cout, C0+C1]) that shares the halo kernel's GroupNorm operand path.
+    shortcut = (s0, s1 or None): the ResNet shortcut folded in -- wgt is [Cout, 9*(C0+C1) + Cs0 + Cs1] (the 1x1
+    shortcut matrix appended along K), bias the sum of both biases, s0 / s1 NHWC fp16 at the output resolution."""
     _req(x, torch.float16, "conv3x3 x")
     _req(wgt, torch.float16, "conv3x3 wgt")
     nimg, h, w, _ = x.shape
@@ -406,6 +424,15 @@ def conv3x3(x, wgt, bias=None, residual=None, *, x1=None, stride=1, out_dtype=to
                      stride=stride, bias_rows=bias_rows, bias_stride=bias_stride, split_k=split_k, block_n=block_n, act=act,
                      pad_after_only=pad_after_only, m=(nimg * h * w if taps == 1 else 0))
     args.halo, args.upsample2x = int(halo), int(upsample)
+    if shortcut is not None:
+        s0, s1 = shortcut
+        if stride != 1 or taps != 9 or halo or not (static_w and TILED_WEIGHTS):
+            raise B200SDError("conv3x3: a folded shortcut needs the stride-1 9-tap kernel with static pre-tiled weights")
+        _req(s0, torch.float16, "conv3x3 shortcut source")
+        args.a2, args.c2 = s0.data_ptr(), s0.shape[-1]
+        if s1 is not None:
+            _req(s1, torch.float16, "conv3x3 shortcut source 1")
+            args.a3, args.c3 = s1.data_ptr(), s1.shape[-1]
     _keep = None
     if gn is not None or stats is not None or rowstats is not None:
         args.split_k = 1

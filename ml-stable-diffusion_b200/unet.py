@@ -114,6 +114,8 @@ class UNetEngine:
         # plain stride-1 3x3 convolutions on maps of at least this many pixels take the halo-reuse kernel with TMA patches
         # (lib.conv3x3(halo=2)); smaller maps keep the 9-tap form, whose split-K fills the GPU.  0 disables.
         self.halo_tma_min_hw = int(os.environ.get("B200SD_HALO_TMA", "0"))
+        # ResNet shortcuts (1x1 convolutions on the block input) run as extra k-blocks of conv2 instead of their own launch
+        self.fold_shortcut = os.environ.get("B200SD_FOLD_SC", "1") != "0"
         for c, h in zip(boc, self.heads):
             if c % h or c // h != 64:
                 raise L.B200SDError(f"b200sd attention kernel needs head dim 64 (got {c}/{h})")
@@ -143,6 +145,11 @@ class UNetEngine:
             if (p + ".conv_shortcut.weight") in sd:
                 r["sc"] = P.lin(p + ".conv_shortcut")
                 r["scb"] = P.bias(p + ".conv_shortcut")
+                # the shortcut folded into conv2: its [Cout, Cin] matrix appended along K (extra centre-tap k-blocks of
+                # the same convolution launch, lib.conv3x3(shortcut=...)), one bias vector for both
+                if self.fold_shortcut and not self.fuse_gn and self.fused:
+                    r["c2sc"] = torch.cat([r["c2"], r["sc"]], 1).contiguous()
+                    r["c2scb"] = (r["c2b"] + r["scb"]).contiguous()
             w[p] = r
 
         def transformer(p, c, depth):
@@ -293,7 +300,7 @@ class UNetEngine:
     def _gn_conv(self, x, xs, x1, x1s, gamma, beta, eps, silu, wgt, bias, residual=None, stats=None, **kw):
         if not self.fuse_gn:  # standalone GroupNorm launch + plain convolution, no statistics side outputs
             hh = L.group_norm(x, gamma, beta, self.groups, eps, silu=silu, x1=x1)
-            return L.conv3x3(hh, wgt, bias, residual, halo=self._halo_tma(hh, wgt, kw), **kw)
+            return L.conv3x3(hh, wgt, bias, residual, halo=False if kw.get("shortcut") else self._halo_tma(hh, wgt, kw), **kw)
         have = xs is not None and (x1 is None or x1s is not None)
         halo = self._use_halo(x)
         if have and halo:
@@ -312,6 +319,11 @@ class UNetEngine:
         st1, st2 = {}, {}
         hh = self._gn_conv(x, xs, x1, x1s, r["n1g"], r["n1b"], self.eps, True, r["c1"], temb_all[:, off:],
                            stats=st1 if self.fuse_gn else None, bias_rows=h * wd, bias_stride=self.temb_total)
+        if "c2sc" in r:
+            # out = conv2(h) + conv_shortcut(x ++ x1) as ONE launch (unet.py:483-489)
+            out = self._gn_conv(hh, None, None, None, r["n2g"], r["n2b"], self.eps, True, r["c2sc"], r["c2scb"], None,
+                                shortcut=(x, x1))
+            return out, None
         if "sc" in r:
             res = L.linear(x.reshape(n * h * wd, -1), r["sc"], r["scb"],
                            x1=None if x1 is None else x1.reshape(n * h * wd, -1), static_w=True)

@@ -219,3 +219,23 @@ def test_group_norm_apply_from_producer_statistics(cuda_lib, n, h, w, c0, c1, si
     if silu:
         y = F.silu(y)
     _close(out, y.permute(0, 2, 3, 1), 3e-3, 3e-3, "group_norm_apply")
+
+
+@pytest.mark.parametrize("n,h,w,c,cs0,cs1,co", [(2, 64, 64, 320, 640, 320, 320), (2, 32, 32, 640, 320, 0, 640),
+                                                (2, 16, 16, 1280, 1280, 640, 1280), (2, 8, 8, 1280, 1280, 1280, 1280),
+                                                (1, 24, 40, 64, 96, 32, 64), (4, 64, 64, 64, 72, 0, 640)])
+def test_conv3x3_with_folded_shortcut(cuda_lib, n, h, w, c, cs0, cs1, co):
+    """ResnetBlock2D's tail as ONE launch: conv2(h) + conv_shortcut(x ++ x1) (unet.py:483-489) -- the shortcut's 1x1
+    matrix rides as extra centre-tap k-blocks of the 3x3 convolution (split-K plans and ragged channel chunks included)."""
+    hh = _rand(n, h, w, c, seed=1)
+    s0 = _rand(n, h, w, cs0, seed=2)
+    s1 = _rand(n, h, w, cs1, seed=3) if cs1 else None
+    wt = _rand(co, c, 3, 3, scale=(9 * c) ** -0.5, seed=4)
+    ws = _rand(co, cs0 + cs1, scale=(cs0 + cs1) ** -0.5, seed=5)
+    b = torch.randn(co, device="cuda")
+    wcat = torch.cat([_pack(wt), ws], 1).contiguous()
+    out = cuda_lib.conv3x3(hh, wcat, b, shortcut=(s0, s1))
+    sc_in = s0 if s1 is None else torch.cat([s0, s1], -1)
+    ref = _conv_ref(hh, wt, b) + sc_in.float() @ ws.float().t()
+    _close(out, ref, 4e-3, 3e-3, f"conv + folded shortcut {n}x{h}x{w} {c}+{cs0}+{cs1}->{co}")
+    assert torch.equal(out, cuda_lib.conv3x3(hh, wcat, b, shortcut=(s0, s1)))
