@@ -234,6 +234,28 @@ public:
         if (find(p + ".conv_shortcut.weight")) {
             MODEL_TRY(add_lin(p + ".sc", p + ".conv_shortcut"));
             MODEL_TRY(add_bias(p + ".scb", p + ".conv_shortcut"));
+            if (!fuse_gn) {
+                // the shortcut folded into conv2 (like unet.py of this package): rows [conv2 (9 * Cout) | shortcut (Cin)],
+                // one bias vector for both
+                const Mat& c2 = *mats.at(p + ".c2");
+                const Mat& sc = *mats.at(p + ".sc");
+                auto m = std::make_unique<Mat>();
+                m->n = c2.n, m->k = c2.k + sc.k;
+                m->host.resize(static_cast<size_t>(m->n) * m->k);
+                for (int r = 0; r < m->n; ++r) {
+                    std::copy(c2.host.begin() + static_cast<size_t>(r) * c2.k, c2.host.begin() + static_cast<size_t>(r + 1) * c2.k,
+                              m->host.begin() + static_cast<size_t>(r) * m->k);
+                    std::copy(sc.host.begin() + static_cast<size_t>(r) * sc.k, sc.host.begin() + static_cast<size_t>(r + 1) * sc.k,
+                              m->host.begin() + static_cast<size_t>(r) * m->k + c2.k);
+                }
+                mats[p + ".c2sc"] = std::move(m);
+                const HostTensor *b2, *bs;
+                MODEL_TRY(need(p + ".conv2.bias", &b2));
+                MODEL_TRY(need(p + ".conv_shortcut.bias", &bs));
+                std::vector<float> b(b2->v.size());
+                for (size_t i = 0; i < b.size(); ++i) b[i] = b2->v[i] + bs->v[i];
+                MODEL_TRY(upload_f32(p + ".c2scb", b));
+            }
         }
         return 0;
     }
@@ -399,7 +421,7 @@ public:
 
     // ------------------------------------------------------------------ op wrappers (mirror ml-stable-diffusion_b200/lib.py)
     // weight tile of one call site: [n_tiles][k_blocks][bn][64], k-block order of the kernel's main loop
-    int tiled(Mat& m, int c0, int c1, int taps, int bn, bool chunk_major, void** out) {
+    int tiled(Mat& m, int c0, int c1, int taps, int bn, bool chunk_major, void** out, int c2 = 0, int c3 = 0) {
         const auto key = std::make_pair(bn, chunk_major ? 1 : 0);
         auto it = m.tiled.find(key);
         if (it != m.tiled.end()) {
@@ -409,7 +431,10 @@ public:
         B200SD_REQUIRE(!m.host.empty(), "b200sd_unet: weight tiling requested after the host copy was released");
         const int kpt = c0 + c1, kc0 = (c0 + 63) / 64, kc1 = (c1 + 63) / 64, kc = kc0 + kc1;
         const int nt = (m.n + bn - 1) / bn;
-        std::vector<__half> t(static_cast<size_t>(nt) * taps * kc * bn * 64, __float2half(0.f));
+        const int kc2 = (c2 + 63) / 64, kc3 = (c3 + 63) / 64, kbt = taps * kc + kc2 + kc3;  // (+ folded-shortcut k-blocks)
+        const int ktot = taps * kpt + c2 + c3;
+        B200SD_REQUIRE(ktot == m.k && (c2 + c3 == 0 || !chunk_major), "b200sd_unet: weight matrix / call site mismatch");
+        std::vector<__half> t(static_cast<size_t>(nt) * kbt * bn * 64, __float2half(0.f));
         for (int tile = 0; tile < nt; ++tile)
             for (int tap = 0; tap < taps; ++tap)
                 for (int j = 0; j < kc; ++j) {
@@ -419,11 +444,23 @@ public:
                     for (int r = 0; r < bn; ++r) {
                         const int row = tile * bn + r;
                         if (row >= m.n) break;
-                        const __half* src = m.host.data() + static_cast<size_t>(row) * taps * kpt + static_cast<size_t>(tap) * kpt + lo;
-                        __half* dst = t.data() + ((static_cast<size_t>(tile) * taps * kc + kb) * bn + r) * 64;
+                        const __half* src = m.host.data() + static_cast<size_t>(row) * ktot + static_cast<size_t>(tap) * kpt + lo;
+                        __half* dst = t.data() + ((static_cast<size_t>(tile) * kbt + kb) * bn + r) * 64;
                         std::copy(src, src + (hi - lo), dst);
                     }
                 }
+        for (int tile = 0; tile < nt; ++tile)
+            for (int j = 0; j < kc2 + kc3; ++j) {
+                const int lo = j < kc2 ? j * 64 : c2 + (j - kc2) * 64;
+                const int hi = std::min(lo + 64, j < kc2 ? c2 : c2 + c3);
+                for (int r = 0; r < bn; ++r) {
+                    const int row = tile * bn + r;
+                    if (row >= m.n) break;
+                    const __half* src = m.host.data() + static_cast<size_t>(row) * ktot + static_cast<size_t>(taps) * kpt + lo;
+                    __half* dst = t.data() + ((static_cast<size_t>(tile) * kbt + taps * kc + j) * bn + r) * 64;
+                    std::copy(src, src + (hi - lo), dst);
+                }
+            }
         void* d;
         MODEL_TRY(dev_alloc(&d, t.size() * 2));
         B200SD_CHECK_CUDA(cudaMemcpy(d, t.data(), t.size() * 2, cudaMemcpyHostToDevice));
@@ -473,7 +510,7 @@ public:
             rs->rows = a.rs_out, rs->parts = rs_parts;
         }
         void* wt;
-        MODEL_TRY(tiled(w, a.c0, a.c1, taps, bn, a.halo != 0, &wt));
+        MODEL_TRY(tiled(w, a.c0, a.c1, taps, bn, a.halo != 0, &wt, a.c2, a.c3));
         a.wgt = wt, a.block_n = bn, a.wgt_tiled = 1;
         const size_t ws = b200sd_gemm_workspace_bytes(&a);
         if (ws) {
@@ -504,9 +541,11 @@ public:
 
     int conv(const Act& x, const Act* x1, Mat& w, int cout, const float* bias, int bias_rows, int bias_stride, const __half* residual,
              bool halo, int taps, int stride, bool upsample, const GnSpec* gn, bool want_cs, RowStats* rs, bool out_f32, void* out_override,
-             Act* out) {
+             Act* out, const Act* sc0 = nullptr, const Act* sc1 = nullptr) {
         b200sd_gemm_args a;
         memset(&a, 0, sizeof(a));
+        if (sc0) a.a2 = sc0->p, a.c2 = sc0->c;
+        if (sc1) a.a3 = sc1->p, a.c3 = sc1->c;
         const int h = upsample ? 2 * x.h : x.h, wd = upsample ? 2 * x.w : x.w;
         const int ho = h / stride, wo = wd / stride;
         a.mode = taps == 9 ? 1 : 0, a.m = taps == 1 ? x.n * h * wd : 0, a.n = cout, a.c0 = x.c, a.c1 = x1 ? x1->c : 0;
@@ -545,13 +584,13 @@ public:
     // GroupNorm (+SiLU) -> conv: in the halo convolution's operand path when the producers left statistics behind
     int gn_conv(const Act& x, const Act* x1, const std::string& gkey, const std::string& bkey, float eps, int silu, Mat& w, int cout,
                 const float* bias, int bias_rows, int bias_stride, const __half* residual, bool want_cs, bool out_f32, void* out_override,
-                Act* out) {
+                Act* out, const Act* sc0 = nullptr, const Act* sc1 = nullptr) {
         const float *gamma = vecs.at(gkey), *beta = vecs.at(bkey);
         if (!fuse_gn) {
             Act hn;
             MODEL_TRY(group_norm(x, x1, gamma, beta, eps, silu, &hn));
             return conv(hn, nullptr, w, cout, bias, bias_rows, bias_stride, residual, false, 9, 1, false, nullptr, false, nullptr, out_f32,
-                        out_override, out);
+                        out_override, out, sc0, sc1);
         }
         if (x.chan && (!x1 || x1->chan)) {
             GnSpec g{x.chan, x1 ? x1->chan : nullptr, gamma, beta, cfg.norm_num_groups, eps, silu};
@@ -576,6 +615,9 @@ public:
         Act h1;
         MODEL_TRY(gn_conv(x, x1, p + ".n1g", p + ".n1b", cfg.norm_eps, 1, c1, co, temb + temb_off.at(p), x.h * x.w, temb_total, nullptr, true,
                           false, nullptr, &h1));
+        if (!fuse_gn && mats.count(p + ".c2sc"))  // conv2(h) + conv_shortcut(x ++ x1) as one launch
+            return gn_conv(h1, nullptr, p + ".n2g", p + ".n2b", cfg.norm_eps, 1, *mats.at(p + ".c2sc"), co, vecs.at(p + ".c2scb"), 0, 0, nullptr,
+                           false, false, nullptr, out, &x, x1);
         const __half* res = x.p;
         if (mats.count(p + ".sc")) {
             __half* r;
