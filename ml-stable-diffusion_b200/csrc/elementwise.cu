@@ -119,13 +119,24 @@ __global__ void add_kernel(const __half2* __restrict__ a, const __half2* __restr
 }
 
 // ---- small-M linear: one warp per output column, all M rows at once (M <= 8) -------------------
+// The (optionally SiLU-activated) input rows are staged in shared memory ONCE per block -- every column warp used to
+// re-read and re-activate them (the 20 800-column time-embedding projection was MUFU-bound on 20 800 redundant SiLU
+// passes) -- and a warp requests four weight vectors per lane before the first one is consumed.
 template <int kM>
 __global__ void __launch_bounds__(256) linear_small_kernel(const float* __restrict__ x, const __half* __restrict__ w,
                                                            const float* __restrict__ bias,
                                                            const float* __restrict__ add, float* __restrict__ out,
                                                            int m, int n, int k, int act_in, int act_out) {
+    extern __shared__ __align__(16) float xs[];  // [kM][k]
     pdl_trigger();  // no TMEM / large shared memory here: dependents may start their prologue at once
     pdl_wait();
+    for (int i = threadIdx.x; i < kM * k; i += blockDim.x) {
+        const int r = i / k;
+        float v = r < m ? x[i] : 0.f;
+        if (act_in) v = silu_f(v);
+        xs[i] = v;
+    }
+    __syncthreads();
     const int col = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (col >= n) return;
@@ -133,26 +144,32 @@ __global__ void __launch_bounds__(256) linear_small_kernel(const float* __restri
     float acc[kM];
 #pragma unroll
     for (int r = 0; r < kM; ++r) acc[r] = 0.f;
-    for (int kk = lane * 8; kk < k; kk += 32 * 8) {
-        const uint4 raw = *reinterpret_cast<const uint4*>(wr + kk);
-        const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
-        float wf[8];
+    constexpr int kInFlight = 4;
+    for (int kb = lane * 8; kb < k; kb += 32 * 8 * kInFlight) {
+        uint4 raw[kInFlight];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const float2 t = __half22float2(h2[q]);
-            wf[2 * q] = t.x;
-            wf[2 * q + 1] = t.y;
+        for (int i = 0; i < kInFlight; ++i) {
+            const int kk = kb + i * 256;
+            raw[i] = kk < k ? __ldg(reinterpret_cast<const uint4*>(wr + kk)) : make_uint4(0, 0, 0, 0);
         }
 #pragma unroll
-        for (int r = 0; r < kM; ++r) {
-            if (r < m) {
-                const float* xr = x + static_cast<size_t>(r) * k + kk;
+        for (int i = 0; i < kInFlight; ++i) {
+            const int kk = kb + i * 256;
+            if (kk >= k) break;
+            const __half2* h2 = reinterpret_cast<const __half2*>(&raw[i]);
+            float wf[8];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    float xv = xr[e];
-                    if (act_in) xv = silu_f(xv);
-                    acc[r] += xv * wf[e];
-                }
+            for (int q = 0; q < 4; ++q) {
+                const float2 t = __half22float2(h2[q]);
+                wf[2 * q] = t.x;
+                wf[2 * q + 1] = t.y;
+            }
+#pragma unroll
+            for (int r = 0; r < kM; ++r) {
+                const float4 x0 = *reinterpret_cast<const float4*>(xs + r * k + kk);
+                const float4 x1 = *reinterpret_cast<const float4*>(xs + r * k + kk + 4);
+                acc[r] += x0.x * wf[0] + x0.y * wf[1] + x0.z * wf[2] + x0.w * wf[3] + x1.x * wf[4] + x1.y * wf[5] + x1.z * wf[6] +
+                          x1.w * wf[7];
             }
         }
     }
@@ -392,10 +409,18 @@ extern "C" int b200sd_linear_small(const float* x, const void* wgt, const float*
         const int mm = std::min(8, m - r0);
         const float* xr = x + static_cast<size_t>(r0) * k;
         float* orow = out + static_cast<size_t>(r0) * n;
+        const size_t smem = static_cast<size_t>(mm <= 2 ? 2 : 8) * k * sizeof(float);
+        B200SD_REQUIRE(smem <= 160 * 1024, "b200sd_linear_small: k = %d too large for the staged input rows", k);
+        static bool attr = false;
+        if (!attr) {
+            B200SD_CHECK_CUDA(cudaFuncSetAttribute(linear_small_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+            B200SD_CHECK_CUDA(cudaFuncSetAttribute(linear_small_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+            attr = true;
+        }
         if (mm <= 2)
-            B200SD_CHECK_CUDA(launch_kernel(linear_small_kernel<2>, dim3(blocks), dim3(256), 0, stream, xr, w, bias, add, orow, mm, n, k, act_in, act_out));
+            B200SD_CHECK_CUDA(launch_kernel(linear_small_kernel<2>, dim3(blocks), dim3(256), smem, stream, xr, w, bias, add, orow, mm, n, k, act_in, act_out));
         else
-            B200SD_CHECK_CUDA(launch_kernel(linear_small_kernel<8>, dim3(blocks), dim3(256), 0, stream, xr, w, bias, add, orow, mm, n, k, act_in, act_out));
+            B200SD_CHECK_CUDA(launch_kernel(linear_small_kernel<8>, dim3(blocks), dim3(256), smem, stream, xr, w, bias, add, orow, mm, n, k, act_in, act_out));
         B200SD_CHECK_CUDA(cudaGetLastError());
         count_launch(1);
     }
